@@ -85,7 +85,8 @@ int orc_potrf_lower(int64_t n, double *a)
 }
 
 /* pc_chols.c:220-260: trsv("L","N","N") forward / trsv("L","T","N") backward, in place.
- * Dot-product (row-oriented) form for N, and for T the equivalent column walk of L. */
+ * Accumulation order per unknown follows reference-BLAS dtrsv: forward x_i collects k = 0..i-1
+ * ascending; transposed x_i collects k = n-1..i+1 descending (dtrsv 'T' loop "DO I = N,J+1,-1"). */
 void orc_trsv_lower(int64_t n, const double *l, int trans, double *x)
 {
   if (!trans) {
@@ -97,7 +98,7 @@ void orc_trsv_lower(int64_t n, const double *l, int trans, double *x)
   } else {
     for (int64_t i = n - 1; i >= 0; --i) {
       double s = x[i];
-      for (int64_t k = i + 1; k < n; ++k) s = fma(-l[k + i * n], x[k], s);
+      for (int64_t k = n - 1; k > i; --k) s = fma(-l[k + i * n], x[k], s);
       x[i] = s / l[i + i * n];
     }
   }

@@ -1,0 +1,130 @@
+// chol.cu -- dense Cholesky sampler on the device: the PCCHOLSAMPLER analogue for the coarsest level.
+//
+// Reference: src/pc_chols.c:173-195 (dense potrf "L" once), :220-260 (trsv "L","N" / "L","T"),
+// :284-287 (v = L^-1 b; v += z; y = L^-T v  =>  y ~ N(A^-1 b, A^-1)), :306-336 (cached forward solve).
+// The factor is computed once on the host at set-up (not on the per-sample path) and kept on the
+// device as L and L^T (both column-major, so every per-step access is a coalesced column read).
+// One CTA does both triangular solves of a sample from shared memory; per unknown the accumulation
+// order is reference-BLAS dtrsv's (forward k ascending, transposed k descending), so the result is
+// bit-identical to the sequential substitution.
+#include "common.hpp"
+#include "philox.cuh"
+
+namespace {
+constexpr int CHOL_MAX_N   = 4096;
+constexpr int CHOL_THREADS = 1024;
+
+// s[0..n) holds the rhs on entry and the solution on exit
+__device__ void trsv_forward(int n, const double *__restrict__ L, double *s)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int kb = 0; kb < n; kb += 32) {
+    if (warp == 0) {
+      const int i  = kb + lane;
+      double    si = i < n ? s[i] : 0.0;
+      const int kmax = min(32, n - kb);
+      for (int k = 0; k < kmax; ++k) {
+        const int kk = kb + k;
+        double    xk = 0.0;
+        if (lane == k) xk = si / L[kk + (size_t)kk * n];
+        xk = __shfl_sync(0xffffffffu, xk, k);
+        if (lane == k) si = xk;
+        else if (lane > k && i < n) si = fma(-L[i + (size_t)kk * n], xk, si);
+      }
+      if (i < n) s[i] = si;
+    }
+    __syncthreads();
+    const int kmax = min(32, n - kb);
+    for (int i = kb + 32 + tid; i < n; i += blockDim.x) {
+      double si = s[i];
+      for (int k = 0; k < kmax; ++k) si = fma(-L[i + (size_t)(kb + k) * n], s[kb + k], si);
+      s[i] = si;
+    }
+    __syncthreads();
+  }
+}
+
+// LT[i + k n] = L[k + i n]
+__device__ void trsv_backward(int n, const double *__restrict__ L, const double *__restrict__ LT, double *s)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = (n + 31) / 32;
+  for (int blk = nb - 1; blk >= 0; --blk) {
+    const int kb = blk * 32, kmax = min(32, n - kb);
+    if (warp == 0) {
+      const int i  = kb + lane;
+      double    si = i < n ? s[i] : 0.0;
+      for (int k = kmax - 1; k >= 0; --k) {
+        const int kk = kb + k;
+        double    xk = 0.0;
+        if (lane == k) xk = si / L[kk + (size_t)kk * n];
+        xk = __shfl_sync(0xffffffffu, xk, k);
+        if (lane == k) si = xk;
+        else if (lane < k) si = fma(-LT[i + (size_t)kk * n], xk, si);
+      }
+      if (i < n) s[i] = si;
+    }
+    __syncthreads();
+    for (int i = tid; i < kb; i += blockDim.x) {
+      double si = s[i];
+      for (int k = kmax - 1; k >= 0; --k) si = fma(-LT[i + (size_t)(kb + k) * n], s[kb + k], si);
+      s[i] = si;
+    }
+    __syncthreads();
+  }
+}
+
+// mode bit 0: forward solve of `in`; bit 1: add noise and backward solve
+__global__ void __launch_bounds__(CHOL_THREADS) chol_sample_kernel(int n, const double *__restrict__ L, const double *__restrict__ LT, const double *__restrict__ in, double *__restrict__ out, NoiseArgs na, int mode)
+{
+  __shared__ double s[CHOL_MAX_N];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = in[i];
+  __syncthreads();
+  if (mode & 1) trsv_forward(n, L, s);
+  if (mode & 2) {
+    if (na.mode != PMG_NOISE_NONE)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = __dadd_rn(s[i], noise_value(na, i));
+    __syncthreads();
+    trsv_backward(n, L, LT, s);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = s[i];
+}
+} // namespace
+
+int CholSampler::setup(pmg_ctx c, const HostCsr &a)
+{
+  ctx = c;
+  n   = a.n;
+  if (n > CHOL_MAX_N) PMG_FAIL(PMG_ERR_SUP, "coarsest operator has %lld rows; the dense device Cholesky sampler handles up to %d (use more levels)", (long long)n, CHOL_MAX_N);
+  std::vector<double> l((size_t)(n * n), 0.0), lt((size_t)(n * n), 0.0);
+  for (int64_t r = 0; r < n; ++r)
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) l[(size_t)(r + (int64_t)a.col[k] * n)] = a.val[k];
+  const int info = host_potrf_lower(n, l);
+  if (info) PMG_FAIL(PMG_ERR_NOT_SPD, "Dense Cholesky failed: leading minor of order %d is not positive definite", info); // src/pc_chols.c:192
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t k = 0; k < n; ++k) {
+      if (k > i) l[(size_t)(i + k * n)] = 0.0; // strictly upper part of the potrf workspace is not referenced
+      lt[(size_t)(i + k * n)] = k >= i ? l[(size_t)(k + i * n)] : 0.0;
+    }
+  PMG_TRY(L.upload(l, ctx->stream));
+  PMG_TRY(LT.upload(lt, ctx->stream));
+  PMG_TRY(vcache.alloc((size_t)n));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int launch_chol(pmg_ctx ctx, int64_t n, const double *L, const double *LT, const double *in, double *out, const NoiseArgs &na, int mode)
+{
+  chol_sample_kernel<<<1, CHOL_THREADS, 0, ctx->stream>>>((int)n, L, LT, in, out, na, mode);
+  PMG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int CholSampler::sample(const double *b, double *y, const NoiseArgs &na) { return launch_chol(ctx, n, L.p, LT.p, b, y, na, 3); }
+int CholSampler::forward(const double *b, double *v)
+{
+  NoiseArgs none{PMG_NOISE_NONE, nullptr, 0, 0, 0};
+  return launch_chol(ctx, n, L.p, LT.p, b, v, none, 1);
+}
+int CholSampler::backward_noise(const double *v, double *y, const NoiseArgs &na) { return launch_chol(ctx, n, L.p, LT.p, v, y, na, 2); }

@@ -1,0 +1,213 @@
+// common.hpp -- internal types of the B200 sampling library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/parmgmc_b200.h"
+
+void pmg_set_error(const char *fmt, ...);
+
+#define PMG_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      pmg_set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e_));      \
+      return PMG_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define PMG_TRY(call)          \
+  do {                         \
+    int rc_ = (call);          \
+    if (rc_) return rc_;       \
+  } while (0)
+
+#define PMG_FAIL(code, ...)    \
+  do {                         \
+    pmg_set_error(__VA_ARGS__); \
+    return (code);             \
+  } while (0)
+
+// device buffer
+template <class T> struct DevBuf {
+  T     *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n)
+  {
+    o.p = nullptr;
+    o.n = 0;
+  }
+  DevBuf &operator=(DevBuf &&o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p   = o.p;
+      n   = o.n;
+      o.p = nullptr;
+      o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count)
+  {
+    if (count == n && p) return 0;
+    release();
+    if (count == 0) return 0;
+    PMG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+    return 0;
+  }
+  int zero(cudaStream_t s)
+  {
+    if (n) PMG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    return 0;
+  }
+  int upload(const T *h, size_t count, cudaStream_t s)
+  {
+    PMG_TRY(alloc(count));
+    if (count) PMG_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  int upload(const std::vector<T> &h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+};
+
+struct pmg_ctx_s {
+  int          device     = 0;
+  cudaStream_t stream     = nullptr;
+  bool         own_stream = false;
+  int          sm_count   = 148;
+  uint64_t     seed       = 0xCAFE; // examples/ex6.c:131
+  uint64_t     draws      = 0;      // global draw (fill) counter: the "position" in the reference's single stream
+  void        *nccl_comm  = nullptr;
+  int          rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;
+  // measurement
+  int64_t launches = 0, dof_updates = 0;
+};
+
+// One N(0,1) block: what a single VecSetRandomStandardNormal call (src/parmgmc.c:70-116) produces.
+struct NoiseArgs {
+  int           mode; // PMG_NOISE_*
+  const double *tape; // device pointer to this block (injected mode), indexed by local row
+  uint64_t      seed, call;
+  int64_t       row0; // global index of local row 0
+};
+
+// The global noise stream of one top-level sampler call (SURVEY F7 / 8(c) tape contract).
+struct NoiseStream {
+  int            mode = PMG_NOISE_PHILOX;
+  DevBuf<double> tape;
+  int64_t        tape_len = 0, tape_pos = 0;
+  // next block of n local rows
+  int next(pmg_ctx ctx, int64_t n, int64_t row0, NoiseArgs &na)
+  {
+    na.mode = mode;
+    na.tape = nullptr;
+    na.seed = ctx->seed;
+    na.call = ctx->draws;
+    na.row0 = row0;
+    if (mode == PMG_NOISE_INJECTED) {
+      if (tape_pos + n > tape_len) PMG_FAIL(PMG_ERR_NOISE, "injected noise tape exhausted: need %lld more values at position %lld of %lld", (long long)n, (long long)tape_pos, (long long)tape_len);
+      na.tape = tape.p + tape_pos;
+      tape_pos += n;
+    }
+    if (mode != PMG_NOISE_NONE) ctx->draws++;
+    return 0;
+  }
+};
+
+// host CSR (set-up only)
+struct HostCsr {
+  int64_t              n = 0, m = 0;
+  std::vector<int64_t> rowptr;
+  std::vector<int32_t> col;
+  std::vector<double>  val;
+  int64_t nnz() const { return rowptr.empty() ? 0 : rowptr.back(); }
+};
+
+// omega-dependent per-row coefficients of a sweep (src/mc_sor.c:114-124, src/pc_mcgibbs.c:142-153)
+struct SweepCoeffs {
+  double         omega = -1;
+  DevBuf<double> idiag, sqrtdiag; // layout is private to the operator that made them
+};
+
+// An operator on one level on one device.
+struct LevelOp {
+  pmg_ctx ctx = nullptr;
+  virtual ~LevelOp() {}
+  virtual int64_t n() const    = 0; // local rows
+  virtual int64_t nglobal() const { return n(); }
+  virtual int64_t row0() const { return 0; }
+  virtual int     ncolors() const                                  = 0;
+  virtual int     make_coeffs(double omega, SweepCoeffs &c)        = 0;
+  // one directional multicolour sweep of src/mc_sor.c:241-296 on  w = b + sqrtdiag*z  (src/pc_mcgibbs.c:119-128),
+  // w never materialised; dir is PMG_SOR_FORWARD_SWEEP or PMG_SOR_BACKWARD_SWEEP; b may be null (b = 0)
+  virtual int sweep(int dir, const SweepCoeffs &c, const double *b, double *y, const NoiseArgs &na) = 0;
+  virtual int residual(const double *b, const double *x, double *r) = 0; // r = b - A x
+  virtual int mult(const double *x, double *y)                      = 0; // y = A x
+  virtual const HostCsr *host_csr() { return nullptr; }             // assembled form for set-up, if any
+  virtual int  get_coloring(std::vector<int32_t> &color) = 0;
+  virtual int  set_coloring(int ncolors, const int32_t *color) = 0;
+  virtual int  set_coloring_auto(int policy) = 0;
+  virtual void describe(std::string &out) = 0;
+  virtual bool structured(int &dim, int64_t dims[3]) const { (void)dim; (void)dims; return false; }
+};
+
+// grid transfer between level l (fine) and l-1 (coarse): SURVEY Appendix A.3
+struct Transfer {
+  virtual ~Transfer() {}
+  virtual int restrict_to(const double *r_fine, double *b_coarse) = 0; // b_c = P^T r
+  virtual int prolong_add(const double *x_coarse, double *x_fine) = 0; // x_f += P x_c
+};
+
+struct pmg_mat_s {
+  pmg_ctx                  ctx = nullptr;
+  std::unique_ptr<LevelOp> op;
+};
+
+// host-side sparse helpers (host_sparse.cpp)
+void host_transpose(const HostCsr &a, HostCsr &t);
+void host_matmul(const HostCsr &a, const HostCsr &b, HostCsr &c);
+void host_q1_dims(int dim, const int64_t nf[3], int64_t nc[3]);
+void host_q1_interp(int dim, const int64_t nf[3], const int64_t nc[3], HostCsr &p);
+int  host_coloring_greedy(const HostCsr &a, std::vector<int32_t> &color);
+int  host_coloring_levelset(const HostCsr &a, std::vector<int32_t> &color);
+int64_t host_coloring_violations(const HostCsr &a, const std::vector<int32_t> &color);
+int  host_potrf_lower(int64_t n, std::vector<double> &a);
+
+// factories
+int make_csr_op(pmg_ctx ctx, HostCsr &&a, std::unique_ptr<LevelOp> &op);
+int make_csr_grid_op(pmg_ctx ctx, HostCsr &&a, int dim, const int64_t dims[3], std::unique_ptr<LevelOp> &op); // CSR with known grid
+int make_csr_transfer(pmg_ctx ctx, const HostCsr &p, std::unique_ptr<Transfer> &t);
+
+// dense Cholesky sampler (chol.cu): src/pc_chols.c
+struct CholSampler {
+  pmg_ctx        ctx = nullptr;
+  int64_t        n   = 0;
+  DevBuf<double> L, LT, vcache;
+  int setup(pmg_ctx ctx, const HostCsr &a);
+  // y = L^-T (L^-1 b + z)
+  int sample(const double *b, double *y, const NoiseArgs &na);
+  int forward(const double *b, double *v);                      // v = L^-1 b
+  int backward_noise(const double *v, double *y, const NoiseArgs &na); // y = L^-T (v + z)
+};
+
+int launch_normal_fill(pmg_ctx ctx, const NoiseArgs &na, int64_t n, double *z_dev);
+int launch_axpy(pmg_ctx ctx, int64_t n, double a, const double *x, double *y); // y += a x

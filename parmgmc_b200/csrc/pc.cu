@@ -1,0 +1,941 @@
+// pc.cu -- the C ABI: context, operators, MCSOR engine and the four sampler "PC" types.
+//
+// Mirrors the reference's plugin surface:
+//   src/parmgmc.c      ParMGMCInitialize / global RNG / PCSetSampleCallback  -> pmg_ctx_*, pmg_pc_set_sample_callback
+//   src/mc_sor.c       MCSOR*                                                 -> pmg_mcsor_*
+//   src/pc_mcgibbs.c   PCMCGIBBS                                              -> pmg_pc type "mcgibbs"
+//   src/pc_sorgibbs.c  PCSORGIBBS                                             -> pmg_pc type "sorgibbs"
+//   src/pc_gamgmc.c    PCGAMGMC (+ PETSc PCMG cycle)     -> pmg_pc type "gamgmc"
+//   src/pc_chols.c     PCCHOLSAMPLER                                          -> pmg_pc type "cholsampler"
+#include <cmath>
+#include <cstdlib>
+#include <map>
+
+#include "common.hpp"
+
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+void pmg_set_error(const char *fmt, ...)
+{
+  char    buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op);
+int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine, int nlevels, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers);
+
+extern "C" {
+
+const char *pmg_version(void) { return "parmgmc_b200 0.1 (sm_100a)"; }
+const char *pmg_last_error(void) { return g_error.c_str(); }
+
+int pmg_device_count(int *count)
+{
+  int         n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return PMG_OK;
+}
+
+int pmg_ctx_create(int device, pmg_ctx *out)
+{
+  int n = 0;
+  pmg_device_count(&n);
+  if (n == 0) PMG_FAIL(PMG_ERR_NO_DEVICE, "no CUDA device visible: parmgmc_b200 has no CPU fallback");
+  if (device < 0 || device >= n) PMG_FAIL(PMG_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  PMG_CUDA(cudaSetDevice(device));
+  auto *ctx   = new pmg_ctx_s();
+  ctx->device = device;
+  PMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  cudaDeviceProp prop;
+  PMG_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  *out          = ctx;
+  return PMG_OK;
+}
+
+int pmg_ctx_destroy(pmg_ctx ctx)
+{
+  if (!ctx) return PMG_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  return PMG_OK;
+}
+
+int pmg_ctx_set_stream(pmg_ctx ctx, void *s)
+{
+  if (ctx->own_stream && ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  ctx->stream     = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return PMG_OK;
+}
+
+int pmg_ctx_synchronize(pmg_ctx ctx)
+{
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+int pmg_ctx_set_seed(pmg_ctx ctx, uint64_t seed)
+{
+  ctx->seed  = seed;
+  ctx->draws = 0;
+  return PMG_OK;
+}
+int pmg_ctx_get_draw_counter(pmg_ctx ctx, uint64_t *d)
+{
+  *d = ctx->draws;
+  return PMG_OK;
+}
+int pmg_ctx_set_draw_counter(pmg_ctx ctx, uint64_t d)
+{
+  ctx->draws = d;
+  return PMG_OK;
+}
+
+// ---- operators --------------------------------------------------------------------------------------
+int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr, const int32_t *col, const double *val, pmg_mat *out)
+{
+  if (!ctx || !rowptr || !col || !val || n <= 0) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_csr: bad arguments");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  HostCsr a;
+  a.n = a.m = n;
+  a.rowptr.assign(rowptr, rowptr + n + 1);
+  if (a.rowptr[0] != 0) PMG_FAIL(PMG_ERR_ARG, "rowptr[0] must be 0");
+  a.col.assign(col, col + a.rowptr[n]);
+  a.val.assign(val, val + a.rowptr[n]);
+  auto m = std::make_unique<pmg_mat_s>();
+  m->ctx = ctx;
+  PMG_TRY(make_csr_op(ctx, std::move(a), m->op));
+  *out = m.release();
+  return PMG_OK;
+}
+
+int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, pmg_mat *out)
+{
+  if (!ctx || (dim != 2 && dim != 3) || nx < 2 || ny < 1) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_laplace: bad arguments");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  auto m = std::make_unique<pmg_mat_s>();
+  m->ctx = ctx;
+  PMG_TRY(make_laplace_op(ctx, dim, nx, ny, dim == 3 ? nz : 1, kappa, slab_lo, slab_hi, m->op));
+  *out = m.release();
+  return PMG_OK;
+}
+
+int pmg_mat_destroy(pmg_mat m)
+{
+  if (m) {
+    cudaSetDevice(m->ctx->device);
+    delete m;
+  }
+  return PMG_OK;
+}
+
+int pmg_mat_get_size(pmg_mat m, int64_t *nl, int64_t *ng, int64_t *r0)
+{
+  if (nl) *nl = m->op->n();
+  if (ng) *ng = m->op->nglobal();
+  if (r0) *r0 = m->op->row0();
+  return PMG_OK;
+}
+
+int pmg_mat_set_coloring(pmg_mat m, int ncolors, const int32_t *color)
+{
+  PMG_CUDA(cudaSetDevice(m->ctx->device));
+  return m->op->set_coloring(ncolors, color);
+}
+int pmg_mat_set_coloring_auto(pmg_mat m, int policy)
+{
+  PMG_CUDA(cudaSetDevice(m->ctx->device));
+  return m->op->set_coloring_auto(policy);
+}
+int pmg_mat_get_coloring(pmg_mat m, int *ncolors, int32_t *color)
+{
+  if (ncolors) *ncolors = m->op->ncolors();
+  if (color) {
+    std::vector<int32_t> c;
+    PMG_TRY(m->op->get_coloring(c));
+    std::memcpy(color, c.data(), c.size() * sizeof(int32_t));
+  }
+  return PMG_OK;
+}
+
+int pmg_mat_mult(pmg_mat m, const double *x, double *y)
+{
+  pmg_ctx ctx = m->ctx;
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  const int64_t  n = m->op->n();
+  DevBuf<double> dx, dy;
+  PMG_TRY(dx.upload(x, (size_t)n, ctx->stream));
+  PMG_TRY(dy.alloc((size_t)n));
+  PMG_TRY(m->op->mult(dx.p, dy.p));
+  PMG_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// One Gibbs / SOR sampler on one operator: the body of PCApplyRichardson_MulticolorGibbs's loop
+// (src/pc_mcgibbs.c:168-182) == PCSORGibbsSample (src/pc_sorgibbs.c:76-103) for omega = 1, forward.
+struct GibbsCore {
+  LevelOp    *op = nullptr;
+  SweepCoeffs coeffs;
+  double      omega = 1.0;
+  int         type  = PMG_SOR_FORWARD_SWEEP;
+
+  int ensure()
+  {
+    if (coeffs.omega != omega) PMG_TRY(op->make_coeffs(omega, coeffs)); // omega_changed, src/pc_mcgibbs.c:165
+    return 0;
+  }
+  int sample(NoiseStream &ns, const double *b, double *y)
+  {
+    PMG_TRY(ensure());
+    NoiseArgs na;
+    if (type == PMG_SOR_SYMMETRIC_SWEEP) { // forward with fresh noise, then backward with fresh noise (:172-182)
+      PMG_TRY(ns.next(op->ctx, op->n(), op->row0(), na));
+      PMG_TRY(op->sweep(PMG_SOR_FORWARD_SWEEP, coeffs, b, y, na));
+      PMG_TRY(ns.next(op->ctx, op->n(), op->row0(), na));
+      PMG_TRY(op->sweep(PMG_SOR_BACKWARD_SWEEP, coeffs, b, y, na));
+    } else {
+      const int dir = type == PMG_SOR_BACKWARD_SWEEP ? PMG_SOR_BACKWARD_SWEEP : PMG_SOR_FORWARD_SWEEP;
+      PMG_TRY(ns.next(op->ctx, op->n(), op->row0(), na));
+      PMG_TRY(op->sweep(dir, coeffs, b, y, na));
+    }
+    return 0;
+  }
+  int64_t draws_per_sample() const { return (type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) * op->n(); }
+};
+
+struct pmg_mcsor_s {
+  pmg_mat        mat;
+  GibbsCore      core;
+  NoiseStream    none;
+  DevBuf<double> b, y;
+};
+
+enum { KIND_SORGIBBS = 0, KIND_MCGIBBS = 1, KIND_CHOL = 2 };
+
+struct LevelSampler {
+  int         kind = KIND_SORGIBBS;
+  int         its  = 1;
+  GibbsCore   gibbs;
+  CholSampler chol;
+};
+
+struct MgLevel {
+  LevelOp                  *op = nullptr;
+  std::unique_ptr<LevelOp>  owned;
+  std::unique_ptr<Transfer> P; // between this level and the next coarser one
+  HostCsr                   interp;
+  bool                      has_interp = false;
+  LevelSampler              smp;
+  DevBuf<double>            b, x, r;
+};
+
+struct pmg_pc_s {
+  pmg_ctx                            ctx = nullptr;
+  std::string                        type;
+  pmg_mat                            mat = nullptr;
+  std::map<std::string, std::string> opts;
+  bool                               is_setup = false;
+  NoiseStream                        noise;
+  pmg_sample_cb                      cb      = nullptr;
+  void                              *cbctx   = nullptr;
+  pmg_ctx_deleter                    deleter = nullptr;
+  int64_t                            sample_index = 0;
+  LevelSampler                       smp; // mcgibbs / sorgibbs / cholsampler
+  // gamgmc
+  int                  nlevels = 0;
+  std::vector<MgLevel> lv;
+  DevBuf<double>       w, work;
+  // staging
+  DevBuf<double> d_b, d_y;
+  double        *h_pinned = nullptr;
+  cudaEvent_t    ev0 = nullptr, ev1 = nullptr;
+  double         last_ms = 0;
+  int64_t        last_launches = 0, last_updates = 0;
+
+  ~pmg_pc_s()
+  {
+    if (deleter) deleter(cbctx);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+  bool        has(const std::string &k) const { return opts.count(k) != 0; }
+  std::string get(const std::string &k, const std::string &d) const
+  {
+    auto it = opts.find(k);
+    return it == opts.end() ? d : it->second;
+  }
+};
+
+static bool opt_true(const std::string &v) { return v.empty() || v == "1" || v == "true" || v == "yes" || v == "on" || v == "TRUE"; }
+
+// PCSetFromOptions_MulticolorGibbs (src/pc_mcgibbs.c:190-211) / _SORGibbs (src/pc_sorgibbs.c:264-278) for the
+// sampler configured under `prefix` ("" for a stand-alone PC, "gamgmc_mg_levels_" / "gamgmc_mg_coarse_" inside MG)
+static int configure_sampler(pmg_pc pc, const std::string &prefix, const std::string &pctype, LevelSampler &s)
+{
+  if (pctype == "mcgibbs") {
+    s.kind = KIND_MCGIBBS;
+    if (pc->has(prefix + "pc_mcgibbs_omega")) s.gibbs.omega = std::atof(pc->get(prefix + "pc_mcgibbs_omega", "1").c_str());
+    if (!(s.gibbs.omega > 0 && s.gibbs.omega < 2)) PMG_FAIL(PMG_ERR_ARG, "-%spc_mcgibbs_omega must be in (0,2)", prefix.c_str());
+    if (pc->has(prefix + "pc_mcgibbs_forward") && opt_true(pc->get(prefix + "pc_mcgibbs_forward", ""))) s.gibbs.type = PMG_SOR_FORWARD_SWEEP;
+    if (pc->has(prefix + "pc_mcgibbs_backward") && opt_true(pc->get(prefix + "pc_mcgibbs_backward", ""))) s.gibbs.type = PMG_SOR_BACKWARD_SWEEP;
+    if (pc->has(prefix + "pc_mcgibbs_symmetric") && opt_true(pc->get(prefix + "pc_mcgibbs_symmetric", ""))) s.gibbs.type = PMG_SOR_SYMMETRIC_SWEEP;
+  } else if (pctype == "sorgibbs") {
+    s.kind        = KIND_SORGIBBS;
+    s.gibbs.omega = 1.0; // no omega option
+    s.gibbs.type  = PMG_SOR_FORWARD_SWEEP; // forward and local_forward coincide on one device
+  } else if (pctype == "cholsampler") {
+    s.kind = KIND_CHOL;
+  } else PMG_FAIL(PMG_ERR_SUP, "sampler type '%s' is not supported (mcgibbs | sorgibbs | cholsampler)", pctype.c_str());
+  return 0;
+}
+
+static int apply_coloring_policy(pmg_pc pc, LevelOp *op, bool is_user_mat)
+{
+  const std::string p = pc->get("pc_b200_coloring", "");
+  if (p.empty() || p == "keep") return 0; // user matrices keep whatever colouring they carry
+  (void)is_user_mat;
+  if (p == "greedy") return op->set_coloring_auto(PMG_COLORING_GREEDY);
+  if (p == "lexicographic") return op->set_coloring_auto(PMG_COLORING_LEXICOGRAPHIC);
+  if (p == "parity") return op->set_coloring_auto(PMG_COLORING_PARITY);
+  PMG_FAIL(PMG_ERR_ARG, "-pc_b200_coloring %s: expected greedy | lexicographic | parity | keep", p.c_str());
+}
+
+static int setup_level_sampler(pmg_ctx ctx, LevelSampler &s, LevelOp *op)
+{
+  if (s.kind == KIND_CHOL) {
+    const HostCsr *a = op->host_csr();
+    if (!a) PMG_FAIL(PMG_ERR_SUP, "cholsampler needs an assembled operator");
+    return s.chol.setup(ctx, *a);
+  }
+  s.gibbs.op = op;
+  return s.gibbs.ensure();
+}
+
+// KSP(richardson, max_it = its) around a level sampler.  Continues from x (the reference samplers ignore
+// guesszero, src/pc_sorgibbs.c:94 / src/pc_mcgibbs.c:170).
+static int run_level_sampler(pmg_pc pc, LevelSampler &s, const double *b, double *x)
+{
+  if (s.kind == KIND_CHOL) {
+    NoiseArgs na;
+    if (s.its == 1) { // src/pc_chols.c:303-304 -> PCApply_CholSampler :262-291
+      PMG_TRY(pc->noise.next(pc->ctx, s.chol.n, 0, na));
+      return s.chol.sample(b, x, na);
+    }
+    PMG_TRY(s.chol.forward(b, s.chol.vcache.p)); // forward solve cached (:306-336)
+    for (int it = 0; it < s.its; ++it) {
+      PMG_TRY(pc->noise.next(pc->ctx, s.chol.n, 0, na));
+      PMG_TRY(s.chol.backward_noise(s.chol.vcache.p, x, na));
+    }
+    return 0;
+  }
+  for (int it = 0; it < s.its; ++it) PMG_TRY(s.gibbs.sample(pc->noise, b, x));
+  return 0;
+}
+
+static int64_t sampler_draws(const LevelSampler &s)
+{
+  if (s.kind == KIND_CHOL) return s.its * s.chol.n;
+  return s.its * s.gibbs.draws_per_sample();
+}
+
+// PCMGMCycle_Private, V-cycle
+static int mg_cycle(pmg_pc pc, int l, const double *b, double *x)
+{
+  MgLevel &v = pc->lv[l];
+  PMG_TRY(run_level_sampler(pc, v.smp, b, x));
+  if (l == 0) return 0;
+  MgLevel &c = pc->lv[l - 1];
+  PMG_TRY(v.op->residual(b, x, v.r.p));
+  PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+  PMG_TRY(c.x.zero(pc->ctx->stream));
+  PMG_TRY(mg_cycle(pc, l - 1, c.b.p, c.x.p));
+  PMG_TRY(v.P->prolong_add(c.x.p, x));
+  return run_level_sampler(pc, v.smp, b, x);
+}
+
+// PCApply_MG: x = 0, one cycle
+static int mg_apply(pmg_pc pc, const double *b, double *x)
+{
+  const int64_t n = pc->lv[pc->nlevels - 1].op->n();
+  PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), pc->ctx->stream));
+  return mg_cycle(pc, pc->nlevels - 1, b, x);
+}
+
+static int gamgmc_setup(pmg_pc pc)
+{
+  pmg_ctx  ctx  = pc->ctx;
+  LevelOp *fine = pc->mat->op.get();
+  // -pc_gamgmc_mg_type (src/pc_gamgmc.c:364): only the geometric hierarchy can be built without PETSc's GAMG
+  const std::string mgtype = pc->get("pc_gamgmc_mg_type", "mg");
+  bool              user_p = false;
+  for (auto &l : pc->lv) user_p |= l.has_interp;
+  if (mgtype != "mg" && !user_p) PMG_FAIL(PMG_ERR_SUP, "-pc_gamgmc_mg_type %s: algebraic (GAMG) coarsening is PETSc-internal and not reproduced; use 'mg' on a structured operator or supply interpolations", mgtype.c_str());
+  int L = pc->nlevels;
+  if (pc->has("gamgmc_pc_mg_levels")) L = std::atoi(pc->get("gamgmc_pc_mg_levels", "0").c_str());
+  int     dim = 0;
+  int64_t dims[3] = {0, 0, 0};
+  const bool structured = fine->structured(dim, dims);
+  if (L <= 0) { // automatic depth: coarsen until the coarsest grid is at most 17 nodes per direction
+    if (!structured) PMG_FAIL(PMG_ERR_ORDER, "gamgmc: set the number of levels (-gamgmc_pc_mg_levels / pmg_pc_gamgmc_set_levels)");
+    L = 1;
+    int64_t d[3] = {dims[0], dims[1], dims[2]};
+    while (std::max(d[0], std::max(d[1], d[2])) > 17 && L < 30) {
+      int64_t c[3];
+      host_q1_dims(dim, d, c);
+      std::memcpy(d, c, sizeof d);
+      ++L;
+    }
+  }
+  if (L < 1) PMG_FAIL(PMG_ERR_ARG, "gamgmc: need at least one level");
+  std::vector<MgLevel> old = std::move(pc->lv);
+  pc->lv.clear();
+  pc->lv.resize((size_t)L);
+  for (int l = 0; l < L && l < (int)old.size(); ++l)
+    if (old[l].has_interp) {
+      pc->lv[l].interp     = std::move(old[l].interp);
+      pc->lv[l].has_interp = true;
+    }
+  pc->nlevels      = L;
+  pc->lv[L - 1].op = fine;
+  PMG_TRY(apply_coloring_policy(pc, fine, true));
+
+  bool all_user = L > 1;
+  for (int l = 1; l < L; ++l) all_user &= pc->lv[l].has_interp;
+  if (L > 1 && !all_user && !structured) PMG_FAIL(PMG_ERR_SUP, "gamgmc: operator is not structured; supply an interpolation for every level 1..%d", L - 1);
+
+  if (L > 1 && !all_user && structured && !fine->host_csr()) {
+    // matrix-free structured hierarchy built on the device
+    std::vector<std::unique_ptr<LevelOp>>  ops;
+    std::vector<std::unique_ptr<Transfer>> trs;
+    PMG_TRY(build_structured_hierarchy(ctx, fine, L, ops, trs));
+    for (int l = L - 1; l >= 1; --l) {
+      pc->lv[l].P         = std::move(trs[(size_t)l]);
+      pc->lv[l - 1].owned = std::move(ops[(size_t)l - 1]);
+      pc->lv[l - 1].op    = pc->lv[l - 1].owned.get();
+    }
+  } else {
+    // assembled hierarchy: Q1 interpolation unless supplied, Galerkin A_c = P^T A P
+    int64_t d[3] = {dims[0], dims[1], dims[2]};
+    for (int l = L - 1; l >= 1; --l) {
+      MgLevel &v = pc->lv[l];
+      const HostCsr *A = v.op->host_csr();
+      if (!A) PMG_FAIL(PMG_ERR_SUP, "gamgmc: level %d has no assembled operator", l);
+      bool grid_known = false;
+      if (!v.has_interp) {
+        int64_t c[3];
+        host_q1_dims(dim, d, c);
+        if (c[0] * c[1] * c[2] == d[0] * d[1] * d[2]) PMG_FAIL(PMG_ERR_ARG, "gamgmc: cannot coarsen a %lldx%lldx%lld grid further (level %d)", (long long)d[0], (long long)d[1], (long long)d[2], l);
+        host_q1_interp(dim, d, c, v.interp);
+        std::memcpy(d, c, sizeof d);
+        grid_known = true;
+      }
+      if (v.interp.n != A->n) PMG_FAIL(PMG_ERR_ARG, "gamgmc: interpolation of level %d has %lld rows, operator has %lld", l, (long long)v.interp.n, (long long)A->n);
+      HostCsr R, AP, Ac;
+      host_transpose(v.interp, R);
+      host_matmul(*A, v.interp, AP);
+      host_matmul(R, AP, Ac);
+      PMG_TRY(make_csr_transfer(ctx, v.interp, v.P));
+      if (grid_known) PMG_TRY(make_csr_grid_op(ctx, std::move(Ac), dim, d, pc->lv[l - 1].owned));
+      else PMG_TRY(make_csr_op(ctx, std::move(Ac), pc->lv[l - 1].owned));
+      pc->lv[l - 1].op = pc->lv[l - 1].owned.get();
+    }
+  }
+  // samplers: defaults of src/pc_gamgmc.c:305-349 (levels: richardson + sorgibbs, 1 it; coarse: cholsampler)
+  for (int l = 0; l < L; ++l) {
+    MgLevel          &v      = pc->lv[l];
+    const std::string prefix = l == 0 ? "gamgmc_mg_coarse_" : "gamgmc_mg_levels_";
+    const std::string ptype  = pc->get(prefix + "pc_type", l == 0 ? "cholsampler" : "sorgibbs");
+    PMG_TRY(configure_sampler(pc, prefix, ptype, v.smp));
+    const std::string ksp = pc->get(prefix + "ksp_type", "richardson");
+    if (ksp != "richardson" && ksp != "preonly") PMG_FAIL(PMG_ERR_SUP, "-%sksp_type %s: samplers run under richardson (or preonly)", prefix.c_str(), ksp.c_str());
+    v.smp.its = ksp == "preonly" ? 1 : std::atoi(pc->get(prefix + "ksp_max_it", "1").c_str());
+    if (v.smp.its < 1) PMG_FAIL(PMG_ERR_ARG, "-%sksp_max_it must be >= 1", prefix.c_str());
+    if (l < L - 1) PMG_TRY(apply_coloring_policy(pc, v.op, false));
+    PMG_TRY(setup_level_sampler(ctx, v.smp, v.op));
+    const size_t n = (size_t)v.op->n();
+    if (l < L - 1) {
+      PMG_TRY(v.b.alloc(n));
+      PMG_TRY(v.x.alloc(n));
+    }
+    if (l > 0) PMG_TRY(v.r.alloc(n));
+  }
+  const size_t nf = (size_t)fine->n();
+  PMG_TRY(pc->w.alloc(nf));
+  PMG_TRY(pc->work.alloc(nf));
+  return 0;
+}
+
+static int pc_alloc_staging(pmg_pc pc)
+{
+  const size_t n = (size_t)pc->mat->op->n();
+  PMG_TRY(pc->d_b.alloc(n));
+  PMG_TRY(pc->d_y.alloc(n));
+  if (pc->h_pinned) cudaFreeHost(pc->h_pinned);
+  pc->h_pinned = nullptr;
+  PMG_CUDA(cudaMallocHost((void **)&pc->h_pinned, n * sizeof(double)));
+  if (!pc->ev0) {
+    PMG_CUDA(cudaEventCreate(&pc->ev0));
+    PMG_CUDA(cudaEventCreate(&pc->ev1));
+  }
+  return 0;
+}
+
+static int pc_notify(pmg_pc pc, int64_t it, const double *y_dev)
+{
+  if (!pc->cb) return 0;
+  const int64_t n = pc->mat->op->n();
+  PMG_CUDA(cudaMemcpyAsync(pc->h_pinned, y_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, pc->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream)); // host-visible y before the callback fires (SURVEY 8(b) threading)
+  if (pc->cb(it, pc->h_pinned, n, pc->cbctx)) PMG_FAIL(PMG_ERR_CALLBACK, "sample callback returned an error at sample %lld", (long long)it);
+  return 0;
+}
+
+static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero)
+{
+  pmg_ctx ctx = pc->ctx;
+  if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
+  const int64_t n  = pc->mat->op->n();
+  const int64_t l0 = ctx->launches, u0 = ctx->dof_updates;
+  PMG_CUDA(cudaEventRecord(pc->ev0, ctx->stream));
+  if (pc->type == "gamgmc") { // src/pc_gamgmc.c:242-259
+    LevelOp *A = pc->lv[pc->nlevels - 1].op;
+    if (!b) {
+      PMG_TRY(pc->d_b.zero(ctx->stream));
+      b = pc->d_b.p;
+    }
+    for (int64_t it = 0; it < its; ++it) {
+      if (it == 0 && guesszero) {
+        PMG_TRY(mg_apply(pc, b, y));
+      } else {
+        PMG_TRY(A->residual(b, y, pc->w.p));             // w = b - A y
+        PMG_TRY(mg_apply(pc, pc->w.p, pc->work.p));      // work = MG(w)
+        PMG_TRY(launch_axpy(ctx, n, 1.0, pc->work.p, y)); // y += work
+      }
+      PMG_TRY(pc_notify(pc, it, y));
+    }
+  } else if (pc->type == "cholsampler") { // src/pc_chols.c:293-342
+    if (!b) {
+      PMG_TRY(pc->d_b.zero(ctx->stream));
+      b = pc->d_b.p;
+    }
+    NoiseArgs na;
+    if (its == 1) {
+      PMG_TRY(pc->noise.next(ctx, n, 0, na));
+      PMG_TRY(pc->smp.chol.sample(b, y, na));
+      PMG_TRY(pc_notify(pc, pc->sample_index++, y));
+    } else {
+      PMG_TRY(pc->smp.chol.forward(b, pc->smp.chol.vcache.p));
+      for (int64_t it = 0; it < its; ++it) {
+        PMG_TRY(pc->noise.next(ctx, n, 0, na));
+        PMG_TRY(pc->smp.chol.backward_noise(pc->smp.chol.vcache.p, y, na));
+        PMG_TRY(pc_notify(pc, pc->sample_index++, y));
+      }
+    }
+  } else { // mcgibbs: src/pc_mcgibbs.c:167-184; sorgibbs: src/pc_sorgibbs.c:125-129 (running sample_index from 0)
+    if (pc->type == "sorgibbs") pc->sample_index = 0;
+    for (int64_t it = 0; it < its; ++it) {
+      PMG_TRY(pc->smp.gibbs.sample(pc->noise, b, y));
+      PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
+    }
+  }
+  PMG_CUDA(cudaEventRecord(pc->ev1, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  PMG_CUDA(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+  pc->last_ms       = ms;
+  pc->last_launches = ctx->launches - l0;
+  pc->last_updates  = ctx->dof_updates - u0;
+  return 0;
+}
+
+extern "C" {
+
+// ---- MCSOR -------------------------------------------------------------------------------------------
+int pmg_mcsor_create(pmg_mat mat, pmg_mcsor *out)
+{
+  if (!mat) PMG_FAIL(PMG_ERR_ARG, "pmg_mcsor_create: null operator");
+  PMG_CUDA(cudaSetDevice(mat->ctx->device));
+  auto mc       = std::make_unique<pmg_mcsor_s>();
+  mc->mat       = mat;
+  mc->core.op   = mat->op.get();
+  mc->none.mode = PMG_NOISE_NONE;
+  const char *e = std::getenv("PMG_MC_SOR_OMEGA"); // -mc_sor_omega read at create (src/mc_sor.c:638)
+  if (e) mc->core.omega = std::atof(e);
+  PMG_TRY(mc->core.ensure());
+  PMG_TRY(mc->b.alloc((size_t)mat->op->n()));
+  PMG_TRY(mc->y.alloc((size_t)mat->op->n()));
+  *out = mc.release();
+  return PMG_OK;
+}
+int pmg_mcsor_destroy(pmg_mcsor mc)
+{
+  if (mc) {
+    cudaSetDevice(mc->mat->ctx->device);
+    delete mc;
+  }
+  return PMG_OK;
+}
+int pmg_mcsor_set_omega(pmg_mcsor mc, double omega)
+{
+  mc->core.omega = omega;
+  return PMG_OK;
+}
+int pmg_mcsor_set_sweep_type(pmg_mcsor mc, int type)
+{
+  if (type != PMG_SOR_FORWARD_SWEEP && type != PMG_SOR_BACKWARD_SWEEP && type != PMG_SOR_SYMMETRIC_SWEEP) PMG_FAIL(PMG_ERR_SUP, "Only forward, backward and symmetric sweep supported"); // src/mc_sor.c:427
+  mc->core.type = type;
+  return PMG_OK;
+}
+int pmg_mcsor_get_sweep_type(pmg_mcsor mc, int *type)
+{
+  *type = mc->core.type;
+  return PMG_OK;
+}
+int pmg_mcsor_get_num_colors(pmg_mcsor mc, int *n)
+{
+  *n = mc->mat->op->ncolors();
+  return PMG_OK;
+}
+int pmg_mcsor_apply_dev(pmg_mcsor mc, const double *b, double *y)
+{
+  PMG_CUDA(cudaSetDevice(mc->mat->ctx->device));
+  PMG_TRY(mc->core.sample(mc->none, b, y));
+  PMG_CUDA(cudaStreamSynchronize(mc->mat->ctx->stream));
+  return PMG_OK;
+}
+int pmg_mcsor_apply(pmg_mcsor mc, const double *b, double *y)
+{
+  pmg_ctx ctx = mc->mat->ctx;
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)mc->mat->op->n();
+  PMG_CUDA(cudaMemcpyAsync(mc->b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PMG_CUDA(cudaMemcpyAsync(mc->y.p, y, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PMG_TRY(mc->core.sample(mc->none, mc->b.p, mc->y.p));
+  PMG_CUDA(cudaMemcpyAsync(y, mc->y.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+// ---- PC ------------------------------------------------------------------------------------------------
+int pmg_pc_create(pmg_ctx ctx, const char *type, pmg_pc *out)
+{
+  if (!ctx || !type) PMG_FAIL(PMG_ERR_ARG, "pmg_pc_create: bad arguments");
+  const std::string t = type;
+  if (t != "mcgibbs" && t != "sorgibbs" && t != "gamgmc" && t != "cholsampler") PMG_FAIL(PMG_ERR_SUP, "PC type '%s' is not provided by parmgmc_b200 (mcgibbs | sorgibbs | gamgmc | cholsampler)", type);
+  auto pc  = std::make_unique<pmg_pc_s>();
+  pc->ctx  = ctx;
+  pc->type = t;
+  *out     = pc.release();
+  return PMG_OK;
+}
+
+int pmg_pc_destroy(pmg_pc pc)
+{
+  if (pc) {
+    cudaSetDevice(pc->ctx->device);
+    delete pc;
+  }
+  return PMG_OK;
+}
+
+int pmg_pc_reset(pmg_pc pc)
+{
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  pc->lv.clear();
+  pc->is_setup     = false;
+  pc->sample_index = 0;
+  pc->smp          = LevelSampler();
+  if (pc->deleter) { // PCReset_* runs the deleter (src/pc_mcgibbs.c:113-116)
+    pc->deleter(pc->cbctx);
+    pc->deleter = nullptr;
+  }
+  return PMG_OK;
+}
+
+int pmg_pc_set_operator(pmg_pc pc, pmg_mat mat)
+{
+  if (!mat) PMG_FAIL(PMG_ERR_ARG, "null operator");
+  if (mat->ctx != pc->ctx) PMG_FAIL(PMG_ERR_ARG, "operator and PC live on different contexts");
+  pc->mat      = mat;
+  pc->is_setup = false;
+  return PMG_OK;
+}
+
+int pmg_pc_set_option(pmg_pc pc, const char *key, const char *value)
+{
+  if (!key) PMG_FAIL(PMG_ERR_ARG, "null option key");
+  std::string k = key;
+  while (!k.empty() && k[0] == '-') k.erase(0, 1);
+  pc->opts[k]  = value ? value : "";
+  pc->is_setup = false;
+  return PMG_OK;
+}
+
+int pmg_pc_setup(pmg_pc pc)
+{
+  if (!pc->mat) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup: no operator set");
+  pmg_ctx ctx = pc->ctx;
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  const std::string nm = pc->get("pc_b200_noise", "");
+  if (nm == "philox") pc->noise.mode = PMG_NOISE_PHILOX;
+  else if (nm == "injected") pc->noise.mode = PMG_NOISE_INJECTED;
+  else if (nm == "none") pc->noise.mode = PMG_NOISE_NONE;
+  else if (!nm.empty()) PMG_FAIL(PMG_ERR_ARG, "-pc_b200_noise %s: expected philox | injected | none", nm.c_str());
+  if (pc->type == "gamgmc") PMG_TRY(gamgmc_setup(pc));
+  else {
+    const double omega_keep = pc->smp.gibbs.omega;
+    const int    type_keep  = pc->smp.gibbs.type;
+    PMG_TRY(configure_sampler(pc, "", pc->type, pc->smp));
+    if (pc->type == "mcgibbs") { // setters called before set-up survive unless an option overrides them
+      if (!pc->has("pc_mcgibbs_omega")) pc->smp.gibbs.omega = omega_keep;
+      if (!pc->has("pc_mcgibbs_forward") && !pc->has("pc_mcgibbs_backward") && !pc->has("pc_mcgibbs_symmetric")) pc->smp.gibbs.type = type_keep;
+    }
+    PMG_TRY(apply_coloring_policy(pc, pc->mat->op.get(), true));
+    PMG_TRY(setup_level_sampler(ctx, pc->smp, pc->mat->op.get()));
+  }
+  PMG_TRY(pc_alloc_staging(pc));
+  pc->is_setup = true;
+  return PMG_OK;
+}
+
+int pmg_pc_view(pmg_pc pc, char *buf, size_t len)
+{
+  std::string s = "PC type: " + pc->type + "\n";
+  char        t[256];
+  if (!pc->is_setup) s += "  (not set up)\n";
+  else if (pc->type == "mcgibbs") { // PCView_MulticolorGibbs, src/pc_mcgibbs.c:257-266
+    snprintf(t, sizeof t, "Number of colours: %d\n", pc->mat->op->ncolors());
+    s += t;
+  } else if (pc->type == "sorgibbs") { // PCView_SORGibbs, src/pc_sorgibbs.c:295-305
+    s += "Sweep type: Forward\n";
+    snprintf(t, sizeof t, "Number of colours: %d\n", pc->mat->op->ncolors());
+    s += t;
+  } else if (pc->type == "cholsampler") { // PCView_CholSampler, src/pc_chols.c:383-396
+    snprintf(t, sizeof t, "Dense Cholesky factor for sequential block of size %lld\n", (long long)pc->smp.chol.n);
+    s += t;
+  } else {
+    snprintf(t, sizeof t, "MG: type is MULTIPLICATIVE, levels=%d cycles=v\n", pc->nlevels);
+    s += t;
+    for (int l = 0; l < pc->nlevels; ++l) {
+      std::string d;
+      pc->lv[l].op->describe(d);
+      const LevelSampler &sm = pc->lv[l].smp;
+      snprintf(t, sizeof t, "  level %d: %s; sampler %s, max_it %d\n", l, d.c_str(), sm.kind == KIND_CHOL ? "cholsampler" : sm.kind == KIND_MCGIBBS ? "mcgibbs" : "sorgibbs", sm.its);
+      s += t;
+    }
+  }
+  if (buf && len) {
+    std::strncpy(buf, s.c_str(), len - 1);
+    buf[len - 1] = 0;
+  }
+  return PMG_OK;
+}
+
+int pmg_pc_apply_richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero, int64_t *outits, int *reason)
+{
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  PMG_TRY(richardson_dev(pc, b, y, its, guesszero));
+  if (outits) *outits = its;
+  if (reason) *reason = 4; // PCRICHARDSON_CONVERGED_ITS
+  return PMG_OK;
+}
+
+int pmg_pc_apply_richardson(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero, int64_t *outits, int *reason)
+{
+  pmg_ctx ctx = pc->ctx;
+  if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)pc->mat->op->n();
+  if (b) PMG_CUDA(cudaMemcpyAsync(pc->d_b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PMG_CUDA(cudaMemcpyAsync(pc->d_y.p, y, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PMG_TRY(richardson_dev(pc, b ? pc->d_b.p : nullptr, pc->d_y.p, its, guesszero));
+  PMG_CUDA(cudaMemcpyAsync(y, pc->d_y.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (outits) *outits = its;
+  if (reason) *reason = 4;
+  return PMG_OK;
+}
+
+int pmg_pc_apply(pmg_pc pc, const double *x, double *y)
+{
+  pmg_ctx ctx = pc->ctx;
+  if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
+  if (pc->type != "sorgibbs" && pc->type != "cholsampler") PMG_FAIL(PMG_ERR_SUP, "PCApply is only defined for sorgibbs and cholsampler (the reference sets ops->apply only there)");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)pc->mat->op->n();
+  PMG_CUDA(cudaMemcpyAsync(pc->d_b.p, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (pc->type == "sorgibbs") { // src/pc_sorgibbs.c:105-113: zero y, one sample, no callback
+    PMG_TRY(pc->d_y.zero(ctx->stream));
+    PMG_TRY(pc->smp.gibbs.sample(pc->noise, pc->d_b.p, pc->d_y.p));
+  } else { // src/pc_chols.c:262-291 (+ notify)
+    NoiseArgs na;
+    PMG_TRY(pc->noise.next(ctx, (int64_t)n, 0, na));
+    PMG_TRY(pc->smp.chol.sample(pc->d_b.p, pc->d_y.p, na));
+    PMG_TRY(pc_notify(pc, pc->sample_index++, pc->d_y.p));
+  }
+  PMG_CUDA(cudaMemcpyAsync(y, pc->d_y.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+int pmg_pc_set_sample_callback(pmg_pc pc, pmg_sample_cb cb, void *cbctx, pmg_ctx_deleter deleter)
+{
+  if (pc->type == "gamgmc") { // src/pc_gamgmc.c:369-380: must pass a callback; NULL ctx/deleter are ignored, not cleared
+    if (pc->cb && pc->deleter) pc->deleter(pc->cbctx);
+    if (!cb) PMG_FAIL(PMG_ERR_SUP, "Must pass callback function");
+    pc->cb = cb;
+    if (cbctx) pc->cbctx = cbctx;
+    if (deleter) pc->deleter = deleter;
+    return PMG_OK;
+  }
+  if (pc->deleter) pc->deleter(pc->cbctx); // src/pc_mcgibbs.c:295-298
+  pc->cb      = cb;
+  pc->cbctx   = cbctx;
+  pc->deleter = deleter;
+  return PMG_OK;
+}
+
+int pmg_pc_mcgibbs_set_omega(pmg_pc pc, double omega)
+{
+  if (pc->type != "mcgibbs") PMG_FAIL(PMG_ERR_ARG, "not a mcgibbs PC");
+  pc->smp.gibbs.omega = omega; // lazily rebuilt at the next sample (omega_changed, src/pc_mcgibbs.c:275-276)
+  pc->opts.erase("pc_mcgibbs_omega");
+  return PMG_OK;
+}
+int pmg_pc_mcgibbs_set_sweep_type(pmg_pc pc, int type)
+{
+  if (pc->type != "mcgibbs") PMG_FAIL(PMG_ERR_ARG, "not a mcgibbs PC");
+  if (type != PMG_SOR_FORWARD_SWEEP && type != PMG_SOR_BACKWARD_SWEEP && type != PMG_SOR_SYMMETRIC_SWEEP) PMG_FAIL(PMG_ERR_SUP, "Only forward, backward and symmetric sweep supported");
+  pc->smp.gibbs.type = type;
+  pc->opts.erase("pc_mcgibbs_forward");
+  pc->opts.erase("pc_mcgibbs_backward");
+  pc->opts.erase("pc_mcgibbs_symmetric");
+  return PMG_OK;
+}
+
+int pmg_pc_gamgmc_set_levels(pmg_pc pc, int levels)
+{
+  if (pc->type != "gamgmc") PMG_FAIL(PMG_ERR_ARG, "not a gamgmc PC");
+  if (levels < 1) PMG_FAIL(PMG_ERR_ARG, "levels must be >= 1");
+  pc->nlevels = levels;
+  if ((int)pc->lv.size() < levels) pc->lv.resize((size_t)levels);
+  pc->opts.erase("gamgmc_pc_mg_levels");
+  pc->is_setup = false;
+  return PMG_OK;
+}
+int pmg_pc_gamgmc_get_levels(pmg_pc pc, int *levels)
+{
+  *levels = pc->nlevels;
+  return PMG_OK;
+}
+int pmg_pc_gamgmc_set_interpolation(pmg_pc pc, int level, int64_t nf, int64_t nc, const int64_t *rowptr, const int32_t *col, const double *val)
+{
+  if (pc->type != "gamgmc") PMG_FAIL(PMG_ERR_ARG, "not a gamgmc PC");
+  if (level < 1) PMG_FAIL(PMG_ERR_ARG, "interpolation is defined for levels >= 1");
+  if ((int)pc->lv.size() <= level) pc->lv.resize((size_t)level + 1);
+  MgLevel &v = pc->lv[level];
+  v.interp.n = nf;
+  v.interp.m = nc;
+  v.interp.rowptr.assign(rowptr, rowptr + nf + 1);
+  v.interp.col.assign(col, col + rowptr[nf]);
+  v.interp.val.assign(val, val + rowptr[nf]);
+  v.has_interp = true;
+  pc->is_setup = false;
+  return PMG_OK;
+}
+int pmg_pc_gamgmc_get_level_info(pmg_pc pc, int level, int64_t *n, int64_t *nnz, int *ncolors)
+{
+  if (!pc->is_setup || level < 0 || level >= pc->nlevels) PMG_FAIL(PMG_ERR_ARG, "bad level");
+  LevelOp *op = pc->lv[level].op;
+  if (n) *n = op->n();
+  if (nnz) *nnz = op->host_csr() ? op->host_csr()->nnz() : -1;
+  if (ncolors) *ncolors = op->ncolors();
+  return PMG_OK;
+}
+int pmg_pc_gamgmc_get_level_csr(pmg_pc pc, int level, int64_t *rowptr, int32_t *col, double *val)
+{
+  if (!pc->is_setup || level < 0 || level >= pc->nlevels) PMG_FAIL(PMG_ERR_ARG, "bad level");
+  const HostCsr *a = pc->lv[level].op->host_csr();
+  if (!a) PMG_FAIL(PMG_ERR_SUP, "level %d is matrix-free", level);
+  std::memcpy(rowptr, a->rowptr.data(), a->rowptr.size() * sizeof(int64_t));
+  std::memcpy(col, a->col.data(), a->col.size() * sizeof(int32_t));
+  std::memcpy(val, a->val.data(), a->val.size() * sizeof(double));
+  return PMG_OK;
+}
+
+int pmg_pc_set_noise_mode(pmg_pc pc, int mode)
+{
+  if (mode != PMG_NOISE_PHILOX && mode != PMG_NOISE_INJECTED && mode != PMG_NOISE_NONE) PMG_FAIL(PMG_ERR_ARG, "bad noise mode");
+  pc->noise.mode = mode;
+  pc->opts.erase("pc_b200_noise");
+  return PMG_OK;
+}
+int pmg_pc_set_noise_tape(pmg_pc pc, const double *z, int64_t len)
+{
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  PMG_TRY(pc->noise.tape.upload(z, (size_t)len, pc->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream));
+  pc->noise.tape_len = len;
+  pc->noise.tape_pos = 0;
+  pc->noise.mode     = PMG_NOISE_INJECTED;
+  pc->opts.erase("pc_b200_noise");
+  return PMG_OK;
+}
+int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles)
+{
+  if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
+  int64_t d = 0;
+  if (pc->type == "gamgmc") {
+    for (int l = 0; l < pc->nlevels; ++l) d += (l == 0 ? 1 : 2) * sampler_draws(pc->lv[l].smp);
+  } else if (pc->type == "cholsampler") d = pc->smp.chol.n;
+  else d = pc->smp.gibbs.draws_per_sample();
+  *doubles = d;
+  return PMG_OK;
+}
+
+int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z)
+{
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> d;
+  PMG_TRY(d.alloc((size_t)n));
+  NoiseArgs na{PMG_NOISE_PHILOX, nullptr, seed, call, row0};
+  PMG_TRY(launch_normal_fill(ctx, na, n, d.p));
+  PMG_CUDA(cudaMemcpyAsync(z, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+int pmg_pc_last_stats(pmg_pc pc, double *ms, int64_t *launches, int64_t *updates)
+{
+  if (ms) *ms = pc->last_ms;
+  if (launches) *launches = pc->last_launches;
+  if (updates) *updates = pc->last_updates;
+  return PMG_OK;
+}
+
+// ---- multi-GPU plumbing is in comm.cu ---------------------------------------------------------------------
+
+} // extern "C"

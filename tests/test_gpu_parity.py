@@ -1,0 +1,474 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Integer/index work (colourings) and injected-noise sweeps must be bit-exact; paths
+whose operation order legitimately differs are held to a relative error of 1e-12 (the tolerance
+BASELINE.json's north_star states for FP64)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20260625  # examples/ex13.py:38
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def pmg():
+    import parmgmc_b200 as m
+    if m.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(pmg):
+    c = pmg.Context(0, seed=0xCAFE)
+    yield c
+    c.close()
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make_mat(pmg, ctx, A, coloring=None, policy=None):
+    m = pmg.Mat.from_csr(ctx, A.rowptr, A.col, A.val)
+    if coloring is not None:
+        m.set_coloring(coloring.color, coloring.ncolors)
+    if policy is not None:
+        m.set_coloring_auto(policy)
+    return m
+
+
+# ---- a6/a8: MCSORApply --------------------------------------------------------------------------
+@pytest.mark.parametrize("kappa", [10.0, 1.0])
+@pytest.mark.parametrize("omega", [1.0, 1.2, 1.6])
+def test_mcsor_config1_redblack_bitexact(pmg, ctx, orc, kappa, omega):
+    """Config 1 (129x129, src/problems.c semantics), same injected colouring on both sides."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 129, 129, kappa=kappa)
+    col = orc.Coloring.parity((129, 129))
+    mat = make_mat(pmg, ctx, A, col)
+    mc = pmg.MCSOR(mat)
+    assert mc.get_num_colors() == 2
+    mc.set_omega(omega)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    for sweep, osweep in ((pmg.SOR_FORWARD_SWEEP, orc.SOR_FORWARD), (pmg.SOR_BACKWARD_SWEEP, orc.SOR_BACKWARD), (pmg.SOR_SYMMETRIC_SWEEP, orc.SOR_SYMMETRIC)):
+        mc.set_sweep_type(sweep)
+        assert mc.get_sweep_type() == sweep
+        y = mc.apply(b, y0.copy())
+        ref = orc.MCSOR(A, col, omega).apply(b, y0.copy(), osweep)
+        assert np.array_equal(y, ref), relerr(y, ref)
+
+
+def test_mcsor_lexicographic_reproduces_one_rank_reference_bitexact(pmg, ctx, orc):
+    """The 1-rank reference sweeps ONE colour in natural order (src/mc_sor.c:397-410).  The level-set
+    colouring makes the device do exactly that order: compare with the oracle's one-colour sweep."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 129, 129, kappa=10.0)
+    mat = make_mat(pmg, ctx, A, policy=pmg.COLORING_LEXICOGRAPHIC)
+    k, color = mat.get_coloring()
+    assert k == 257
+    assert np.array_equal(color, orc.Coloring.levelset(A).color)  # colouring matches bit-exactly
+    mc = pmg.MCSOR(mat)
+    mc.set_omega(1.2)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    for sweep, osweep in ((1, orc.SOR_FORWARD), (2, orc.SOR_BACKWARD), (3, orc.SOR_SYMMETRIC)):
+        mc.set_sweep_type(sweep)
+        y = mc.apply(b, y0.copy())
+        ref = orc.MCSOR(A, None, 1.2).apply(b, y0.copy(), osweep)  # one colour, lexicographic
+        assert np.array_equal(y, ref)
+
+
+def test_greedy_coloring_matches_oracle_and_is_valid(pmg, ctx, orc):
+    for A in (orc.laplace(2, 33, 17, kappa=1.0), orc.laplace(3, 9, 8, 7, kappa=1.0), orc.MG.geometric(2, 17, 17, 1, 1.0, 2).level_csr(0)):
+        mat = make_mat(pmg, ctx, A, policy=pmg.COLORING_GREEDY)
+        k, color = mat.get_coloring()
+        ref = orc.Coloring.greedy(A)
+        assert k == ref.ncolors and np.array_equal(color, ref.color)
+        assert orc.Coloring(color, k).violations(A) == 0
+
+
+def test_ex5_identity_on_device(pmg, ctx, orc):
+    """examples/ex5.c:60-70."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 9, 9, kappa=1.0)
+    mat = make_mat(pmg, ctx, A, policy=pmg.COLORING_GREEDY)
+    mc = pmg.MCSOR(mat)
+    b, x = rng.random(81), rng.random(81)
+    y = x.copy()
+    mc.set_sweep_type(1); mc.apply(b, x)
+    mc.set_sweep_type(2); mc.apply(b, x)
+    mc.set_sweep_type(3); mc.apply(b, y)
+    assert np.linalg.norm(x - y) < 1e-15
+
+
+def test_mcsor_ragged_rows_and_3d(pmg, ctx, orc):
+    """rows of very different length (SELL padding) and a 3D 7-point operator"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(SEED)
+    n = 300
+    M = sp.random(n, n, density=0.03, random_state=7, format="csr")
+    M = M + M.T
+    M = sp.csr_matrix(M + sp.diags(np.asarray(abs(M).sum(axis=1)).ravel() + 1.0))
+    dense_row = np.zeros(n); dense_row[:] = 0.01
+    M = sp.lil_matrix(M); M[5, :] = dense_row; M[:, 5] = dense_row.reshape(-1, 1); M[5, 5] = 10.0
+    M = sp.csr_matrix(M); M.sort_indices()
+    for A in (orc.CSR(n, M.indptr, M.indices, M.data), orc.laplace(3, 9, 8, 7, kappa=2.0)):
+        col = orc.Coloring.greedy(A)
+        mat = make_mat(pmg, ctx, A, col)
+        mc = pmg.MCSOR(mat)
+        mc.set_omega(0.9)
+        mc.set_sweep_type(3)
+        b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+        y = mc.apply(b, y0.copy())
+        ref = orc.MCSOR(A, col, 0.9).apply(b, y0.copy(), orc.SOR_SYMMETRIC)
+        assert np.array_equal(y, ref)
+        np.testing.assert_allclose(mat.mult(y0), A.to_scipy() @ y0, rtol=1e-13, atol=1e-13)
+
+
+def test_error_codes(pmg, ctx, orc):
+    A = orc.laplace(2, 5, 5, kappa=1.0)
+    mat = make_mat(pmg, ctx, A)
+    mc = pmg.MCSOR(mat)
+    with pytest.raises(pmg.PMGError) as e:
+        mc.set_sweep_type(7)  # src/mc_sor.c:427 PETSC_ERR_SUP
+    assert e.value.code == 2
+    with pytest.raises(pmg.PMGError) as e:
+        mat.set_coloring(np.zeros(25, np.int32), 1)  # one colour is not a distance-1 colouring
+    assert e.value.code == 8
+    with pytest.raises(pmg.PMGError) as e:
+        pmg.PC(ctx, "parsor")
+    assert e.value.code == 2
+    pc = pmg.PC(ctx, "mcgibbs")
+    with pytest.raises(pmg.PMGError) as e:
+        pc.setup()
+    assert e.value.code == 6
+    pc.set_operator(mat)
+    pc.set_option("-pc_mcgibbs_omega", 2.5)
+    with pytest.raises(pmg.PMGError) as e:
+        pc.setup()
+    assert e.value.code == 1
+    pc.set_option("-pc_mcgibbs_omega", 1.0)
+    pc.setup()
+    pc.set_noise_tape(np.zeros(10))
+    with pytest.raises(pmg.PMGError) as e:
+        pc.apply_richardson(np.zeros(25), np.zeros(25), its=1)
+    assert e.value.code == 7
+    bad = orc.laplace(2, 4, 4, kappa=1.0)
+    bad.val[bad.diag_ptrs()] = -1.0
+    chol = pmg.PC(ctx, "cholsampler")
+    chol.set_operator(make_mat(pmg, ctx, bad))
+    with pytest.raises(pmg.PMGError) as e:
+        chol.setup()
+    assert e.value.code == 5  # PETSC_ERR_MAT_CH_ZRPVT, src/pc_chols.c:192
+
+
+# ---- a10-a13: the Gibbs samplers -----------------------------------------------------------------
+@pytest.mark.parametrize("pctype,opts,osweep,omega", [
+    ("mcgibbs", {}, 1, 1.0),
+    ("mcgibbs", {"-pc_mcgibbs_omega": 1.6, "-pc_mcgibbs_backward": ""}, 2, 1.6),
+    ("mcgibbs", {"-pc_mcgibbs_omega": 1.2, "-pc_mcgibbs_symmetric": ""}, 3, 1.2),
+    ("sorgibbs", {}, 1, 1.0),
+])
+def test_gibbs_sampler_injected_noise_bitexact(pmg, ctx, orc, pctype, opts, osweep, omega):
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 129, 129, kappa=10.0)
+    col = orc.Coloring.parity((129, 129))
+    mat = make_mat(pmg, ctx, A, col)
+    pc = pmg.PC(ctx, pctype)
+    pc.set_operator(mat)
+    pc.set_options(opts)
+    pc.setup()
+    its = 4
+    per = pc.noise_per_sample()
+    assert per == (2 if osweep == 3 else 1) * A.n
+    z = rng.standard_normal(its * per)
+    pc.set_noise_tape(z)
+    b, y = np.ones(A.n), np.zeros(A.n)
+    seen = []
+    pc.set_sample_callback(lambda it, yy: seen.append((it, yy.copy())))
+    outits, reason = pc.apply_richardson(b, y, its=its)
+    assert (outits, reason) == (its, pmg.PCRICHARDSON_CONVERGED_ITS)
+    ref_seen = []
+    ref = orc.gibbs_richardson(A, b, np.zeros(A.n), its, orc.Noise.tape(z), col, omega, osweep, callback=lambda it, yy: ref_seen.append((it, yy.copy())))
+    assert np.array_equal(y, ref)
+    assert [s[0] for s in seen] == list(range(its))
+    for (_, a), (_, r) in zip(seen, ref_seen):
+        assert np.array_equal(a, r)
+
+
+def test_sorgibbs_pcapply_zeroes_guess(pmg, ctx, orc):
+    """src/pc_sorgibbs.c:105-113."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 17, 17, kappa=1.0)
+    col = orc.Coloring.parity((17, 17))
+    pc = pmg.PC(ctx, "sorgibbs")
+    pc.set_operator(make_mat(pmg, ctx, A, col))
+    pc.setup()
+    z, b = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    pc.set_noise_tape(z)
+    y = pc.apply(b)
+    ref = orc.gibbs_richardson(A, b, np.zeros(A.n), 1, orc.Noise.tape(z), col, 1.0, orc.SOR_FORWARD)
+    assert np.array_equal(y, ref)
+
+
+def test_prior_sampling_null_rhs(pmg, ctx, orc):
+    """b = NULL (examples/ex8.c:47-49 samples the prior with f = 0)."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 17, 9, kappa=1.0)
+    col = orc.Coloring.parity((17, 9))
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(make_mat(pmg, ctx, A, col))
+    pc.setup()
+    z = rng.standard_normal(2 * A.n)
+    pc.set_noise_tape(z)
+    y = np.zeros(A.n)
+    pc.apply_richardson(None, y, its=2)
+    ref = orc.gibbs_richardson(A, np.zeros(A.n), np.zeros(A.n), 2, orc.Noise.tape(z), col)
+    assert np.array_equal(y, ref)
+
+
+def test_callback_deleter_and_setters(pmg, ctx, orc):
+    A = orc.laplace(2, 9, 9, kappa=1.0)
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(make_mat(pmg, ctx, A, orc.Coloring.parity((9, 9))))
+    pc.setup()
+    assert "Number of colours: 2" in pc.view()  # PCView_MulticolorGibbs
+    deleted = []
+    pc.set_sample_callback(lambda it, y: None, deleter=lambda: deleted.append(1))
+    pc.set_sample_callback(lambda it, y: None)  # replacing runs the old deleter (src/pc_mcgibbs.c:295-298)
+    assert deleted == [1]
+    # a failing callback surfaces as an error (PetscCall propagation)
+    pc.set_sample_callback(lambda it, y: 1)
+    with pytest.raises(pmg.PMGError) as e:
+        pc.apply_richardson(np.ones(81), np.zeros(81), its=1)
+    assert e.value.code == 10
+    # omega / sweep setters after set-up take effect lazily (omega_changed)
+    pc.set_sample_callback(None)
+    pc.mcgibbs_set_omega(1.5)
+    pc.mcgibbs_set_sweep_type(pmg.SOR_BACKWARD_SWEEP)
+    z = np.random.default_rng(1).standard_normal(81)
+    pc.set_noise_tape(z)
+    y = np.zeros(81)
+    pc.apply_richardson(np.ones(81), y, its=1)
+    ref = orc.gibbs_richardson(A, np.ones(81), np.zeros(81), 1, orc.Noise.tape(z), orc.Coloring.parity((9, 9)), 1.5, orc.SOR_BACKWARD)
+    assert np.array_equal(y, ref)
+
+
+# ---- a11: device normals ---------------------------------------------------------------------------
+def test_device_philox_normals_match_definition(pmg, ctx, orc):
+    for row0, n in ((0, 100001), (12345, 4097), (2 ** 33 + 1, 1000)):
+        z = ctx.normal_fill(0xCAFE, 7, row0, n)
+        ref = orc.normal_philox(0xCAFE, 7, row0, n)
+        assert np.abs(z - ref).max() < 5e-15 * max(1.0, np.abs(ref).max())
+    z = ctx.normal_fill(1, 0, 0, 1 << 20)
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1) < 5e-3 and abs(np.mean(z ** 4) - 3) < 0.03
+
+
+def test_gibbs_philox_mode_matches_oracle_philox(pmg, ctx, orc):
+    A = orc.laplace(2, 65, 33, kappa=1.0)
+    col = orc.Coloring.parity((65, 33))
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(make_mat(pmg, ctx, A, col))
+    pc.set_options({"-pc_mcgibbs_symmetric": "", "-pc_b200_noise": "philox"})
+    pc.setup()
+    ctx.set_seed(0xCAFE)
+    b, y = np.ones(A.n), np.zeros(A.n)
+    pc.apply_richardson(b, y, its=5)
+    assert ctx.draw_counter == 10
+    ref = orc.gibbs_richardson(A, b, np.zeros(A.n), 5, orc.Noise.philox(0xCAFE), col, 1.0, orc.SOR_SYMMETRIC)
+    assert relerr(y, ref) < RTOL
+    # checkpoint / resume: (y, seed, draw counter) is the whole chain state
+    y2 = np.zeros(A.n)
+    ctx.set_seed(0xCAFE)
+    pc.apply_richardson(b, y2, its=2)
+    ctx.draw_counter = 4
+    pc.apply_richardson(b, y2, its=3)
+    assert np.array_equal(y, y2)
+
+
+# ---- a16: Cholesky sampler ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(5, 5), (9, 9), (17, 17), (33, 20)])
+def test_cholsampler_bitexact(pmg, ctx, orc, dims):
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, dims[0], dims[1], kappa=1.0)
+    n = A.n
+    pc = pmg.PC(ctx, "cholsampler")
+    pc.set_operator(make_mat(pmg, ctx, A))
+    pc.setup()
+    assert f"size {n}" in pc.view()
+    Lf = orc.potrf_lower(A.to_scipy().toarray())
+    z, b = rng.standard_normal(4 * n), rng.standard_normal(n)
+    # its == 1 (PCApply path) and its > 1 (cached forward solve, src/pc_chols.c:306-336)
+    pc.set_noise_tape(z)
+    y = np.zeros(n)
+    pc.apply_richardson(b, y, its=1)
+    assert np.array_equal(y, orc.chol_sample(Lf, n, orc.Noise.tape(z[:n]), b))
+    y3 = np.zeros(n)
+    its_seen = []
+    pc.set_sample_callback(lambda it, yy: its_seen.append(it))
+    pc.apply_richardson(b, y3, its=3)
+    assert np.array_equal(y3, orc.chol_sample(Lf, n, orc.Noise.tape(z[3 * n:]), b))
+    assert len(its_seen) == 3
+    # exactness: mean of many samples -> A^-1 b is covered by the statistical test
+
+
+# ---- a14/a15: MGMC V-cycle ------------------------------------------------------------------------------
+def oracle_mg(orc, dim, dims, kappa, levels, smoother="sorgibbs", its=1, coarse="chol", coarse_its=1, omega=1.0, sweep=1):
+    mg = orc.MG.geometric(dim, dims[0], dims[1], dims[2] if dim == 3 else 1, kappa, levels)
+    kind = orc.KIND_SORGIBBS if smoother == "sorgibbs" else orc.KIND_MCGIBBS
+    for l in range(levels):
+        d = mg.level_dims(l)
+        dd = d[:dim]
+        star = l == levels - 1  # the fine operator is a star stencil (red-black); Galerkin levels are box stencils (2^d colours)
+        col = orc.Coloring.parity(dd, 2 if star else 2 ** dim)
+        if l == 0:
+            if coarse == "chol":
+                mg.set_smoother(0, orc.KIND_CHOL, 1.0, 1, coarse_its, None)
+            else:
+                mg.set_smoother(0, kind, omega, sweep, coarse_its, col)
+        else:
+            mg.set_smoother(l, kind, omega, sweep, its, col)
+    mg.setup()
+    return mg
+
+
+@pytest.mark.parametrize("dims,levels", [((33, 33), 3), ((65, 33), 4), ((17, 17), 1), ((24, 16), 3)])
+def test_gamgmc_default_cycle_matches_oracle(pmg, ctx, orc, dims, levels):
+    """Defaults of src/pc_gamgmc.c:305-349: sorgibbs on the levels, cholsampler on the coarsest, V(1,1), Galerkin."""
+    rng = np.random.default_rng(SEED)
+    lap = pmg.Mat.laplace(ctx, 2, dims[0], dims[1], kappa=1.0)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(lap)
+    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity"})
+    pc.setup()
+    assert pc.gamgmc_get_levels() == levels
+    omg = oracle_mg(orc, 2, dims + (1,), 1.0, levels)
+    # hierarchy: same sizes, Galerkin operators within rounding
+    for l in range(levels):
+        n, nnz, _ = pc.gamgmc_level_info(l)
+        ref = omg.level_csr(l)
+        assert n == ref.n
+        if nnz >= 0:
+            rp, col, val = pc.gamgmc_level_csr(l)
+            assert np.array_equal(rp, ref.rowptr) and np.array_equal(col, ref.col)
+            np.testing.assert_allclose(val, ref.val, rtol=1e-14, atol=1e-18)
+    its = 3
+    per = pc.noise_per_sample()
+    z = rng.standard_normal(its * per)
+    n = dims[0] * dims[1]
+    b = rng.standard_normal(n)
+    for guesszero in (False, True):
+        pc.set_noise_tape(z)
+        y = np.full(n, 0.5)
+        pc.apply_richardson(b, y, its=its, guesszero=guesszero)
+        tape = orc.Noise.tape(z)
+        ref = omg.richardson(tape, b, np.full(n, 0.5), its, guesszero=guesszero)
+        assert tape.tape_pos == its * per  # same noise-tape contract
+        assert relerr(y, ref) < RTOL, relerr(y, ref)
+
+
+def test_gamgmc_ex1_options_mcgibbs_everywhere(pmg, ctx, orc):
+    """examples/ex1.c:41: geometric, 3 levels on 9x9, mcgibbs on levels and coarse, 2 its each."""
+    rng = np.random.default_rng(SEED)
+    lap = pmg.Mat.laplace(ctx, 2, 9, 9, kappa=10.0)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(lap)
+    pc.set_options({"-pc_gamgmc_mg_type": "mg", "-gamgmc_pc_mg_levels": 3, "-gamgmc_mg_levels_ksp_type": "richardson", "-gamgmc_mg_levels_pc_type": "mcgibbs",
+                    "-gamgmc_mg_coarse_ksp_type": "richardson", "-gamgmc_mg_coarse_pc_type": "mcgibbs", "-gamgmc_mg_coarse_ksp_max_it": 2,
+                    "-gamgmc_mg_levels_ksp_max_it": 2, "-pc_b200_coloring": "parity"})
+    pc.setup()
+    omg = oracle_mg(orc, 2, (9, 9, 1), 10.0, 3, smoother="mcgibbs", its=2, coarse="mcgibbs", coarse_its=2)
+    per = pc.noise_per_sample()
+    assert per == 4 * (81 + 25) + 2 * 9
+    z = rng.standard_normal(2 * per)
+    pc.set_noise_tape(z)
+    b, y = np.ones(81), np.zeros(81)
+    pc.apply_richardson(b, y, its=2)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(81), 2)
+    assert relerr(y, ref) < RTOL
+    assert "levels=3" in pc.view()
+
+
+def test_gamgmc_user_interpolation_on_plain_csr(pmg, ctx, orc):
+    """PCMGSetInterpolation path: a CSR operator with user-supplied P (here Q1 built by the oracle)."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 17, 17, kappa=1.0)
+    omg = oracle_mg(orc, 2, (17, 17, 1), 1.0, 2)
+    mat = make_mat(pmg, ctx, A, orc.Coloring.parity((17, 17)))
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(mat)
+    pc.gamgmc_set_levels(2)
+    nf, nc = np.array([17, 17, 1], np.int64), np.array([9, 9, 1], np.int64)
+    nnz = orc.lib().orc_q1_nnz(2, nf, nc)
+    rp, col, val = np.empty(290, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    orc.lib().orc_q1_interp(2, nf, nc, rp, col, val)
+    pc.gamgmc_set_interpolation(1, 289, 81, rp, col, val)
+    pc.setup()
+    z = rng.standard_normal(pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(289), np.zeros(289)
+    pc.apply_richardson(b, y, its=1)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(289), 1)
+    assert relerr(y, ref) < RTOL
+    # algebraic coarsening is PETSc-internal: refused, not faked
+    pc2 = pmg.PC(ctx, "gamgmc")
+    pc2.set_operator(mat)
+    pc2.set_options({"-pc_gamgmc_mg_type": "gamg", "-gamgmc_pc_mg_levels": 2})
+    with pytest.raises(pmg.PMGError) as e:
+        pc2.setup()
+    assert e.value.code == 2
+
+
+def test_gamgmc_3d(pmg, ctx, orc):
+    rng = np.random.default_rng(SEED)
+    lap = pmg.Mat.laplace(ctx, 3, 9, 9, 9, kappa=1.0)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(lap)
+    pc.set_options({"-gamgmc_pc_mg_levels": 2, "-pc_b200_coloring": "parity"})
+    pc.setup()
+    omg = oracle_mg(orc, 3, (9, 9, 9), 1.0, 2)
+    z = rng.standard_normal(2 * pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(729), np.zeros(729)
+    pc.apply_richardson(b, y, its=2)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(729), 2)
+    assert relerr(y, ref) < RTOL
+
+
+# ---- statistics with the device RNG (examples/ex1.c) -------------------------------------------------------
+@pytest.mark.parametrize("pctype,opts,nsamp", [
+    ("mcgibbs", {}, 400000),
+    ("mcgibbs", {"-pc_mcgibbs_symmetric": ""}, 300000),
+    ("sorgibbs", {}, 400000),
+    ("gamgmc", {"-gamgmc_pc_mg_levels": 3}, 200000),
+    ("cholsampler", {}, 200000),
+])
+def test_ex1_mean_convergence_device_rng(pmg, ctx, orc, pctype, opts, nsamp):
+    """examples/ex1.c:83-135 acceptance check (rel. error of the sample mean <= 0.02) with the Philox
+    generator.  The running mean is formed on the device side of the callback-free path: the chain is
+    advanced in blocks and the block end states are averaged, which keeps the test fast; the estimator
+    is the same sample mean."""
+    A = orc.laplace(2, 9, 9, kappa=10.0)
+    b = np.ones(81)
+    ex_mean = np.linalg.solve(A.to_scipy().toarray(), b)
+    lap = pmg.Mat.laplace(ctx, 2, 9, 9, kappa=10.0)
+    pc = pmg.PC(ctx, pctype)
+    pc.set_operator(lap)
+    pc.set_options(opts)
+    pc.set_option("-pc_b200_noise", "philox")
+    pc.setup()
+    ctx.set_seed(0xCAFE)
+    y = np.zeros(81)
+    pc.apply_richardson(b, y, its=1000)  # burn-in
+    acc = {"m": np.zeros(81), "k": 0}
+
+    def cb(it, yy):
+        acc["k"] += 1
+        acc["m"] += (yy - acc["m"]) / acc["k"]
+
+    pc.set_sample_callback(cb)
+    pc.apply_richardson(b, y, its=nsamp)
+    rel = np.linalg.norm(acc["m"] - ex_mean) / np.linalg.norm(ex_mean)
+    assert acc["k"] == nsamp
+    assert rel <= 0.02, rel
