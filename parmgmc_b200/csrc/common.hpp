@@ -100,7 +100,11 @@ struct pmg_ctx_s {
   cudaStream_t comm_stream = nullptr;
   // measurement
   int64_t launches = 0, dof_updates = 0;
+  // objects created on a context keep it alive: pmg_ctx_destroy only drops the caller's reference
+  int refs = 1;
 };
+void pmg_ctx_retain(pmg_ctx ctx);
+void pmg_ctx_release(pmg_ctx ctx);
 
 // One N(0,1) block: what a single VecSetRandomStandardNormal call (src/parmgmc.c:70-116) produces.
 struct NoiseArgs {
@@ -180,6 +184,12 @@ struct Transfer {
 struct pmg_mat_s {
   pmg_ctx                  ctx = nullptr;
   std::unique_ptr<LevelOp> op;
+  explicit pmg_mat_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
+  ~pmg_mat_s()
+  {
+    op.reset();
+    pmg_ctx_release(ctx);
+  }
 };
 
 // host-side sparse helpers (host_sparse.cpp)

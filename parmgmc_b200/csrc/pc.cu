@@ -26,8 +26,27 @@ void pmg_set_error(const char *fmt, ...)
   g_error = buf;
 }
 
+// Reports (and clears) a CUDA error left behind by an earlier call whose status nobody looked at, so that
+// it is attributed to the right place instead of to the next kernel launch.
+static void pmg_stale(const char *where)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fprintf(stderr, "[parmgmc_b200] stale CUDA error '%s' found on entry to %s\n", cudaGetErrorString(e), where);
+}
+
 int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op);
 int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine, int nlevels, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers);
+
+void pmg_ctx_retain(pmg_ctx ctx) { ctx->refs++; }
+void pmg_ctx_release(pmg_ctx ctx)
+{
+  if (--ctx->refs > 0) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+}
 
 extern "C" {
 
@@ -36,6 +55,7 @@ const char *pmg_last_error(void) { return g_error.c_str(); }
 
 int pmg_device_count(int *count)
 {
+  pmg_stale("pmg_device_count");
   int         n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) {
@@ -48,6 +68,7 @@ int pmg_device_count(int *count)
 
 int pmg_ctx_create(int device, pmg_ctx *out)
 {
+  pmg_stale("pmg_ctx_create");
   int n = 0;
   pmg_device_count(&n);
   if (n == 0) PMG_FAIL(PMG_ERR_NO_DEVICE, "no CUDA device visible: parmgmc_b200 has no CPU fallback");
@@ -66,16 +87,14 @@ int pmg_ctx_create(int device, pmg_ctx *out)
 
 int pmg_ctx_destroy(pmg_ctx ctx)
 {
-  if (!ctx) return PMG_OK;
-  cudaSetDevice(ctx->device);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
-  delete ctx;
+  pmg_stale("pmg_ctx_destroy");
+  if (ctx) pmg_ctx_release(ctx);
   return PMG_OK;
 }
 
 int pmg_ctx_set_stream(pmg_ctx ctx, void *s)
 {
+  pmg_stale("pmg_ctx_set_stream");
   if (ctx->own_stream && ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
@@ -87,6 +106,7 @@ int pmg_ctx_set_stream(pmg_ctx ctx, void *s)
 
 int pmg_ctx_synchronize(pmg_ctx ctx)
 {
+  pmg_stale("pmg_ctx_synchronize");
   PMG_CUDA(cudaSetDevice(ctx->device));
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));
   return PMG_OK;
@@ -94,17 +114,20 @@ int pmg_ctx_synchronize(pmg_ctx ctx)
 
 int pmg_ctx_set_seed(pmg_ctx ctx, uint64_t seed)
 {
+  pmg_stale("pmg_ctx_set_seed");
   ctx->seed  = seed;
   ctx->draws = 0;
   return PMG_OK;
 }
 int pmg_ctx_get_draw_counter(pmg_ctx ctx, uint64_t *d)
 {
+  pmg_stale("pmg_ctx_get_draw_counter");
   *d = ctx->draws;
   return PMG_OK;
 }
 int pmg_ctx_set_draw_counter(pmg_ctx ctx, uint64_t d)
 {
+  pmg_stale("pmg_ctx_set_draw_counter");
   ctx->draws = d;
   return PMG_OK;
 }
@@ -112,6 +135,7 @@ int pmg_ctx_set_draw_counter(pmg_ctx ctx, uint64_t d)
 // ---- operators --------------------------------------------------------------------------------------
 int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr, const int32_t *col, const double *val, pmg_mat *out)
 {
+  pmg_stale("pmg_mat_create_csr");
   if (!ctx || !rowptr || !col || !val || n <= 0) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_csr: bad arguments");
   PMG_CUDA(cudaSetDevice(ctx->device));
   HostCsr a;
@@ -120,8 +144,7 @@ int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr, const int3
   if (a.rowptr[0] != 0) PMG_FAIL(PMG_ERR_ARG, "rowptr[0] must be 0");
   a.col.assign(col, col + a.rowptr[n]);
   a.val.assign(val, val + a.rowptr[n]);
-  auto m = std::make_unique<pmg_mat_s>();
-  m->ctx = ctx;
+  auto m = std::make_unique<pmg_mat_s>(ctx);
   PMG_TRY(make_csr_op(ctx, std::move(a), m->op));
   *out = m.release();
   return PMG_OK;
@@ -129,10 +152,10 @@ int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr, const int3
 
 int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, pmg_mat *out)
 {
+  pmg_stale("pmg_mat_create_laplace");
   if (!ctx || (dim != 2 && dim != 3) || nx < 2 || ny < 1) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_laplace: bad arguments");
   PMG_CUDA(cudaSetDevice(ctx->device));
-  auto m = std::make_unique<pmg_mat_s>();
-  m->ctx = ctx;
+  auto m = std::make_unique<pmg_mat_s>(ctx);
   PMG_TRY(make_laplace_op(ctx, dim, nx, ny, dim == 3 ? nz : 1, kappa, slab_lo, slab_hi, m->op));
   *out = m.release();
   return PMG_OK;
@@ -140,6 +163,7 @@ int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t
 
 int pmg_mat_destroy(pmg_mat m)
 {
+  pmg_stale("pmg_mat_destroy");
   if (m) {
     cudaSetDevice(m->ctx->device);
     delete m;
@@ -149,6 +173,7 @@ int pmg_mat_destroy(pmg_mat m)
 
 int pmg_mat_get_size(pmg_mat m, int64_t *nl, int64_t *ng, int64_t *r0)
 {
+  pmg_stale("pmg_mat_get_size");
   if (nl) *nl = m->op->n();
   if (ng) *ng = m->op->nglobal();
   if (r0) *r0 = m->op->row0();
@@ -157,16 +182,19 @@ int pmg_mat_get_size(pmg_mat m, int64_t *nl, int64_t *ng, int64_t *r0)
 
 int pmg_mat_set_coloring(pmg_mat m, int ncolors, const int32_t *color)
 {
+  pmg_stale("pmg_mat_set_coloring");
   PMG_CUDA(cudaSetDevice(m->ctx->device));
   return m->op->set_coloring(ncolors, color);
 }
 int pmg_mat_set_coloring_auto(pmg_mat m, int policy)
 {
+  pmg_stale("pmg_mat_set_coloring_auto");
   PMG_CUDA(cudaSetDevice(m->ctx->device));
   return m->op->set_coloring_auto(policy);
 }
 int pmg_mat_get_coloring(pmg_mat m, int *ncolors, int32_t *color)
 {
+  pmg_stale("pmg_mat_get_coloring");
   if (ncolors) *ncolors = m->op->ncolors();
   if (color) {
     std::vector<int32_t> c;
@@ -178,6 +206,7 @@ int pmg_mat_get_coloring(pmg_mat m, int *ncolors, int32_t *color)
 
 int pmg_mat_mult(pmg_mat m, const double *x, double *y)
 {
+  pmg_stale("pmg_mat_mult");
   pmg_ctx ctx = m->ctx;
   PMG_CUDA(cudaSetDevice(ctx->device));
   const int64_t  n = m->op->n();
@@ -226,7 +255,16 @@ struct GibbsCore {
 };
 
 struct pmg_mcsor_s {
+  pmg_ctx        ctx;
   pmg_mat        mat;
+  explicit pmg_mcsor_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
+  ~pmg_mcsor_s()
+  {
+    core.coeffs = SweepCoeffs();
+    b.release();
+    y.release();
+    pmg_ctx_release(ctx);
+  }
   GibbsCore      core;
   NoiseStream    none;
   DevBuf<double> b, y;
@@ -274,12 +312,18 @@ struct pmg_pc_s {
   double         last_ms = 0;
   int64_t        last_launches = 0, last_updates = 0;
 
+  explicit pmg_pc_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
   ~pmg_pc_s()
   {
     if (deleter) deleter(cbctx);
     if (h_pinned) cudaFreeHost(h_pinned);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    lv.clear();
+    smp = LevelSampler();
+    noise.tape.release();
+    w.release(); work.release(); d_b.release(); d_y.release();
+    pmg_ctx_release(ctx);
   }
   bool        has(const std::string &k) const { return opts.count(k) != 0; }
   std::string get(const std::string &k, const std::string &d) const
@@ -576,9 +620,10 @@ extern "C" {
 // ---- MCSOR -------------------------------------------------------------------------------------------
 int pmg_mcsor_create(pmg_mat mat, pmg_mcsor *out)
 {
+  pmg_stale("pmg_mcsor_create");
   if (!mat) PMG_FAIL(PMG_ERR_ARG, "pmg_mcsor_create: null operator");
   PMG_CUDA(cudaSetDevice(mat->ctx->device));
-  auto mc       = std::make_unique<pmg_mcsor_s>();
+  auto mc       = std::make_unique<pmg_mcsor_s>(mat->ctx);
   mc->mat       = mat;
   mc->core.op   = mat->op.get();
   mc->none.mode = PMG_NOISE_NONE;
@@ -592,42 +637,49 @@ int pmg_mcsor_create(pmg_mat mat, pmg_mcsor *out)
 }
 int pmg_mcsor_destroy(pmg_mcsor mc)
 {
+  pmg_stale("pmg_mcsor_destroy");
   if (mc) {
-    cudaSetDevice(mc->mat->ctx->device);
+    cudaSetDevice(mc->ctx->device);
     delete mc;
   }
   return PMG_OK;
 }
 int pmg_mcsor_set_omega(pmg_mcsor mc, double omega)
 {
+  pmg_stale("pmg_mcsor_set_omega");
   mc->core.omega = omega;
   return PMG_OK;
 }
 int pmg_mcsor_set_sweep_type(pmg_mcsor mc, int type)
 {
+  pmg_stale("pmg_mcsor_set_sweep_type");
   if (type != PMG_SOR_FORWARD_SWEEP && type != PMG_SOR_BACKWARD_SWEEP && type != PMG_SOR_SYMMETRIC_SWEEP) PMG_FAIL(PMG_ERR_SUP, "Only forward, backward and symmetric sweep supported"); // src/mc_sor.c:427
   mc->core.type = type;
   return PMG_OK;
 }
 int pmg_mcsor_get_sweep_type(pmg_mcsor mc, int *type)
 {
+  pmg_stale("pmg_mcsor_get_sweep_type");
   *type = mc->core.type;
   return PMG_OK;
 }
 int pmg_mcsor_get_num_colors(pmg_mcsor mc, int *n)
 {
+  pmg_stale("pmg_mcsor_get_num_colors");
   *n = mc->mat->op->ncolors();
   return PMG_OK;
 }
 int pmg_mcsor_apply_dev(pmg_mcsor mc, const double *b, double *y)
 {
-  PMG_CUDA(cudaSetDevice(mc->mat->ctx->device));
+  pmg_stale("pmg_mcsor_apply_dev");
+  PMG_CUDA(cudaSetDevice(mc->ctx->device));
   PMG_TRY(mc->core.sample(mc->none, b, y));
-  PMG_CUDA(cudaStreamSynchronize(mc->mat->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(mc->ctx->stream));
   return PMG_OK;
 }
 int pmg_mcsor_apply(pmg_mcsor mc, const double *b, double *y)
 {
+  pmg_stale("pmg_mcsor_apply");
   pmg_ctx ctx = mc->mat->ctx;
   PMG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)mc->mat->op->n();
@@ -642,11 +694,11 @@ int pmg_mcsor_apply(pmg_mcsor mc, const double *b, double *y)
 // ---- PC ------------------------------------------------------------------------------------------------
 int pmg_pc_create(pmg_ctx ctx, const char *type, pmg_pc *out)
 {
+  pmg_stale("pmg_pc_create");
   if (!ctx || !type) PMG_FAIL(PMG_ERR_ARG, "pmg_pc_create: bad arguments");
   const std::string t = type;
   if (t != "mcgibbs" && t != "sorgibbs" && t != "gamgmc" && t != "cholsampler") PMG_FAIL(PMG_ERR_SUP, "PC type '%s' is not provided by parmgmc_b200 (mcgibbs | sorgibbs | gamgmc | cholsampler)", type);
-  auto pc  = std::make_unique<pmg_pc_s>();
-  pc->ctx  = ctx;
+  auto pc  = std::make_unique<pmg_pc_s>(ctx);
   pc->type = t;
   *out     = pc.release();
   return PMG_OK;
@@ -654,6 +706,7 @@ int pmg_pc_create(pmg_ctx ctx, const char *type, pmg_pc *out)
 
 int pmg_pc_destroy(pmg_pc pc)
 {
+  pmg_stale("pmg_pc_destroy");
   if (pc) {
     cudaSetDevice(pc->ctx->device);
     delete pc;
@@ -663,6 +716,7 @@ int pmg_pc_destroy(pmg_pc pc)
 
 int pmg_pc_reset(pmg_pc pc)
 {
+  pmg_stale("pmg_pc_reset");
   PMG_CUDA(cudaSetDevice(pc->ctx->device));
   pc->lv.clear();
   pc->is_setup     = false;
@@ -677,6 +731,7 @@ int pmg_pc_reset(pmg_pc pc)
 
 int pmg_pc_set_operator(pmg_pc pc, pmg_mat mat)
 {
+  pmg_stale("pmg_pc_set_operator");
   if (!mat) PMG_FAIL(PMG_ERR_ARG, "null operator");
   if (mat->ctx != pc->ctx) PMG_FAIL(PMG_ERR_ARG, "operator and PC live on different contexts");
   pc->mat      = mat;
@@ -686,6 +741,7 @@ int pmg_pc_set_operator(pmg_pc pc, pmg_mat mat)
 
 int pmg_pc_set_option(pmg_pc pc, const char *key, const char *value)
 {
+  pmg_stale("pmg_pc_set_option");
   if (!key) PMG_FAIL(PMG_ERR_ARG, "null option key");
   std::string k = key;
   while (!k.empty() && k[0] == '-') k.erase(0, 1);
@@ -696,6 +752,7 @@ int pmg_pc_set_option(pmg_pc pc, const char *key, const char *value)
 
 int pmg_pc_setup(pmg_pc pc)
 {
+  pmg_stale("pmg_pc_setup");
   if (!pc->mat) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup: no operator set");
   pmg_ctx ctx = pc->ctx;
   PMG_CUDA(cudaSetDevice(ctx->device));
@@ -723,6 +780,7 @@ int pmg_pc_setup(pmg_pc pc)
 
 int pmg_pc_view(pmg_pc pc, char *buf, size_t len)
 {
+  pmg_stale("pmg_pc_view");
   std::string s = "PC type: " + pc->type + "\n";
   char        t[256];
   if (!pc->is_setup) s += "  (not set up)\n";
@@ -756,6 +814,7 @@ int pmg_pc_view(pmg_pc pc, char *buf, size_t len)
 
 int pmg_pc_apply_richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero, int64_t *outits, int *reason)
 {
+  pmg_stale("pmg_pc_apply_richardson_dev");
   PMG_CUDA(cudaSetDevice(pc->ctx->device));
   PMG_TRY(richardson_dev(pc, b, y, its, guesszero));
   if (outits) *outits = its;
@@ -765,6 +824,7 @@ int pmg_pc_apply_richardson_dev(pmg_pc pc, const double *b, double *y, int64_t i
 
 int pmg_pc_apply_richardson(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero, int64_t *outits, int *reason)
 {
+  pmg_stale("pmg_pc_apply_richardson");
   pmg_ctx ctx = pc->ctx;
   if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
   PMG_CUDA(cudaSetDevice(ctx->device));
@@ -781,6 +841,7 @@ int pmg_pc_apply_richardson(pmg_pc pc, const double *b, double *y, int64_t its, 
 
 int pmg_pc_apply(pmg_pc pc, const double *x, double *y)
 {
+  pmg_stale("pmg_pc_apply");
   pmg_ctx ctx = pc->ctx;
   if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
   if (pc->type != "sorgibbs" && pc->type != "cholsampler") PMG_FAIL(PMG_ERR_SUP, "PCApply is only defined for sorgibbs and cholsampler (the reference sets ops->apply only there)");
@@ -803,6 +864,7 @@ int pmg_pc_apply(pmg_pc pc, const double *x, double *y)
 
 int pmg_pc_set_sample_callback(pmg_pc pc, pmg_sample_cb cb, void *cbctx, pmg_ctx_deleter deleter)
 {
+  pmg_stale("pmg_pc_set_sample_callback");
   if (pc->type == "gamgmc") { // src/pc_gamgmc.c:369-380: must pass a callback; NULL ctx/deleter are ignored, not cleared
     if (pc->cb && pc->deleter) pc->deleter(pc->cbctx);
     if (!cb) PMG_FAIL(PMG_ERR_SUP, "Must pass callback function");
@@ -820,6 +882,7 @@ int pmg_pc_set_sample_callback(pmg_pc pc, pmg_sample_cb cb, void *cbctx, pmg_ctx
 
 int pmg_pc_mcgibbs_set_omega(pmg_pc pc, double omega)
 {
+  pmg_stale("pmg_pc_mcgibbs_set_omega");
   if (pc->type != "mcgibbs") PMG_FAIL(PMG_ERR_ARG, "not a mcgibbs PC");
   pc->smp.gibbs.omega = omega; // lazily rebuilt at the next sample (omega_changed, src/pc_mcgibbs.c:275-276)
   pc->opts.erase("pc_mcgibbs_omega");
@@ -827,6 +890,7 @@ int pmg_pc_mcgibbs_set_omega(pmg_pc pc, double omega)
 }
 int pmg_pc_mcgibbs_set_sweep_type(pmg_pc pc, int type)
 {
+  pmg_stale("pmg_pc_mcgibbs_set_sweep_type");
   if (pc->type != "mcgibbs") PMG_FAIL(PMG_ERR_ARG, "not a mcgibbs PC");
   if (type != PMG_SOR_FORWARD_SWEEP && type != PMG_SOR_BACKWARD_SWEEP && type != PMG_SOR_SYMMETRIC_SWEEP) PMG_FAIL(PMG_ERR_SUP, "Only forward, backward and symmetric sweep supported");
   pc->smp.gibbs.type = type;
@@ -838,6 +902,7 @@ int pmg_pc_mcgibbs_set_sweep_type(pmg_pc pc, int type)
 
 int pmg_pc_gamgmc_set_levels(pmg_pc pc, int levels)
 {
+  pmg_stale("pmg_pc_gamgmc_set_levels");
   if (pc->type != "gamgmc") PMG_FAIL(PMG_ERR_ARG, "not a gamgmc PC");
   if (levels < 1) PMG_FAIL(PMG_ERR_ARG, "levels must be >= 1");
   pc->nlevels = levels;
@@ -848,11 +913,13 @@ int pmg_pc_gamgmc_set_levels(pmg_pc pc, int levels)
 }
 int pmg_pc_gamgmc_get_levels(pmg_pc pc, int *levels)
 {
+  pmg_stale("pmg_pc_gamgmc_get_levels");
   *levels = pc->nlevels;
   return PMG_OK;
 }
 int pmg_pc_gamgmc_set_interpolation(pmg_pc pc, int level, int64_t nf, int64_t nc, const int64_t *rowptr, const int32_t *col, const double *val)
 {
+  pmg_stale("pmg_pc_gamgmc_set_interpolation");
   if (pc->type != "gamgmc") PMG_FAIL(PMG_ERR_ARG, "not a gamgmc PC");
   if (level < 1) PMG_FAIL(PMG_ERR_ARG, "interpolation is defined for levels >= 1");
   if ((int)pc->lv.size() <= level) pc->lv.resize((size_t)level + 1);
@@ -868,6 +935,7 @@ int pmg_pc_gamgmc_set_interpolation(pmg_pc pc, int level, int64_t nf, int64_t nc
 }
 int pmg_pc_gamgmc_get_level_info(pmg_pc pc, int level, int64_t *n, int64_t *nnz, int *ncolors)
 {
+  pmg_stale("pmg_pc_gamgmc_get_level_info");
   if (!pc->is_setup || level < 0 || level >= pc->nlevels) PMG_FAIL(PMG_ERR_ARG, "bad level");
   LevelOp *op = pc->lv[level].op;
   if (n) *n = op->n();
@@ -877,6 +945,7 @@ int pmg_pc_gamgmc_get_level_info(pmg_pc pc, int level, int64_t *n, int64_t *nnz,
 }
 int pmg_pc_gamgmc_get_level_csr(pmg_pc pc, int level, int64_t *rowptr, int32_t *col, double *val)
 {
+  pmg_stale("pmg_pc_gamgmc_get_level_csr");
   if (!pc->is_setup || level < 0 || level >= pc->nlevels) PMG_FAIL(PMG_ERR_ARG, "bad level");
   const HostCsr *a = pc->lv[level].op->host_csr();
   if (!a) PMG_FAIL(PMG_ERR_SUP, "level %d is matrix-free", level);
@@ -888,6 +957,7 @@ int pmg_pc_gamgmc_get_level_csr(pmg_pc pc, int level, int64_t *rowptr, int32_t *
 
 int pmg_pc_set_noise_mode(pmg_pc pc, int mode)
 {
+  pmg_stale("pmg_pc_set_noise_mode");
   if (mode != PMG_NOISE_PHILOX && mode != PMG_NOISE_INJECTED && mode != PMG_NOISE_NONE) PMG_FAIL(PMG_ERR_ARG, "bad noise mode");
   pc->noise.mode = mode;
   pc->opts.erase("pc_b200_noise");
@@ -895,6 +965,7 @@ int pmg_pc_set_noise_mode(pmg_pc pc, int mode)
 }
 int pmg_pc_set_noise_tape(pmg_pc pc, const double *z, int64_t len)
 {
+  pmg_stale("pmg_pc_set_noise_tape");
   PMG_CUDA(cudaSetDevice(pc->ctx->device));
   PMG_TRY(pc->noise.tape.upload(z, (size_t)len, pc->ctx->stream));
   PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream));
@@ -906,6 +977,7 @@ int pmg_pc_set_noise_tape(pmg_pc pc, const double *z, int64_t len)
 }
 int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles)
 {
+  pmg_stale("pmg_pc_noise_per_sample");
   if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
   int64_t d = 0;
   if (pc->type == "gamgmc") {
@@ -918,6 +990,7 @@ int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles)
 
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z)
 {
+  pmg_stale("pmg_normal_fill");
   PMG_CUDA(cudaSetDevice(ctx->device));
   DevBuf<double> d;
   PMG_TRY(d.alloc((size_t)n));
@@ -930,6 +1003,7 @@ int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int
 
 int pmg_pc_last_stats(pmg_pc pc, double *ms, int64_t *launches, int64_t *updates)
 {
+  pmg_stale("pmg_pc_last_stats");
   if (ms) *ms = pc->last_ms;
   if (launches) *launches = pc->last_launches;
   if (updates) *updates = pc->last_updates;

@@ -441,8 +441,8 @@ def test_gamgmc_3d(pmg, ctx, orc):
     ("mcgibbs", {}, 400000),
     ("mcgibbs", {"-pc_mcgibbs_symmetric": ""}, 300000),
     ("sorgibbs", {}, 400000),
-    ("gamgmc", {"-gamgmc_pc_mg_levels": 3}, 200000),
-    ("cholsampler", {}, 200000),
+    ("gamgmc", {"-gamgmc_pc_mg_levels": 3}, 600000),
+    ("cholsampler", {}, 600000),
 ])
 def test_ex1_mean_convergence_device_rng(pmg, ctx, orc, pctype, opts, nsamp):
     """examples/ex1.c:83-135 acceptance check (rel. error of the sample mean <= 0.02) with the Philox
