@@ -11,12 +11,12 @@
  *   rander48  - the reference's default generator (statistics + CPU baseline timing)
  *
  * Philox normal definition (shared with parmgmc_b200/csrc/philox.cuh):
- *   pair p = global_row >> 1;  ctr = (lo32 p, hi32 p, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
+ *   quad q = global_row >> 2;  ctr = (lo32 q, hi32 q, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
  *   (w0,w1,w2,w3) = philox4x32-10(ctr, key)
- *   u1 = (((w1:w0) >> 11) + 0.5) 2^-53,  u2 = (((w3:w2) >> 11) + 0.5) 2^-53      both in (0,1)
- *   r = sqrt(-2 ln u1);  z[2p] = r cospi(2 u2);  z[2p+1] = r sinpi(2 u2)
+ *   rows 4q, 4q+1 use (u1,u2) = ((w0+0.5) 2^-32, (w1+0.5) 2^-32); rows 4q+2, 4q+3 use (w2, w3) likewise
+ *   r = sqrt(-2 ln u1);  even row: z = r cospi(2 u2);  odd row: z = r sinpi(2 u2)
  * which is the reference's pairing (i, i+1) -> (r cos, r sin) of parmgmc.c:106-109, made
- * independent of how rows are partitioned.
+ * independent of how rows are partitioned (one generator call serves four consecutive rows).
  */
 #include "oracle.h"
 #include <math.h>
@@ -60,18 +60,19 @@ static void sincospi_02(double x, double *s, double *c)
   }
 }
 
+/* the two normals of rows (2 pair, 2 pair + 1); pair = global_row >> 1 */
 static void philox_pair(uint64_t seed, uint64_t call, uint64_t pair, double *zc, double *zs)
 {
-  const uint32_t ctr[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
+  const uint64_t quad   = pair >> 1;
+  const uint32_t ctr[4] = {(uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t       w[4];
   orc_philox4x32_10(ctr, key, w);
-  const uint64_t a  = (((uint64_t)w[1] << 32) | w[0]) >> 11;
-  const uint64_t b  = (((uint64_t)w[3] << 32) | w[2]) >> 11;
-  const double   u1 = ((double)a + 0.5) * 0x1p-53;
-  const double   u2 = ((double)b + 0.5) * 0x1p-53;
-  const double   r  = sqrt(-2. * log(u1));
-  double         s, c;
+  const int    o  = (int)(pair & 1) * 2;
+  const double u1 = ((double)w[o] + 0.5) * 0x1p-32;
+  const double u2 = ((double)w[o + 1] + 0.5) * 0x1p-32;
+  const double r  = sqrt(-2. * log(u1));
+  double       s, c;
   sincospi_02(2. * u2, &s, &c);
   *zc = r * c;
   *zs = r * s;

@@ -14,30 +14,36 @@ namespace {
 constexpr int CHOL_MAX_N   = 4096;
 constexpr int CHOL_THREADS = 1024;
 
-// s[0..n) holds the rhs on entry and the solution on exit
-__device__ void trsv_forward(int n, const double *__restrict__ L, double *s)
+// s[0..n) holds the rhs on entry and the solution on exit.  blk is a 32x33 staging area for the diagonal
+// block, so that the 32 dependent steps of a block read shared memory instead of waiting on L2 each time.
+__device__ void trsv_forward(int n, const double *__restrict__ L, double *s, double (*blk)[33])
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int kb = 0; kb < n; kb += 32) {
+    const int kmax = min(32, n - kb);
+    {
+      const int r = tid & 31, c = tid >> 5; // 1024 threads: one block entry each, column-major read is coalesced
+      if (r < kmax && c < kmax) blk[r][c] = L[(kb + r) + (size_t)(kb + c) * n];
+    }
+    __syncthreads();
     if (warp == 0) {
       const int i  = kb + lane;
       double    si = i < n ? s[i] : 0.0;
-      const int kmax = min(32, n - kb);
       for (int k = 0; k < kmax; ++k) {
-        const int kk = kb + k;
-        double    xk = 0.0;
-        if (lane == k) xk = si / L[kk + (size_t)kk * n];
+        double xk = 0.0;
+        if (lane == k) xk = si / blk[k][k];
         xk = __shfl_sync(0xffffffffu, xk, k);
         if (lane == k) si = xk;
-        else if (lane > k && i < n) si = fma(-L[i + (size_t)kk * n], xk, si);
+        else if (lane > k && i < n) si = fma(-blk[lane][k], xk, si);
       }
       if (i < n) s[i] = si;
     }
     __syncthreads();
-    const int kmax = min(32, n - kb);
     for (int i = kb + 32 + tid; i < n; i += blockDim.x) {
-      double si = s[i];
-      for (int k = 0; k < kmax; ++k) si = fma(-L[i + (size_t)(kb + k) * n], s[kb + k], si);
+      double        si = s[i];
+      const double *Lp = L + i + (size_t)kb * n;
+#pragma unroll 8
+      for (int k = 0; k < kmax; ++k) si = fma(-Lp[(size_t)k * n], s[kb + k], si);
       s[i] = si;
     }
     __syncthreads();
@@ -45,29 +51,36 @@ __device__ void trsv_forward(int n, const double *__restrict__ L, double *s)
 }
 
 // LT[i + k n] = L[k + i n]
-__device__ void trsv_backward(int n, const double *__restrict__ L, const double *__restrict__ LT, double *s)
+__device__ void trsv_backward(int n, const double *__restrict__ L, const double *__restrict__ LT, double *s, double (*blk)[33])
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = (n + 31) / 32;
-  for (int blk = nb - 1; blk >= 0; --blk) {
-    const int kb = blk * 32, kmax = min(32, n - kb);
+  (void)L;
+  for (int b = nb - 1; b >= 0; --b) {
+    const int kb = b * 32, kmax = min(32, n - kb);
+    {
+      const int r = tid & 31, c = tid >> 5;
+      if (r < kmax && c < kmax) blk[r][c] = LT[(kb + r) + (size_t)(kb + c) * n]; // = L[kb+c, kb+r]
+    }
+    __syncthreads();
     if (warp == 0) {
       const int i  = kb + lane;
       double    si = i < n ? s[i] : 0.0;
       for (int k = kmax - 1; k >= 0; --k) {
-        const int kk = kb + k;
-        double    xk = 0.0;
-        if (lane == k) xk = si / L[kk + (size_t)kk * n];
+        double xk = 0.0;
+        if (lane == k) xk = si / blk[k][k];
         xk = __shfl_sync(0xffffffffu, xk, k);
         if (lane == k) si = xk;
-        else if (lane < k) si = fma(-LT[i + (size_t)kk * n], xk, si);
+        else if (lane < k) si = fma(-blk[lane][k], xk, si);
       }
       if (i < n) s[i] = si;
     }
     __syncthreads();
     for (int i = tid; i < kb; i += blockDim.x) {
-      double si = s[i];
-      for (int k = kmax - 1; k >= 0; --k) si = fma(-LT[i + (size_t)(kb + k) * n], s[kb + k], si);
+      double        si = s[i];
+      const double *Lp = LT + i + (size_t)kb * n;
+#pragma unroll 8
+      for (int k = kmax - 1; k >= 0; --k) si = fma(-Lp[(size_t)k * n], s[kb + k], si);
       s[i] = si;
     }
     __syncthreads();
@@ -78,14 +91,15 @@ __device__ void trsv_backward(int n, const double *__restrict__ L, const double 
 __global__ void __launch_bounds__(CHOL_THREADS) chol_sample_kernel(int n, const double *__restrict__ L, const double *__restrict__ LT, const double *__restrict__ in, double *__restrict__ out, NoiseArgs na, int mode)
 {
   __shared__ double s[CHOL_MAX_N];
+  __shared__ double blk[32][33];
   for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = in[i];
   __syncthreads();
-  if (mode & 1) trsv_forward(n, L, s);
+  if (mode & 1) trsv_forward(n, L, s, blk);
   if (mode & 2) {
     if (na.mode != PMG_NOISE_NONE)
       for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = __dadd_rn(s[i], noise_value(na, i));
     __syncthreads();
-    trsv_backward(n, L, LT, s);
+    trsv_backward(n, L, LT, s, blk);
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = s[i];
 }

@@ -172,6 +172,16 @@ struct LevelOp {
   virtual int  set_coloring_auto(int policy) = 0;
   virtual void describe(std::string &out) = 0;
   virtual bool structured(int &dim, int64_t dims[3]) const { (void)dim; (void)dims; return false; }
+  virtual bool matrix_free() const { return false; } // true: hierarchy is built on the device (stencil_op.cu)
+  // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
+  // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
+  virtual bool fused_ok() const { return false; }
+  virtual int  fused_sweep(int dir, const SweepCoeffs &c, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc)
+  {
+    (void)dir; (void)c; (void)b; (void)xin; (void)xout; (void)na; (void)coarse; (void)xc; (void)bc;
+    pmg_set_error("fused sweep not available for this operator");
+    return PMG_ERR_SUP;
+  }
 };
 
 // grid transfer between level l (fine) and l-1 (coarse): SURVEY Appendix A.3

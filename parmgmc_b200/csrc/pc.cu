@@ -287,6 +287,7 @@ struct MgLevel {
   bool                      has_interp = false;
   LevelSampler              smp;
   DevBuf<double>            b, x, r;
+  DevBuf<double>            x2; // second iterate buffer of the fused (out-of-place) sweeps
 };
 
 struct pmg_pc_s {
@@ -305,6 +306,8 @@ struct pmg_pc_s {
   int                  nlevels = 0;
   std::vector<MgLevel> lv;
   DevBuf<double>       w, work;
+  bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
+  DevBuf<double>       scratch;             // out-of-place partner of y for the fused sweeps
   // staging
   DevBuf<double> d_b, d_y;
   double        *h_pinned = nullptr;
@@ -322,7 +325,7 @@ struct pmg_pc_s {
     lv.clear();
     smp = LevelSampler();
     noise.tape.release();
-    w.release(); work.release(); d_b.release(); d_y.release();
+    w.release(); work.release(); d_b.release(); d_y.release(); scratch.release();
     pmg_ctx_release(ctx);
   }
   bool        has(const std::string &k) const { return opts.count(k) != 0; }
@@ -428,6 +431,61 @@ static int mg_apply(pmg_pc pc, const double *b, double *x)
   return mg_cycle(pc, pc->nlevels - 1, b, x);
 }
 
+// the directional sweeps one level-KSP solve performs, with a fresh noise block each (src/pc_mcgibbs.c:168-182)
+static int sweep_dirs(const LevelSampler &s, std::vector<int> &dirs)
+{
+  dirs.clear();
+  for (int it = 0; it < s.its; ++it) {
+    if (s.gibbs.type == PMG_SOR_SYMMETRIC_SWEEP) {
+      dirs.push_back(PMG_SOR_FORWARD_SWEEP);
+      dirs.push_back(PMG_SOR_BACKWARD_SWEEP);
+    } else dirs.push_back(s.gibbs.type == PMG_SOR_BACKWARD_SWEEP ? PMG_SOR_BACKWARD_SWEEP : PMG_SOR_FORWARD_SWEEP);
+  }
+  return 0;
+}
+
+// The same V-cycle applied directly to (b, x): because every stage is affine in (b, x) and acts on the residual,
+// cycle(b, x) == x + cycle(b - A x, 0) (hard part 8), so the outer w = b - A y / y += work passes of
+// src/pc_gamgmc.c:253-256 disappear.  Levels whose operator has a fused streaming sweep run pre-smoothing + residual +
+// restriction in one pass over memory and prolongation + post-smoothing in another.
+static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool zero_guess)
+{
+  pmg_ctx  ctx = pc->ctx;
+  MgLevel &v   = pc->lv[l];
+  const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_ok() && v.x2.p;
+  if (!fused) {
+    if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
+    PMG_TRY(run_level_sampler(pc, v.smp, b, x));
+    if (l == 0) return 0;
+    MgLevel &c = pc->lv[l - 1];
+    PMG_TRY(v.op->residual(b, x, v.r.p));
+    PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
+    PMG_TRY(v.P->prolong_add(c.x.p, x));
+    return run_level_sampler(pc, v.smp, b, x);
+  }
+  MgLevel         &c = pc->lv[l - 1];
+  std::vector<int> dirs;
+  sweep_dirs(v.smp, dirs);
+  PMG_TRY(v.smp.gibbs.ensure());
+  double   *cur = x, *oth = v.x2.p;
+  NoiseArgs na;
+  for (size_t s = 0; s < dirs.size(); ++s) { // pre-smoothing; the last sweep also forms the coarse right-hand side
+    const bool last = s + 1 == dirs.size();
+    PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, (zero_guess && s == 0) ? nullptr : cur, oth, na, c.op, nullptr, last ? c.b.p : nullptr));
+    std::swap(cur, oth);
+  }
+  PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
+  for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c
+    PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? c.x.p : nullptr, nullptr));
+    std::swap(cur, oth);
+  }
+  if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->n() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
 static int gamgmc_setup(pmg_pc pc)
 {
   pmg_ctx  ctx  = pc->ctx;
@@ -470,7 +528,7 @@ static int gamgmc_setup(pmg_pc pc)
   for (int l = 1; l < L; ++l) all_user &= pc->lv[l].has_interp;
   if (L > 1 && !all_user && !structured) PMG_FAIL(PMG_ERR_SUP, "gamgmc: operator is not structured; supply an interpolation for every level 1..%d", L - 1);
 
-  if (L > 1 && !all_user && structured && !fine->host_csr()) {
+  if (L > 1 && !all_user && structured && fine->matrix_free()) {
     // matrix-free structured hierarchy built on the device
     std::vector<std::unique_ptr<LevelOp>>  ops;
     std::vector<std::unique_ptr<Transfer>> trs;
@@ -525,7 +583,11 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(v.x.alloc(n));
     }
     if (l > 0) PMG_TRY(v.r.alloc(n));
+    if (l > 0 && v.op->fused_ok() && v.smp.kind != KIND_CHOL) PMG_TRY(v.x2.alloc(n));
   }
+  const std::string cyc = pc->get("pc_b200_cycle", "direct");
+  if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
+  pc->direct_cycle = cyc == "direct";
   const size_t nf = (size_t)fine->n();
   PMG_TRY(pc->w.alloc(nf));
   PMG_TRY(pc->work.alloc(nf));
@@ -571,7 +633,9 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
       b = pc->d_b.p;
     }
     for (int64_t it = 0; it < its; ++it) {
-      if (it == 0 && guesszero) {
+      if (pc->direct_cycle) {
+        PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, b, y, it == 0 && guesszero));
+      } else if (it == 0 && guesszero) {
         PMG_TRY(mg_apply(pc, b, y));
       } else {
         PMG_TRY(A->residual(b, y, pc->w.p));             // w = b - A y
@@ -600,9 +664,30 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
     }
   } else { // mcgibbs: src/pc_mcgibbs.c:167-184; sorgibbs: src/pc_sorgibbs.c:125-129 (running sample_index from 0)
     if (pc->type == "sorgibbs") pc->sample_index = 0;
-    for (int64_t it = 0; it < its; ++it) {
-      PMG_TRY(pc->smp.gibbs.sample(pc->noise, b, y));
-      PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
+    LevelOp *op = pc->smp.gibbs.op;
+    if (op->fused_ok() && pc->scratch.p) { // one fused pass per directional sweep, ping-pong between y and scratch
+      std::vector<int> dirs;
+      LevelSampler     one;
+      one.its        = 1;
+      one.gibbs.type = pc->smp.gibbs.type;
+      sweep_dirs(one, dirs);
+      PMG_TRY(pc->smp.gibbs.ensure());
+      double   *cur = y, *oth = pc->scratch.p;
+      NoiseArgs na;
+      for (int64_t it = 0; it < its; ++it) {
+        for (int d : dirs) {
+          PMG_TRY(pc->noise.next(ctx, n, op->row0(), na));
+          PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, b, cur, oth, na, nullptr, nullptr, nullptr));
+          std::swap(cur, oth);
+        }
+        PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, cur));
+      }
+      if (cur != y) PMG_CUDA(cudaMemcpyAsync(y, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      for (int64_t it = 0; it < its; ++it) {
+        PMG_TRY(pc->smp.gibbs.sample(pc->noise, b, y));
+        PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
+      }
     }
   }
   PMG_CUDA(cudaEventRecord(pc->ev1, ctx->stream));
@@ -772,6 +857,7 @@ int pmg_pc_setup(pmg_pc pc)
     }
     PMG_TRY(apply_coloring_policy(pc, pc->mat->op.get(), true));
     PMG_TRY(setup_level_sampler(ctx, pc->smp, pc->mat->op.get()));
+    if (pc->smp.kind != KIND_CHOL && pc->mat->op->fused_ok()) PMG_TRY(pc->scratch.alloc((size_t)pc->mat->op->n()));
   }
   PMG_TRY(pc_alloc_staging(pc));
   pc->is_setup = true;

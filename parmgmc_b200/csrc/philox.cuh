@@ -6,15 +6,17 @@
 // rows are partitioned over threads, colours or GPUs.
 //
 // Definition (must stay identical to oracle/noise.c, which is only the checker):
-//   pair p = global_row >> 1;  ctr = (lo32 p, hi32 p, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
+//   quad q = global_row >> 2;  ctr = (lo32 q, hi32 q, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
 //   (w0..w3) = philox4x32-10(ctr, key)
-//   u1 = (((w1:w0) >> 11) + 0.5) 2^-53,   u2 = (((w3:w2) >> 11) + 0.5) 2^-53
-//   r = sqrt(-2 ln u1);   z[2p] = r cospi(2 u2);   z[2p+1] = r sinpi(2 u2)
-// i.e. the reference's Box-Muller pairing (i, i+1) -> (r cos, r sin) of src/parmgmc.c:100-110.
+//   rows 4q, 4q+1 use (u1,u2) = ((w0+0.5) 2^-32, (w1+0.5) 2^-32); rows 4q+2, 4q+3 use (w2, w3) likewise
+//   r = sqrt(-2 ln u1);  even row: z = r cospi(2 u2);  odd row: z = r sinpi(2 u2)
+// i.e. the reference's Box-Muller pairing (i, i+1) -> (r cos, r sin) of src/parmgmc.c:100-110; one generator
+// call serves four consecutive rows, which is what a thread of the fused sweeps owns.
 #pragma once
 #include <cstdint>
 
 #include "common.hpp"
+#include "fastnormal.cuh"
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
 {
@@ -32,30 +34,33 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-// both normals of pair p
-__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t call, uint64_t pair, double &zc, double &zs)
+// Box-Muller on two 32-bit words: (r cos, r sin); the arithmetic is fastnormal.cuh's in every kernel, so all device
+// paths produce bit-identical normals
+__device__ __forceinline__ void box_muller_32(uint32_t wa, uint32_t wb, double &zc, double &zs)
 {
-  uint32_t w0, w1, w2, w3;
-  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), w0, w1, w2, w3);
-  const uint64_t a  = (((uint64_t)w1 << 32) | w0) >> 11;
-  const uint64_t b  = (((uint64_t)w3 << 32) | w2) >> 11;
-  const double   u1 = __dmul_rn(__dadd_rn((double)a, 0.5), 0x1p-53);
-  const double   u2 = __dmul_rn(__dadd_rn((double)b, 0.5), 0x1p-53);
-  const double   r  = sqrt(__dmul_rn(-2.0, log(u1)));
-  double         s, c;
-  sincospi(__dmul_rn(2.0, u2), &s, &c);
-  zc = __dmul_rn(r, c);
-  zs = __dmul_rn(r, s);
+  fastnormal::box_muller(fastnormal::global_tables(), wa, wb, zc, zs);
 }
 
-// z of one local row
+// the four normals of rows 4q .. 4q+3
+__device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t call, uint64_t quad, double z[4])
+{
+  uint32_t w0, w1, w2, w3;
+  philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), w0, w1, w2, w3);
+  box_muller_32(w0, w1, z[0], z[1]);
+  box_muller_32(w2, w3, z[2], z[3]);
+}
+
+// z of one local row (per-row kernels: only one of the four values is used)
 __device__ __forceinline__ double noise_value(const NoiseArgs &na, int64_t local_row)
 {
   if (na.mode == PMG_NOISE_INJECTED) return na.tape[local_row];
   if (na.mode == PMG_NOISE_NONE) return 0.0;
   const uint64_t g = (uint64_t)(na.row0 + local_row);
-  double         zc, zs;
-  philox_normal_pair(na.seed, na.call, g >> 1, zc, zs);
+  uint32_t       w0, w1, w2, w3;
+  philox4x32_10((uint32_t)(g >> 2), (uint32_t)(g >> 34), (uint32_t)na.call, (uint32_t)(na.call >> 32), (uint32_t)na.seed, (uint32_t)(na.seed >> 32), w0, w1, w2, w3);
+  double zc, zs;
+  if (g & 2) box_muller_32(w2, w3, zc, zs);
+  else box_muller_32(w0, w1, zc, zs);
   return (g & 1) ? zs : zc;
 }
 

