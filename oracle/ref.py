@@ -1,0 +1,103 @@
+"""ctypes front-end of oracle/_ref/libparmgmc_ref.so: the reference's OWN mc_sor.c / pc_mcgibbs.c / parmgmc.c,
+compiled unmodified from /root/reference against oracle/petsc_stub (see oracle/Makefile target `ref`).
+
+TEST INFRASTRUCTURE ONLY: used by tests/test_oracle_ref.py to pin the oracle restatement, and by
+tests/golden/make_golden.py to write the committed golden vectors.  Never imported by parmgmc_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libparmgmc_ref.so")
+_lib = None
+
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+
+def available() -> bool:
+    """True when the library exists or can be built (the reference tree is present in this container only)."""
+    if os.path.exists(_PATH):
+        return True
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libparmgmc_ref.so is not built (needs /root/reference)")
+        L = C.CDLL(_PATH)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_mcsor_seq.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, f64p, f64p]
+        L.ref_mcsor_num_colors.argtypes = [C.c_int, i32p, i32p, f64p, C.POINTER(C.c_int)]
+        L.ref_mcsor_mpi.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, i32p, C.c_int, u16p, C.c_double, C.c_int, C.c_int, f64p, f64p]
+        L.ref_mcgibbs_richardson.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_longlong, C.c_int, C.c_void_p, f64p, CB, C.c_void_p]
+        L.ref_normal_fill.argtypes = [C.c_longlong, C.c_int, C.c_int, f64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError(f"reference call failed ({rc}): {lib().ref_last_error().decode()}")
+
+
+def _csr32(A):
+    return A.n, np.ascontiguousarray(A.rowptr, np.int32), np.ascontiguousarray(A.col, np.int32), A.val
+
+
+def mcsor_apply(A, b, y, coloring=None, omega=1.0, sweep=1, nsweeps=1):
+    """MCSORCreate/SetUp/SetOmega/SetSweepType + nsweeps x MCSORApply (src/mc_sor.c:216-296) on one rank, in place on y.
+    coloring=None: the reference's own 1-rank colouring (one colour)."""
+    n, rp, cj, va = _csr32(A)
+    col16 = None if coloring is None else np.ascontiguousarray(coloring.color, np.uint16)
+    _check(lib().ref_mcsor_seq(n, rp, cj, va, 0 if coloring is None else coloring.ncolors, None if col16 is None else col16.ctypes.data, omega, sweep, nsweeps,
+                               np.ascontiguousarray(b, np.float64), y))
+    return y
+
+
+def mcsor_num_colors(A) -> int:
+    n, rp, cj, va = _csr32(A)
+    out = C.c_int(0)
+    _check(lib().ref_mcsor_num_colors(n, rp, cj, va, C.byref(out)))
+    return out.value
+
+
+def mcsor_apply_mpi(A, rowstart, coloring, b, y, omega=1.0, sweep=1, nsweeps=1):
+    """MCSORApply_MPIAIJ (src/mc_sor.c:298-381) on len(rowstart)-1 emulated ranks, in place on the global y."""
+    n, rp, cj, va = _csr32(A)
+    rs = np.ascontiguousarray(rowstart, np.int32)
+    _check(lib().ref_mcsor_mpi(n, rp, cj, va, rs.size - 1, rs, coloring.ncolors, np.ascontiguousarray(coloring.color, np.uint16), omega, sweep, nsweeps,
+                               np.ascontiguousarray(b, np.float64), y))
+    return y
+
+
+def mcgibbs_richardson(A, b, y, its, seed, coloring=None, omega=None, sweep_opt="", callback=None):
+    """PCSetFromOptions + PCSetUp + PCApplyRichardson of PCMCGIBBS (src/pc_mcgibbs.c:155-251), noise from the library's
+    global rander48 stream through VecSetRandomStandardNormal (src/parmgmc.c:100-110)."""
+    n, rp, cj, va = _csr32(A)
+    col16 = None if coloring is None else np.ascontiguousarray(coloring.color, np.uint16)
+    bptr = None if b is None else np.ascontiguousarray(b, np.float64).ctypes.data
+    if callback is None:
+        cbf = C.cast(None, CB)
+    else:
+        cbf = CB(lambda it, yp, m, _c: int(callback(int(it), np.ctypeslib.as_array(yp, shape=(m,))) or 0))
+    _check(lib().ref_mcgibbs_richardson(n, rp, cj, va, 0 if coloring is None else coloring.ncolors, None if col16 is None else col16.ctypes.data,
+                                        b"" if omega is None else repr(float(omega)).encode(), sweep_opt.encode(), seed, its, bptr, y, cbf, None))
+    return y
+
+
+def normal_fill(seed, n, ncalls=1):
+    out = np.empty(n * ncalls, np.float64)
+    _check(lib().ref_normal_fill(seed, n, ncalls, out))
+    return out
