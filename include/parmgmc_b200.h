@@ -112,7 +112,9 @@ int pmg_mcsor_apply_dev(pmg_mcsor mc, const double *b_dev, double *y_dev);
  * reference's option keys, e.g.
  *   pmg_pc_set_option(pc, "-pc_mcgibbs_omega", "1.2"); pmg_pc_set_option(pc, "-pc_mcgibbs_symmetric", "");
  *   pmg_pc_set_option(pc, "-gamgmc_pc_mg_levels", "10"); pmg_pc_set_option(pc, "-gamgmc_mg_levels_ksp_max_it", "2");
- * plus "-pc_b200_coloring greedy|lexicographic|parity" and "-pc_b200_noise philox|injected|none". */
+ * plus "-pc_b200_coloring greedy|lexicographic|parity", "-pc_b200_noise philox|injected|none",
+ * "-pc_b200_cycle direct|literal" and "-pc_b200_grid nx,ny[,nz]" (grid of an assembled operator, what PCSetDM tells the
+ * reference's geometric PCMG). */
 typedef int (*pmg_sample_cb)(int64_t it, const double *y_host, int64_t n, void *ctx);
 typedef int (*pmg_ctx_deleter)(void *ctx);
 

@@ -115,6 +115,15 @@ PetscErrorCode PetscOptionsGetReal(PetscOptions o, const char *pre, const char *
   if (set) *set = s ? PETSC_TRUE : PETSC_FALSE;
   return 0;
 }
+PetscErrorCode PetscOptionsGetString(PetscOptions o, const char *pre, const char *name, char *buf, size_t len, PetscBool *set)
+{
+  (void)o;
+  (void)pre;
+  const char *s = opt_find(name);
+  if (s) snprintf(buf, len, "%s", s);
+  if (set) *set = s ? PETSC_TRUE : PETSC_FALSE;
+  return 0;
+}
 PetscErrorCode PetscOptionsRangeReal(const char *opt, const char *text, const char *man, PetscReal cur, PetscReal *v, PetscBool *set, PetscReal lo, PetscReal hi)
 {
   (void)text;

@@ -125,6 +125,7 @@ typedef struct _p_PetscOptionItems *PetscOptionItems;
 struct _p_PetscObject {
   MPI_Comm comm;
   int      refct;
+  const char *prefix;
   void (*composed)(void); /* the one composed function a PC carries ("PCSetSampleCallback_C") */
 };
 MPI_Comm       PetscObjectComm(PetscObject o);
@@ -148,6 +149,7 @@ PetscErrorCode PetscLogEventRegister(const char *name, PetscClassId id, PetscLog
 /* options database: key/value table filled by the driver (PetscStubOptionsSet) */
 PetscErrorCode PetscStubOptionsSet(const char *key, const char *value);
 PetscErrorCode PetscStubOptionsClear(void);
+PetscErrorCode PetscOptionsGetString(PetscOptions o, const char *pre, const char *name, char *buf, size_t len, PetscBool *set);
 PetscErrorCode PetscOptionsGetReal(PetscOptions o, const char *pre, const char *name, PetscReal *v, PetscBool *set);
 #define PetscOptionsHeadBegin(obj, title) (void)(obj)
 #define PetscOptionsHeadEnd() (void)0

@@ -499,7 +499,15 @@ static int gamgmc_setup(pmg_pc pc)
   if (pc->has("gamgmc_pc_mg_levels")) L = std::atoi(pc->get("gamgmc_pc_mg_levels", "0").c_str());
   int     dim = 0;
   int64_t dims[3] = {0, 0, 0};
-  const bool structured = fine->structured(dim, dims);
+  bool structured = fine->structured(dim, dims);
+  if (!structured && pc->has("pc_b200_grid")) { // the grid of an assembled operator (what PCSetDM tells the reference, src/pc_gamgmc.c:290-294)
+    long long g[3] = {1, 1, 1};
+    const int k    = std::sscanf(pc->get("pc_b200_grid", "").c_str(), "%lld,%lld,%lld", &g[0], &g[1], &g[2]);
+    if (k < 2 || g[0] * g[1] * g[2] != fine->n()) PMG_FAIL(PMG_ERR_ARG, "-pc_b200_grid nx,ny[,nz]: must multiply to the operator size %lld", (long long)fine->n());
+    dim = k;
+    for (int q = 0; q < 3; ++q) dims[q] = g[q];
+    structured = true;
+  }
   if (L <= 0) { // automatic depth: coarsen until the coarsest grid is at most 17 nodes per direction
     if (!structured) PMG_FAIL(PMG_ERR_ORDER, "gamgmc: set the number of levels (-gamgmc_pc_mg_levels / pmg_pc_gamgmc_set_levels)");
     L = 1;

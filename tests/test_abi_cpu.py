@@ -50,3 +50,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".hpp", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "liboracle" not in txt and "import oracle" not in txt and "oracle/oracle.h" not in txt.replace("FP contract: oracle/oracle.h", ""), f
+
+
+def test_petsc_shim_builds_and_fails_loudly_without_device():
+    """shim/petsc: the PETSc-facing registration layer + an ex1-shaped C host program link against the C ABI
+    (PETSc objects from oracle/petsc_stub, since PETSc is not in this image); without a GPU the program must stop
+    with the no-CPU-fallback error instead of computing anything."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(pmg.HEADER_PATH))
+    shim = os.path.join(root, "shim", "petsc")
+    subprocess.check_call(["make", "-s", "-C", shim])
+    exe = os.path.join(shim, "build", "host_ex1")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is tests/test_shim_host.py")
+    r = subprocess.run([exe, "mcgibbs", "10"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr

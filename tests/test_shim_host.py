@@ -1,0 +1,33 @@
+"""The drop-in boundary exercised from C: shim/petsc/host_ex1.c is an examples/ex1.c-shaped host program that only uses
+ParMGMCInitialize, -pc_type style PC creation, option keys, PCSetSampleCallback and PCApplyRichardson; underneath it the
+PETSc shim forwards to libparmgmc_b200.so.  Acceptance is the reference's own: relative error of the sample mean <= 0.02
+(examples/ex1.c:20-44, :135)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "shim", "petsc")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    subprocess.check_call(["make", "-s", "-C", SHIM])
+    return os.path.join(SHIM, "build", "host_ex1")
+
+
+@pytest.mark.parametrize("args", [
+    ["mcgibbs", "20000"],                                                  # examples/ex1.c:20
+    ["mcgibbs", "20000", "-pc_mcgibbs_backward", "", "-pc_mcgibbs_omega", "1.2"],   # :21
+    ["mcgibbs", "20000", "-pc_mcgibbs_symmetric", ""],                     # :22
+    ["sorgibbs", "20000"],                                                 # :23
+    ["cholsampler", "20000"],                                              # :26
+    ["gamgmc", "20000", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "2", "-pc_b200_grid", "9,9"],  # :41
+    ["gamgmc", "20000", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "3", "-pc_b200_grid", "9,9", "-gamgmc_mg_coarse_pc_type", "mcgibbs", "-gamgmc_mg_coarse_ksp_max_it", "2"],  # :44
+])
+def test_ex1_shaped_c_host_program(exe, args):
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "relative mean error" in r.stdout
