@@ -163,10 +163,9 @@ def run_b200(args):
     n = args.n
     if world == 1:
         ny, slab = n, None
-    else:
+    else:  # weak scaling in y: one (n-1)-row slab per rank, the last rank also owns the closing row
         ny = (n - 1) * world + 1
-        lo = rank * (n - 1)
-        slab = (lo, lo + (n - 1) + (1 if rank == world - 1 else 0))
+        slab = pmg.partition_slabs(ny, world)[rank]
     mat = pmg.Mat.laplace(ctx, 2, n, ny, 1, args.kappa, slab=slab)
     pc = pmg.PC(ctx, "gamgmc")
     pc.set_operator(mat)
@@ -272,7 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4097)
-    ap.add_argument("--levels", type=int, default=9)
+    ap.add_argument("--levels", type=int, default=0, help="0: 9 + log2(gpus), i.e. the coarsest grid stays about 17 nodes wide in y as the grid grows")
     ap.add_argument("--kappa", type=float, default=1.0)
     ap.add_argument("--samples-per-step", type=int, default=5)
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
@@ -280,6 +279,8 @@ def main():
     ap.add_argument("--bytes-per-update", type=float, default=32.0, help="algorithmic bytes per DOF update of the fine sweep (DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.levels <= 0:
+        args.levels = 9 + max(0, (max(1, args.gpus) - 1).bit_length())
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

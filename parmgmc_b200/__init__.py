@@ -211,6 +211,17 @@ class Context:
             pass
 
 
+def partition_slabs(n_units: int, nranks: int, align: int = 2):
+    """Contiguous slabs [lo, hi) of the slowest grid dimension, one per rank, in rank order: the row-block ownership
+    ranges PETSc gives an MPIAIJ matrix (src/mc_sor.c:308-310), with every cut on a multiple of `align` so that coarse
+    unit J and fine unit 2J have the same owner on the first coarsenings."""
+    if nranks < 1 or n_units < nranks * align:
+        raise ValueError(f"cannot split {n_units} units over {nranks} ranks with alignment {align}")
+    per = (n_units // nranks) // align * align
+    cuts = [r * per for r in range(nranks)] + [n_units]
+    return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
+
+
 def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib().pmg_comm_unique_id(buf))

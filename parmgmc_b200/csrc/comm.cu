@@ -18,6 +18,7 @@ struct NcclApi {
   decltype(&ncclRecv)           Recv           = nullptr;
   decltype(&ncclGroupStart)     GroupStart     = nullptr;
   decltype(&ncclGroupEnd)       GroupEnd       = nullptr;
+  decltype(&ncclAllGather)      AllGather      = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   bool                          ok             = false;
 };
@@ -30,9 +31,9 @@ NcclApi &nccl()
     if (!h) return a;
 #define PMG_SYM(name) a.name = (decltype(a.name))dlsym(h, "nccl" #name)
     PMG_SYM(GetUniqueId); PMG_SYM(CommInitRank); PMG_SYM(CommDestroy); PMG_SYM(Send); PMG_SYM(Recv);
-    PMG_SYM(GroupStart); PMG_SYM(GroupEnd); PMG_SYM(GetErrorString);
+    PMG_SYM(GroupStart); PMG_SYM(GroupEnd); PMG_SYM(GetErrorString); PMG_SYM(AllGather);
 #undef PMG_SYM
-    a.ok = a.GetUniqueId && a.CommInitRank && a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetErrorString && a.AllGather;
     return a;
   }();
   return api;
@@ -104,6 +105,43 @@ int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, cons
   if (ctx->rank < ctx->nranks - 1 && count_hi) {
     PMG_NCCL(nccl().Send(send_hi, count_hi, ncclDouble, ctx->rank + 1, comm, stream));
     PMG_NCCL(nccl().Recv(recv_hi, count_hi, ncclDouble, ctx->rank + 1, comm, stream));
+  }
+  PMG_NCCL(nccl().GroupEnd());
+  return 0;
+}
+
+// every rank contributes `count` int64 values; all_host receives nranks*count values in rank order (set-up only: blocking)
+int comm_allgather_i64(pmg_ctx ctx, const int64_t *local_host, int count, int64_t *all_host)
+{
+  if (ctx->nranks == 1) {
+    std::memcpy(all_host, local_host, sizeof(int64_t) * (size_t)count);
+    return 0;
+  }
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  if (!comm) PMG_FAIL(PMG_ERR_COMM, "communicator not initialised");
+  DevBuf<int64_t> in, out;
+  PMG_TRY(in.upload(local_host, (size_t)count, ctx->stream));
+  PMG_TRY(out.alloc((size_t)count * (size_t)ctx->nranks));
+  PMG_NCCL(nccl().AllGather(in.p, out.p, (size_t)count, ncclInt64, comm, ctx->stream));
+  PMG_CUDA(cudaMemcpyAsync(all_host, out.p, sizeof(int64_t) * (size_t)count * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// variable-size all-gather: rank r contributes counts[r] doubles (its own block is `send`), placed at recv + displs[r]
+// on every rank.  One grouped send/recv round; the own block is a device copy.
+int comm_allgatherv(pmg_ctx ctx, const double *send, double *recv, const int64_t *counts, const int64_t *displs, cudaStream_t stream)
+{
+  const int me = ctx->rank;
+  if (counts[me] && recv + displs[me] != send) PMG_CUDA(cudaMemcpyAsync(recv + displs[me], send, sizeof(double) * (size_t)counts[me], cudaMemcpyDeviceToDevice, stream));
+  if (ctx->nranks == 1) return 0;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  if (!comm) PMG_FAIL(PMG_ERR_COMM, "communicator not initialised");
+  PMG_NCCL(nccl().GroupStart());
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == me) continue;
+    if (counts[me]) PMG_NCCL(nccl().Send(send, (size_t)counts[me], ncclDouble, r, comm, stream));
+    if (counts[r]) PMG_NCCL(nccl().Recv(recv + displs[r], (size_t)counts[r], ncclDouble, r, comm, stream));
   }
   PMG_NCCL(nccl().GroupEnd());
   return 0;

@@ -35,7 +35,7 @@ static void pmg_stale(const char *where)
 }
 
 int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op);
-int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine, int nlevels, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers);
+int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine, int nlevels, int64_t replicate_below, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers);
 
 void pmg_ctx_retain(pmg_ctx ctx) { ctx->refs++; }
 void pmg_ctx_release(pmg_ctx ctx)
@@ -540,7 +540,9 @@ static int gamgmc_setup(pmg_pc pc)
     // matrix-free structured hierarchy built on the device
     std::vector<std::unique_ptr<LevelOp>>  ops;
     std::vector<std::unique_ptr<Transfer>> trs;
-    PMG_TRY(build_structured_hierarchy(ctx, fine, L, ops, trs));
+    // levels of at most this many nodes (globally) are held in full by every rank instead of being split into slabs
+    const int64_t repl = std::atoll(pc->get("pc_b200_replicate_below", "4194304").c_str());
+    PMG_TRY(build_structured_hierarchy(ctx, fine, L, repl, ops, trs));
     for (int l = L - 1; l >= 1; --l) {
       pc->lv[l].P         = std::move(trs[(size_t)l]);
       pc->lv[l - 1].owned = std::move(ops[(size_t)l - 1]);

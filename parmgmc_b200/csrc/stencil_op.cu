@@ -26,6 +26,8 @@
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
+int comm_allgather_i64(pmg_ctx ctx, const int64_t *local_host, int count, int64_t *all_host);
+int comm_allgatherv(pmg_ctx ctx, const double *send, double *recv, const int64_t *counts, const int64_t *displs, cudaStream_t stream);
 
 namespace {
 
@@ -420,7 +422,7 @@ struct GridOp : LevelOp {
   }
   int init_ghosts()
   {
-    parallel = ctx->nranks > 1;
+    parallel = ctx->nranks > 1 && !(g.slo == 0 && g.shi == g.nslow()); // a whole-grid operator is a replica, not a slab
     if (parallel) {
       PMG_TRY(ghost_lo.alloc((size_t)g.unit));
       PMG_TRY(ghost_hi.alloc((size_t)g.unit));
@@ -594,6 +596,21 @@ struct BoxOp final : GridOp {
   bool           star() const override { return false; }
   int            nst() const { return g.dim == 2 ? 9 : 27; }
 
+  // ghost units of the coefficient arrays (needed by the next Galerkin product across a slab boundary)
+  int exchange_coef_ghosts()
+  {
+    if (!parallel) return 0;
+    PMG_TRY(coef_lo.alloc((size_t)nst() * g.unit));
+    PMG_TRY(coef_hi.alloc((size_t)nst() * g.unit));
+    PMG_TRY(coef_lo.zero(ctx->stream));
+    PMG_TRY(coef_hi.zero(ctx->stream));
+    for (int s = 0; s < nst(); ++s) {
+      const double *a = coef.p + (size_t)s * g.nl;
+      PMG_TRY(comm_halo_exchange(ctx, a, coef_lo.p + (size_t)s * g.unit, a + g.nl - g.unit, coef_hi.p + (size_t)s * g.unit, (size_t)g.unit, (size_t)g.unit, ctx->stream));
+    }
+    return 0;
+  }
+
   int detect_interior()
   {
     bc.on = 0;
@@ -730,6 +747,39 @@ struct GridTransfer final : Transfer {
   }
 };
 
+// Transfer between a slab-distributed fine level and a coarse level that every rank holds in full (the reference
+// agglomerates its coarse levels on rank 0, src/pc_chols.c:38-47 / src/pc_gamgmc.c:210-222; replicating them instead
+// costs the same wall time, needs no scatter on the way up and keeps every rank's noise counters in step).
+struct ReplicatingTransfer final : Transfer {
+  pmg_ctx              ctx;
+  GridOp              *fine;
+  Geom                 gc; // this rank's slab of the coarse grid (owner of fine unit 2J owns coarse unit J)
+  std::vector<int64_t> counts, displs;
+  DevBuf<double>       slab;
+  int restrict_to(const double *r, double *bcoarse_full) override
+  {
+    PMG_TRY(fine->halo(r));
+    const Geom &gf = fine->g;
+    if (gc.nl > 0) {
+      if (gf.dim == 2) restrict_kernel<2><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
+      else restrict_kernel<3><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return comm_allgatherv(ctx, slab.p, bcoarse_full, counts.data(), displs.data(), ctx->stream);
+  }
+  int prolong_add(const double *xc_full, double *xf) override
+  {
+    const Geom   &gf = fine->g;
+    const double *xc = xc_full + gc.row0(); // the neighbouring units are simply adjacent in the replica
+    if (gf.dim == 2) prolong_kernel<2><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
+    else prolong_kernel<3><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+};
+
 } // namespace
 
 int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op)
@@ -751,15 +801,29 @@ int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, do
 }
 
 // Galerkin hierarchy below a matrix-free fine operator, built on the device (levels are numbered like PCMG: 0 = coarsest).
-int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers)
+// With several ranks the upper levels stay slab-distributed; from the first level that is small (at most
+// `replicate_below` nodes globally), too thin to split (a rank would own fewer than two units) or the coarsest, every rank
+// holds the whole level.
+int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64_t replicate_below, std::vector<std::unique_ptr<LevelOp>> &ops, std::vector<std::unique_ptr<Transfer>> &transfers)
 {
   auto *fine = dynamic_cast<GridOp *>(fine_op);
   if (!fine) PMG_FAIL(PMG_ERR_SUP, "not a grid operator");
-  if (ctx->nranks > 1) PMG_FAIL(PMG_ERR_SUP, "the multi-GPU V-cycle is not available yet (multi-GPU Gibbs sweeps are)");
   ops.clear();
   transfers.clear();
   ops.resize((size_t)nlevels);
   transfers.resize((size_t)nlevels);
+  const int            R = ctx->nranks, me = ctx->rank;
+  std::vector<int64_t> slabs((size_t)2 * R, 0);
+  bool                 dist = fine->parallel;
+  if (dist) {
+    const int64_t mine[2] = {fine->g.slo, fine->g.shi};
+    PMG_TRY(comm_allgather_i64(ctx, mine, 2, slabs.data()));
+    for (int r = 0; r < R; ++r)
+      if (slabs[2 * r] != (r ? slabs[2 * r - 1] : 0) || slabs[2 * r + 1] <= slabs[2 * r] || (r == R - 1 && slabs[2 * r + 1] != fine->g.nslow()))
+        PMG_FAIL(PMG_ERR_ARG, "gamgmc: the slabs of the ranks must tile the grid in rank order (rank %d owns [%lld, %lld))", r, (long long)slabs[2 * r], (long long)slabs[2 * r + 1]);
+    if (nlevels < 2) PMG_FAIL(PMG_ERR_SUP, "gamgmc on a distributed grid needs at least two levels (the coarsest level is replicated)");
+  }
+  std::vector<std::unique_ptr<BoxOp>> keep; // distributed shadows of replicated levels are only needed during set-up
   GridOp *cur = fine;
   for (int l = nlevels - 1; l >= 1; --l) {
     const Geom   &gf = cur->g;
@@ -767,30 +831,73 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, std::
     int64_t       nc[3];
     host_q1_dims(gf.dim, nf, nc);
     if (nc[0] * nc[1] * nc[2] == nf[0] * nf[1] * nf[2]) PMG_FAIL(PMG_ERR_ARG, "gamgmc: cannot coarsen a %lldx%lldx%lld grid further (level %d)", (long long)nf[0], (long long)nf[1], (long long)nf[2], l);
+    int64_t clo = (gf.slo + 1) / 2, chi = (gf.shi + 1) / 2; // coarse unit J is owned by the owner of fine unit 2J
+    bool    replicate = false;
+    std::vector<int64_t> cs((size_t)2 * R, 0);
+    if (dist) {
+      int64_t minthick = INT64_MAX;
+      for (int r = 0; r < R; ++r) {
+        cs[2 * r]     = (slabs[2 * r] + 1) / 2;
+        cs[2 * r + 1] = (slabs[2 * r + 1] + 1) / 2;
+        minthick      = std::min(minthick, cs[2 * r + 1] - cs[2 * r]);
+      }
+      replicate = l - 1 == 0 || nc[0] * nc[1] * nc[2] <= replicate_below || minthick < 2;
+    }
     auto c = std::make_unique<BoxOp>();
     c->ctx = ctx;
-    c->g   = make_geom(gf.dim, nc, (gf.slo + 1) / 2, (gf.shi + 1) / 2); // coarse unit J is owned by the owner of fine unit 2J
+    c->g   = make_geom(gf.dim, nc, clo, chi);
     PMG_TRY(c->init_ghosts());
-    PMG_TRY(c->coef.alloc((size_t)c->nst() * c->g.nl));
+    PMG_TRY(c->coef.alloc((size_t)c->nst() * std::max<int64_t>(c->g.nl, 1)));
     const Geom &gc = c->g;
-    if (auto *lap = dynamic_cast<LapOp *>(cur)) {
-      if (gf.dim == 2) galerkin_kernel<2, FineLap<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<2>{gf, lap->tab}, gc, c->coef.p, gc.nl);
-      else galerkin_kernel<3, FineLap<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<3>{gf, lap->tab}, gc, c->coef.p, gc.nl);
-    } else {
-      auto *box = static_cast<BoxOp *>(cur);
-      if (gf.dim == 2) galerkin_kernel<2, FineBox<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<2>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
-      else galerkin_kernel<3, FineBox<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<3>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
+    if (gc.nl > 0) {
+      if (auto *lap = dynamic_cast<LapOp *>(cur)) {
+        if (gf.dim == 2) galerkin_kernel<2, FineLap<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<2>{gf, lap->tab}, gc, c->coef.p, gc.nl);
+        else galerkin_kernel<3, FineLap<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineLap<3>{gf, lap->tab}, gc, c->coef.p, gc.nl);
+      } else {
+        auto *box = static_cast<BoxOp *>(cur);
+        if (gf.dim == 2) galerkin_kernel<2, FineBox<2>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<2>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
+        else galerkin_kernel<3, FineBox<3>><<<nblocks(gc.nl, 128), 128, 0, ctx->stream>>>(FineBox<3>{gf, box->coef.p, box->coef_lo.p, box->coef_hi.p, gf.nl}, gc, c->coef.p, gc.nl);
+      }
+      PMG_CUDA(cudaGetLastError());
     }
-    PMG_CUDA(cudaGetLastError());
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    PMG_TRY(c->detect_interior());
-    auto t    = std::make_unique<GridTransfer>();
-    t->ctx    = ctx;
-    t->fine   = cur;
-    t->coarse = c.get();
-    transfers[(size_t)l] = std::move(t);
-    cur                  = c.get();
-    ops[(size_t)l - 1]   = std::move(c);
+    if (!replicate) {
+      PMG_TRY(c->exchange_coef_ghosts());
+      PMG_TRY(c->detect_interior());
+      auto t    = std::make_unique<GridTransfer>();
+      t->ctx    = ctx;
+      t->fine   = cur;
+      t->coarse = c.get();
+      transfers[(size_t)l] = std::move(t);
+      cur                  = c.get();
+      ops[(size_t)l - 1]   = std::move(c);
+      slabs                = cs;
+    } else { // gather the coefficient arrays: from here down every rank holds whole levels
+      auto full = std::make_unique<BoxOp>();
+      full->ctx = ctx;
+      full->g   = make_geom(gf.dim, nc, 0, gf.dim == 2 ? nc[1] : nc[2]);
+      PMG_TRY(full->init_ghosts());
+      PMG_TRY(full->coef.alloc((size_t)full->nst() * full->g.nl));
+      auto t    = std::make_unique<ReplicatingTransfer>();
+      t->ctx    = ctx;
+      t->fine   = cur;
+      t->gc     = gc;
+      t->counts.resize((size_t)R);
+      t->displs.resize((size_t)R);
+      for (int r = 0; r < R; ++r) {
+        t->counts[(size_t)r] = gc.unit * (cs[2 * r + 1] - cs[2 * r]);
+        t->displs[(size_t)r] = gc.unit * cs[2 * r];
+      }
+      PMG_TRY(t->slab.alloc((size_t)std::max<int64_t>(gc.nl, 1)));
+      for (int s = 0; s < full->nst(); ++s) PMG_TRY(comm_allgatherv(ctx, c->coef.p + (size_t)s * gc.nl, full->coef.p + (size_t)s * full->g.nl, t->counts.data(), t->displs.data(), ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      PMG_TRY(full->detect_interior());
+      transfers[(size_t)l] = std::move(t);
+      cur                  = full.get();
+      ops[(size_t)l - 1]   = std::move(full);
+      dist                 = false;
+      (void)me;
+    }
   }
   return 0;
 }

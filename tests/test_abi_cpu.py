@@ -65,5 +65,5 @@ def test_petsc_shim_builds_and_fails_loudly_without_device():
     assert os.path.exists(exe)
     if torch.cuda.is_available():
         pytest.skip("GPU present: the run itself is tests/test_shim_host.py")
-    r = subprocess.run([exe, "mcgibbs", "10"], capture_output=True, text=True)
+    r = subprocess.run([exe, "mcgibbs", "10", "0.02"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr

@@ -19,13 +19,13 @@ def exe():
 
 
 @pytest.mark.parametrize("args", [
-    ["mcgibbs", "20000"],                                                  # examples/ex1.c:20
-    ["mcgibbs", "20000", "-pc_mcgibbs_backward", "", "-pc_mcgibbs_omega", "1.2"],   # :21
-    ["mcgibbs", "20000", "-pc_mcgibbs_symmetric", ""],                     # :22
-    ["sorgibbs", "20000"],                                                 # :23
-    ["cholsampler", "20000"],                                              # :26
-    ["gamgmc", "20000", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "2", "-pc_b200_grid", "9,9"],  # :41
-    ["gamgmc", "20000", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "3", "-pc_b200_grid", "9,9", "-gamgmc_mg_coarse_pc_type", "mcgibbs", "-gamgmc_mg_coarse_ksp_max_it", "2"],  # :44
+    ["mcgibbs", "1000000", "0.02"],                                        # examples/ex1.c:20, the reference's own sample count and tolerance
+    ["mcgibbs", "200000", "0.05", "-pc_mcgibbs_backward", "", "-pc_mcgibbs_omega", "1.2"],   # :21 (fewer samples, 1/sqrt(N)-scaled tolerance)
+    ["mcgibbs", "200000", "0.05", "-pc_mcgibbs_symmetric", ""],            # :22
+    ["sorgibbs", "200000", "0.05"],                                        # :23
+    ["cholsampler", "200000", "0.05"],                                     # :26
+    ["gamgmc", "100000", "0.07", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "2", "-pc_b200_grid", "9,9"],  # :41
+    ["gamgmc", "100000", "0.07", "-pc_gamgmc_mg_type", "mg", "-gamgmc_pc_mg_levels", "3", "-pc_b200_grid", "9,9", "-gamgmc_mg_coarse_pc_type", "mcgibbs", "-gamgmc_mg_coarse_ksp_max_it", "2"],  # :44
 ])
 def test_ex1_shaped_c_host_program(exe, args):
     r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
