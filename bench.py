@@ -215,7 +215,7 @@ def run_b200(args):
     e2e_steps = max(3, min(args.steps, 10))
     e0.record(stream)
     for _ in range(e2e_steps):
-        pc.apply_richardson(hb, hy, its=S)
+        pc.apply_richardson(hb, hy, its=S)  # H2D of b and of the chain state y, S samples, D2H of y
     e1.record(stream)
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")

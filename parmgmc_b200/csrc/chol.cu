@@ -4,9 +4,15 @@
 // :284-287 (v = L^-1 b; v += z; y = L^-T v  =>  y ~ N(A^-1 b, A^-1)), :306-336 (cached forward solve).
 // The factor is computed once on the host at set-up (not on the per-sample path) and kept on the
 // device as L and L^T (both column-major, so every per-step access is a coalesced column read).
-// One CTA does both triangular solves of a sample from shared memory; per unknown the accumulation
-// order is reference-BLAS dtrsv's (forward k ascending, transposed k descending), so the result is
-// bit-identical to the sequential substitution.
+// Two per-sample paths:
+//   gemv (default)  W = L^-1 is formed once at set-up; a sample is two triangular matrix-vector products
+//                   v = W b + z, y = W^T v, one warp per output entry over coalesced rows (W is kept row-major and
+//                   column-major).  Fully parallel: a 289-unknown coarsest level costs a few microseconds instead
+//                   of the ~0.26 ms of two sequential substitutions (profiles/r1_summary.md).  Agrees with the
+//                   substitution to rounding (cond(L) eps).
+//   trsv            (-pc_cholsampler_b200_solve trsv) one CTA does both triangular solves from shared memory; per
+//                   unknown the accumulation order is reference-BLAS dtrsv's (forward k ascending, transposed k
+//                   descending), so the result is bit-identical to the sequential substitution (src/pc_chols.c:231,253).
 #include "common.hpp"
 #include "philox.cuh"
 
@@ -103,6 +109,26 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_sample_kernel(int n, const 
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = s[i];
 }
+// out[i] = sum_{k in [klo(i), khi(i))} M[i*n + k] in[k]  (+ z_i); LOWER: k <= i, else k >= i.  One warp per entry.
+template <bool LOWER> __global__ void __launch_bounds__(256) tri_gemv_kernel(int n, const double *__restrict__ M, const double *__restrict__ in, double *__restrict__ out, NoiseArgs na)
+{
+  const int i    = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int     k0 = LOWER ? 0 : i, k1 = LOWER ? i + 1 : n;
+  const double *row = M + (size_t)i * n;
+  double        acc = 0.0;
+  for (int k = k0 + lane; k < k1; k += 32) acc = fma(row[k], in[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[i] = na.mode != PMG_NOISE_NONE ? __dadd_rn(acc, noise_value(na, i)) : acc;
+}
+
+__global__ void add_noise_kernel(int n, const double *__restrict__ v, double *__restrict__ out, NoiseArgs na)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __dadd_rn(v[i], noise_value(na, i));
+}
 } // namespace
 
 int CholSampler::setup(pmg_ctx c, const HostCsr &a)
@@ -120,8 +146,27 @@ int CholSampler::setup(pmg_ctx c, const HostCsr &a)
       if (k > i) l[(size_t)(i + k * n)] = 0.0; // strictly upper part of the potrf workspace is not referenced
       lt[(size_t)(i + k * n)] = k >= i ? l[(size_t)(k + i * n)] : 0.0;
     }
-  PMG_TRY(L.upload(l, ctx->stream));
-  PMG_TRY(LT.upload(lt, ctx->stream));
+  if (use_gemv) { // W = L^-1 by forward substitution on the columns of the identity (column sweeps: contiguous)
+    std::vector<double> w((size_t)(n * n), 0.0), wt((size_t)(n * n), 0.0);
+    for (int64_t j = 0; j < n; ++j) {
+      double *col = w.data() + (size_t)(j * n);
+      col[j]      = 1.0;
+      for (int64_t k = j; k < n; ++k) {
+        const double x = col[k] / l[(size_t)(k + k * n)];
+        col[k]         = x;
+        const double *lk = l.data() + (size_t)(k * n);
+        for (int64_t i = k + 1; i < n; ++i) col[i] = std::fma(-lk[i], x, col[i]);
+      }
+    }
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t k = 0; k <= i; ++k) wt[(size_t)(k + i * n)] = w[(size_t)(i + k * n)]; // wt = row-major W
+    PMG_TRY(L.upload(wt, ctx->stream));  // "L"  slot: W row-major     (rows of W contiguous: v = W b)
+    PMG_TRY(LT.upload(w, ctx->stream));  // "LT" slot: W column-major  (rows of W^T contiguous: y = W^T v)
+    PMG_TRY(tmp.alloc((size_t)n));
+  } else {
+    PMG_TRY(L.upload(l, ctx->stream));
+    PMG_TRY(LT.upload(lt, ctx->stream));
+  }
   PMG_TRY(vcache.alloc((size_t)n));
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -135,10 +180,36 @@ static int launch_chol(pmg_ctx ctx, int64_t n, const double *L, const double *LT
   return 0;
 }
 
-int CholSampler::sample(const double *b, double *y, const NoiseArgs &na) { return launch_chol(ctx, n, L.p, LT.p, b, y, na, 3); }
+template <bool LOWER> static int launch_gemv(pmg_ctx ctx, int64_t n, const double *M, const double *in, double *out, const NoiseArgs &na)
+{
+  tri_gemv_kernel<LOWER><<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>((int)n, M, in, out, na);
+  PMG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int CholSampler::sample(const double *b, double *y, const NoiseArgs &na)
+{
+  if (!use_gemv) return launch_chol(ctx, n, L.p, LT.p, b, y, na, 3);
+  NoiseArgs none{PMG_NOISE_NONE, nullptr, 0, 0, 0};
+  PMG_TRY(launch_gemv<true>(ctx, n, L.p, b, tmp.p, na)); // v = W b + z
+  return launch_gemv<false>(ctx, n, LT.p, tmp.p, y, none); // y = W^T v
+}
 int CholSampler::forward(const double *b, double *v)
 {
   NoiseArgs none{PMG_NOISE_NONE, nullptr, 0, 0, 0};
-  return launch_chol(ctx, n, L.p, LT.p, b, v, none, 1);
+  if (!use_gemv) return launch_chol(ctx, n, L.p, LT.p, b, v, none, 1);
+  return launch_gemv<true>(ctx, n, L.p, b, v, none);
 }
-int CholSampler::backward_noise(const double *v, double *y, const NoiseArgs &na) { return launch_chol(ctx, n, L.p, LT.p, v, y, na, 2); }
+int CholSampler::backward_noise(const double *v, double *y, const NoiseArgs &na)
+{
+  if (!use_gemv) return launch_chol(ctx, n, L.p, LT.p, v, y, na, 2);
+  NoiseArgs none{PMG_NOISE_NONE, nullptr, 0, 0, 0};
+  if (na.mode != PMG_NOISE_NONE) {
+    add_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int)n, v, tmp.p, na);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    v = tmp.p;
+  }
+  return launch_gemv<false>(ctx, n, LT.p, v, y, none);
+}

@@ -176,6 +176,11 @@ struct LevelOp {
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
+  // The fused sweeps work on PITCHED copies of the level's vectors (row stride rounded up so that every row starts on a
+  // 32-byte boundary): fused_size() elements each; to/from_pitched convert between the natural layout of the API and it.
+  virtual int64_t fused_size() const { return n(); }
+  virtual int     to_pitched(const double *natural, double *pitched) { (void)natural; (void)pitched; return PMG_ERR_SUP; }
+  virtual int     from_pitched(const double *pitched, double *natural) { (void)natural; (void)pitched; return PMG_ERR_SUP; }
   virtual int  fused_sweep(int dir, const SweepCoeffs &c, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc)
   {
     (void)dir; (void)c; (void)b; (void)xin; (void)xout; (void)na; (void)coarse; (void)xc; (void)bc;
@@ -221,7 +226,8 @@ int make_csr_transfer(pmg_ctx ctx, const HostCsr &p, std::unique_ptr<Transfer> &
 struct CholSampler {
   pmg_ctx        ctx = nullptr;
   int64_t        n   = 0;
-  DevBuf<double> L, LT, vcache;
+  DevBuf<double> L, LT, vcache, tmp;
+  bool           use_gemv = true; // false: sequential substitution in dtrsv's order (-pc_cholsampler_b200_solve trsv)
   int setup(pmg_ctx ctx, const HostCsr &a);
   // y = L^-T (L^-1 b + z)
   int sample(const double *b, double *y, const NoiseArgs &na);

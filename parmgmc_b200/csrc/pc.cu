@@ -287,7 +287,7 @@ struct MgLevel {
   bool                      has_interp = false;
   LevelSampler              smp;
   DevBuf<double>            b, x, r;
-  DevBuf<double>            x2; // second iterate buffer of the fused (out-of-place) sweeps
+  DevBuf<double>            x2; // second iterate buffer of the fused (out-of-place) sweeps (pitched)
 };
 
 struct pmg_pc_s {
@@ -307,7 +307,8 @@ struct pmg_pc_s {
   std::vector<MgLevel> lv;
   DevBuf<double>       w, work;
   bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
-  DevBuf<double>       scratch;             // out-of-place partner of y for the fused sweeps
+  DevBuf<double>       scratch;             // out-of-place partner of the iterate for the fused sweeps (pitched)
+  DevBuf<double>       pit_y, pit_b;        // pitched copies of the caller's y and b (LevelOp::fused_size)
   // staging
   DevBuf<double> d_b, d_y;
   double        *h_pinned = nullptr;
@@ -325,7 +326,7 @@ struct pmg_pc_s {
     lv.clear();
     smp = LevelSampler();
     noise.tape.release();
-    w.release(); work.release(); d_b.release(); d_y.release(); scratch.release();
+    w.release(); work.release(); d_b.release(); d_y.release(); scratch.release(); pit_y.release(); pit_b.release();
     pmg_ctx_release(ctx);
   }
   bool        has(const std::string &k) const { return opts.count(k) != 0; }
@@ -355,6 +356,9 @@ static int configure_sampler(pmg_pc pc, const std::string &prefix, const std::st
     s.gibbs.type  = PMG_SOR_FORWARD_SWEEP; // forward and local_forward coincide on one device
   } else if (pctype == "cholsampler") {
     s.kind = KIND_CHOL;
+    const std::string solve = pc->get(prefix + "pc_cholsampler_b200_solve", pc->get("pc_cholsampler_b200_solve", "gemv"));
+    if (solve != "gemv" && solve != "trsv") PMG_FAIL(PMG_ERR_ARG, "-pc_cholsampler_b200_solve %s: expected gemv | trsv", solve.c_str());
+    s.chol.use_gemv = solve == "gemv";
   } else PMG_FAIL(PMG_ERR_SUP, "sampler type '%s' is not supported (mcgibbs | sorgibbs | cholsampler)", pctype.c_str());
   return 0;
 }
@@ -447,7 +451,8 @@ static int sweep_dirs(const LevelSampler &s, std::vector<int> &dirs)
 // The same V-cycle applied directly to (b, x): because every stage is affine in (b, x) and acts on the residual,
 // cycle(b, x) == x + cycle(b - A x, 0) (hard part 8), so the outer w = b - A y / y += work passes of
 // src/pc_gamgmc.c:253-256 disappear.  Levels whose operator has a fused streaming sweep run pre-smoothing + residual +
-// restriction in one pass over memory and prolongation + post-smoothing in another.
+// restriction in one pass over memory and prolongation + post-smoothing in another; on such a level b and x are the
+// PITCHED vectors of LevelOp::fused_size() elements (only the finest level can be one: the caller converts).
 static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool zero_guess)
 {
   pmg_ctx  ctx = pc->ctx;
@@ -482,7 +487,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? c.x.p : nullptr, nullptr));
     std::swap(cur, oth);
   }
-  if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->n() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->fused_size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 
@@ -593,7 +598,11 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(v.x.alloc(n));
     }
     if (l > 0) PMG_TRY(v.r.alloc(n));
-    if (l > 0 && v.op->fused_ok() && v.smp.kind != KIND_CHOL) PMG_TRY(v.x2.alloc(n));
+    if (l > 0 && l == L - 1 && v.op->fused_ok() && v.smp.kind != KIND_CHOL) {
+      PMG_TRY(v.x2.alloc((size_t)v.op->fused_size()));
+      PMG_TRY(pc->pit_y.alloc((size_t)v.op->fused_size()));
+      PMG_TRY(pc->pit_b.alloc((size_t)v.op->fused_size()));
+    }
   }
   const std::string cyc = pc->get("pc_b200_cycle", "direct");
   if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
@@ -642,8 +651,16 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
       PMG_TRY(pc->d_b.zero(ctx->stream));
       b = pc->d_b.p;
     }
+    const bool top_fused = pc->direct_cycle && pc->nlevels > 1 && pc->lv[pc->nlevels - 1].x2.p;
+    if (top_fused) { // the finest level runs the fused streaming sweeps on pitched copies of b and y
+      PMG_TRY(A->to_pitched(b, pc->pit_b.p));
+      if (!guesszero) PMG_TRY(A->to_pitched(y, pc->pit_y.p));
+    }
     for (int64_t it = 0; it < its; ++it) {
-      if (pc->direct_cycle) {
+      if (top_fused) {
+        PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, pc->pit_b.p, pc->pit_y.p, it == 0 && guesszero));
+        if (pc->cb || it + 1 == its) PMG_TRY(A->from_pitched(pc->pit_y.p, y));
+      } else if (pc->direct_cycle) {
         PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, b, y, it == 0 && guesszero));
       } else if (it == 0 && guesszero) {
         PMG_TRY(mg_apply(pc, b, y));
@@ -682,17 +699,23 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
       one.gibbs.type = pc->smp.gibbs.type;
       sweep_dirs(one, dirs);
       PMG_TRY(pc->smp.gibbs.ensure());
-      double   *cur = y, *oth = pc->scratch.p;
+      const double *pb = nullptr;
+      if (b) {
+        PMG_TRY(op->to_pitched(b, pc->pit_b.p));
+        pb = pc->pit_b.p;
+      }
+      PMG_TRY(op->to_pitched(y, pc->pit_y.p));
+      double   *cur = pc->pit_y.p, *oth = pc->scratch.p;
       NoiseArgs na;
       for (int64_t it = 0; it < its; ++it) {
         for (int d : dirs) {
           PMG_TRY(pc->noise.next(ctx, n, op->row0(), na));
-          PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, b, cur, oth, na, nullptr, nullptr, nullptr));
+          PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, pb, cur, oth, na, nullptr, nullptr, nullptr));
           std::swap(cur, oth);
         }
-        PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, cur));
+        if (pc->cb || it + 1 == its) PMG_TRY(op->from_pitched(cur, y));
+        PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
       }
-      if (cur != y) PMG_CUDA(cudaMemcpyAsync(y, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
       for (int64_t it = 0; it < its; ++it) {
         PMG_TRY(pc->smp.gibbs.sample(pc->noise, b, y));
@@ -867,7 +890,11 @@ int pmg_pc_setup(pmg_pc pc)
     }
     PMG_TRY(apply_coloring_policy(pc, pc->mat->op.get(), true));
     PMG_TRY(setup_level_sampler(ctx, pc->smp, pc->mat->op.get()));
-    if (pc->smp.kind != KIND_CHOL && pc->mat->op->fused_ok()) PMG_TRY(pc->scratch.alloc((size_t)pc->mat->op->n()));
+    if (pc->smp.kind != KIND_CHOL && pc->mat->op->fused_ok()) {
+      PMG_TRY(pc->scratch.alloc((size_t)pc->mat->op->fused_size()));
+      PMG_TRY(pc->pit_y.alloc((size_t)pc->mat->op->fused_size()));
+      PMG_TRY(pc->pit_b.alloc((size_t)pc->mat->op->fused_size()));
+    }
   }
   PMG_TRY(pc_alloc_staging(pc));
   pc->is_setup = true;

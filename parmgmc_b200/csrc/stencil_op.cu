@@ -152,6 +152,16 @@ template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_app
   out[idx] = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
 }
 
+// natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
+template <bool TO_PITCHED> __global__ void __launch_bounds__(256) repitch_kernel(int64_t n0, int64_t rows, int64_t pitch, const double *__restrict__ src, double *__restrict__ dst)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n0 * rows) return;
+  const int64_t r = t / n0, i = t - r * n0;
+  if (TO_PITCHED) dst[r * pitch + i] = src[t];
+  else dst[t] = src[r * pitch + i];
+}
+
 // ---- BoxOp kernels -------------------------------------------------------------------------------------
 struct BoxConst { // the shared interior stencil
   double c[27];
@@ -520,6 +530,61 @@ struct LapOp final : GridOp {
     static const bool off = std::getenv("PMG_NO_FUSED") != nullptr;
     return !off && g.dim == 2 && !parallel && g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
   }
+  // Work list of the streaming kernels.  Warps whose tile touches the physical boundary run the predicated loop, which
+  // costs about 1.6x the interior loop per row (profiles/r1_summary.md), and the grid is a single wave, so those warps
+  // get half-height bands: every warp then finishes at about the same time.  Bands start on even rows (the fused
+  // restriction emits coarse row J from the band that owns fine row 2J).
+  DevBuf<stream2d::Item> items[2]; // [restrict ? 1 : 0]
+  int                    nitems[2] = {0, 0};
+  int                    items_by  = 0;
+  int build_items(int by)
+  {
+    using stream2d::Item;
+    using stream2d::STRIP_OUT;
+    const int nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
+    for (int r = 0; r < 2; ++r) {
+      const int         lo_halo = r ? 4 : 2, hi_halo = r ? 4 : 2; // rows touched below ja / above jb (stream2d: jlo, jhi)
+      std::vector<Item> slow, fast;
+      for (int s = 0; s < nstrips; ++s) {
+        const int  c0 = s * STRIP_OUT - 4;
+        const bool edge_strip = !(c0 >= 1 && c0 + 127 <= g.n0 - 2);
+        int64_t    j = g.slo;
+        while (j < g.shi) {
+          // would a full-height band starting here be interior?
+          const int64_t jb_full = std::min<int64_t>(j + by, g.shi);
+          const bool    interior = !edge_strip && j - lo_halo >= 1 && jb_full + hi_halo <= g.n1 - 2 && j - lo_halo >= g.slo && jb_full + hi_halo + 4 < g.shi;
+          int64_t       h = interior ? by : std::max(2, (by / 2) & ~1);
+          const int64_t jb = std::min<int64_t>(j + h, g.shi);
+          (interior ? fast : slow).push_back(Item{s, (int)j, (int)jb});
+          j = jb;
+        }
+      }
+      slow.insert(slow.end(), fast.begin(), fast.end()); // predicated tiles first
+      nitems[r] = (int)slow.size();
+      PMG_TRY(items[r].upload(slow, ctx->stream));
+    }
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    items_by = by;
+    return 0;
+  }
+
+  int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
+  int64_t fused_size() const override { return pitch() * (g.shi - g.slo); }
+  int     to_pitched(const double *natural, double *pitched) override
+  {
+    repitch_kernel<true><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), natural, pitched);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int from_pitched(const double *pitched, double *natural) override
+  {
+    repitch_kernel<false><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), pitched, natural);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  // b, xin, xout are pitched (fused_size() elements); xc / bc are the coarse level's natural-layout vectors
   int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
   {
     using namespace stream2d;
@@ -538,7 +603,11 @@ struct LapOp final : GridOp {
     static const int by_env = std::getenv("PMG_STREAM_BY") ? std::atoi(std::getenv("PMG_STREAM_BY")) : 0;
     int by = by_env > 0 ? by_env : 64;
     by += by & 1;
+    if (items_by != by) PMG_TRY(build_items(by));
     a.by      = by;
+    a.pitch   = (int)pitch();
+    a.items   = items[bc ? 1 : 0].p;
+    a.nitems  = nitems[bc ? 1 : 0];
     a.nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
     a.nbands  = (int)((g.shi - g.slo + by - 1) / by);
     a.flip    = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
@@ -547,8 +616,8 @@ struct LapOp final : GridOp {
     a.tab.h   = t.h;
     a.tab.omo = 1.0 - co.omega;
     a.na      = na;
-    const int64_t warps = (int64_t)a.nstrips * a.nbands;
-    const int     bs    = bc ? 128 : 256; // matches the kernels' __launch_bounds__
+    const int64_t warps = a.nitems;
+    const int     bs    = 128; // matches the kernels' __launch_bounds__
     const unsigned nb   = nblocks(warps * 32, bs);
     if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
     if (bc) {

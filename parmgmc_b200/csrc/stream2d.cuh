@@ -37,8 +37,17 @@ struct LapTab2 {
 
 enum Guess { GUESS_LOAD = 0, GUESS_ZERO = 1, GUESS_PROLONG = 2 };
 
+// one warp's work: output columns of strip `strip`, output rows [ja, jb)
+struct Item {
+  int strip, ja, jb;
+};
+
 struct Args {
   Geom2         g, gc; // fine grid; coarse grid (PROLONG / RESTRICT)
+  const Item   *items; // work list (built on the host: LapOp::stream_items); nitems warps are launched
+  int           nitems;
+  int           pitch; // row stride of xin / xout / b: nx rounded up to 4, so that a lane's four columns are one aligned
+                       // 32-byte access (LDG.256 / STG.256) and a warp row is one contiguous kilobyte
   int           by, nstrips, nbands;
   int           flip; // 0: forward sweep (colour (i+j) even first); 1: backward sweep (colour (i+j) odd first)
   const double *xin, *b, *xc;
@@ -55,23 +64,30 @@ __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("pre
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-// four consecutive entries of row j starting at column c (zero where the node does not exist / is not owned).
-// INTERIOR: the caller guarantees that all four exist.
-template <bool INTERIOR = false>
-__device__ __forceinline__ void load4(const double *__restrict__ v, const Geom2 &g, int j, int c, double (&out)[4])
+__device__ __forceinline__ void ld256(const double *p, double (&out)[4]) { asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(out[0]), "=d"(out[1]), "=d"(out[2]), "=d"(out[3]) : "l"(p)); }
+__device__ __forceinline__ void st256(double *p, const double (&v)[4]) { asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory"); }
+
+// four consecutive entries of row j starting at column c (zero where the node does not exist / is not owned); `stride`
+// is the row stride of v.  INTERIOR: the caller guarantees that all four exist; ALIGNED: stride and c are multiples of 4
+// and v is 32-byte aligned (the pitched fine-level vectors).
+template <bool INTERIOR = false, bool ALIGNED = false>
+__device__ __forceinline__ void load4(const double *__restrict__ v, const Geom2 &g, int stride, int j, int c, double (&out)[4])
 {
   if (INTERIOR) {
     if (v == nullptr) {
       out[0] = out[1] = out[2] = out[3] = 0.0;
       return;
     }
-    const double *p = v + (size_t)(j - g.slo) * g.nx + c;
+    const double *p = v + (size_t)(j - g.slo) * stride + c;
+    if (ALIGNED) ld256(p, out);
+    else {
 #pragma unroll
-    for (int m = 0; m < 4; ++m) out[m] = p[m];
+      for (int m = 0; m < 4; ++m) out[m] = p[m];
+    }
     return;
   }
   const bool rowok = v != nullptr && j >= g.slo && j < g.shi;
-  const double *p  = v + (size_t)(j - g.slo) * g.nx + c;
+  const double *p  = v + (size_t)(j - g.slo) * stride + c;
 #pragma unroll
   for (int m = 0; m < 4; ++m) out[m] = (rowok && c + m >= 0 && c + m < g.nx) ? p[m] : 0.0;
 }
@@ -84,8 +100,8 @@ __device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const Noise
     z[0] = z[1] = z[2] = z[3] = 0.0;
     return;
   }
-  if (na.mode == PMG_NOISE_INJECTED) {
-    load4<INTERIOR>(na.tape, g, j, c, z);
+  if (na.mode == PMG_NOISE_INJECTED) { // the tape is the caller's: natural row stride, no alignment
+    load4<INTERIOR, false>(na.tape, g, g.nx, j, c, z);
     return;
   }
   const long long g0 = (long long)j * g.nx + c; // may be negative for the left halo lane of the first strip
@@ -189,7 +205,7 @@ __device__ __forceinline__ void guess_row(const Args &a, int j, int c, double (&
     out[0] = out[1] = out[2] = out[3] = 0.0;
     return;
   }
-  load4<INTERIOR>(a.xin, a.g, j, c, out);
+  load4<INTERIOR, true>(a.xin, a.g, a.pitch, j, c, out);
   if (GUESS == GUESS_PROLONG && INTERIOR) { // all parents exist
     const int    J0 = j >> 1, nJ = (j & 1) ? 2 : 1;
     const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
@@ -245,24 +261,24 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   const bool noisy    = a.na.mode != PMG_NOISE_NONE;
   constexpr int PF = 3; // L1 prefetch distance in rows (interior warps only)
 
-  double xm3[4] = {0, 0, 0, 0}, xm2[4] = {0, 0, 0, 0}, xm1[4], x0[4], xp1[4]; // rows jj-3 .. jj+1
-  double b0[4], bm1[4] = {0, 0, 0, 0}, bm2[4] = {0, 0, 0, 0};                 // rhs rows jj, jj-1, jj-2
-  double zk[4] = {0, 0, 0, 0};                                                // noise of row jj-1 (second colour used in phase B)
-  double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};                          // residual rows jj-3, jj-4
-  double r1w = 0, r2w = 0;                                                    // their column c-1 (from the lane to the west)
+  double xm3[4] = {0, 0, 0, 0}, xm2[4] = {0, 0, 0, 0}, xm1[4], x0[4]; // rows jj-3 .. jj
+  double bm1[4] = {0, 0, 0, 0}, bm2[4] = {0, 0, 0, 0};                 // rhs rows jj-1, jj-2 (RESTRICT: the residual needs whole rows)
+  double bk[2] = {0, 0}, zk[2] = {0, 0};                               // rhs / noise of row jj-1 at the two second-colour columns phase B updates
+  double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};                   // residual rows jj-3, jj-4
+  double r1w = 0, r2w = 0;                                             // their column c-1 (from the lane to the west)
 
   guess_row<GUESS, INTERIOR>(a, jA0 - 1, c, xm1);
   guess_row<GUESS, INTERIOR>(a, jA0, c, x0);
-  guess_row<GUESS, INTERIOR>(a, jA0 + 1, c, xp1);
-  load4<INTERIOR>(a.b, g, jA0, c, b0);
 
   for (int jj = jA0; jj <= jA1; ++jj) {
-    double xn[4], bn[4]; // next rows, requested early
-    guess_row<GUESS, INTERIOR>(a, jj + 2, c, xn);
-    load4<INTERIOR>(a.b, g, jj + 1, c, bn);
-    if (INTERIOR) { // rows further ahead go to L1 now
-      if (GUESS != GUESS_ZERO) prefetch_l1(a.xin + (size_t)(jj + 2 + PF - g.slo) * g.nx + c);
-      if (a.b) prefetch_l1(a.b + (size_t)(jj + 1 + PF - g.slo) * g.nx + c);
+    // this iteration's incoming rows: requested first, consumed after the normals have been computed, so that the
+    // generator hides their latency; keeping the window this short is what lets 20 warps stay resident per SM
+    double xp1[4], b0[4];
+    guess_row<GUESS, INTERIOR>(a, jj + 1, c, xp1);
+    load4<INTERIOR, true>(a.b, g, a.pitch, jj, c, b0);
+    if (INTERIOR) { // rows further ahead go to L2 / L1 now
+      if (GUESS != GUESS_ZERO) prefetch_l1(a.xin + (size_t)(jj + 1 + PF - g.slo) * a.pitch + c);
+      if (a.b) prefetch_l1(a.b + (size_t)(jj + PF - g.slo) * a.pitch + c);
     }
     double z[4];
     noise4<INTERIOR>(ft, a.na, g, jj, c, z);
@@ -281,19 +297,25 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     { // ---- phase B: second-colour nodes of row jj-1 (same columns); all their neighbours are new ----
       const double west = shfl_up1(xm1[3]), east = shfl_dn1(xm1[0]);
       if (even) {
-        update<0, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bm1[0], zk[0], noisy);
-        update<2, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bm1[2], zk[2], noisy);
+        update<0, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bk[0], zk[0], noisy);
+        update<2, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bk[1], zk[1], noisy);
       } else {
-        update<1, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bm1[1], zk[1], noisy);
-        update<3, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bm1[3], zk[3], noisy);
+        update<1, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bk[0], zk[0], noisy);
+        update<3, INTERIOR>(g, a.tab, jj - 1, c, xm1, xm2, x0, west, east, bk[1], zk[1], noisy);
       }
     }
+    // what phase B of the next iteration (whose columns are the other two) needs of this row
+    bk[0] = even ? b0[1] : b0[0]; bk[1] = even ? b0[3] : b0[2];
+    zk[0] = even ? z[1] : z[0];   zk[1] = even ? z[3] : z[2];
     const int jo = jj - 1; // row jj-1 is final
     if (out_lane && jo >= ja && jo < jb) {
-      double *p = a.xout + (size_t)(jo - g.slo) * g.nx + c;
+      double *p = a.xout + (size_t)(jo - g.slo) * a.pitch + c;
+      if (INTERIOR) st256(p, xm1);
+      else {
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-        if (INTERIOR || c + m < g.nx) p[m] = xm1[m];
+        for (int m = 0; m < 4; ++m)
+          if (c + m < g.nx) p[m] = xm1[m];
+      }
     }
     if (RESTRICT) {
       const int    jr = jj - 2; // residual of row jj-2 (rows jj-3, jj-2, jj-1 are final)
@@ -337,13 +359,15 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       copy4(r1, r0); r1w = r0w;
     }
     // advance the window
-    copy4(xm3, xm2); copy4(xm2, xm1); copy4(xm1, x0); copy4(x0, xp1); copy4(xp1, xn);
-    copy4(bm2, bm1); copy4(bm1, b0); copy4(b0, bn);
-    copy4(zk, z);
+    if (RESTRICT) {
+      copy4(xm3, xm2);
+      copy4(bm2, bm1); copy4(bm1, b0);
+    }
+    copy4(xm2, xm1); copy4(xm1, x0); copy4(x0, xp1);
   }
 }
 
-template <int GUESS, bool RESTRICT> __global__ void __launch_bounds__(RESTRICT ? 128 : 256, RESTRICT ? 3 : 2) lap_stream_kernel(const Args a)
+template <int GUESS, bool RESTRICT> __global__ void __launch_bounds__(128, RESTRICT ? 3 : 5) lap_stream_kernel(const Args a)
 {
   __shared__ fastnormal::SharedTables fts;
   const fastnormal::Tables ft = fastnormal::load_tables(fts);
@@ -351,10 +375,10 @@ template <int GUESS, bool RESTRICT> __global__ void __launch_bounds__(RESTRICT ?
   const Geom2 &g    = a.g;
   const int    lane = threadIdx.x & 31;
   const int    w    = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (w >= a.nstrips * a.nbands) return;
-  const int strip = w % a.nstrips, band = w / a.nstrips;
-  const int c0    = strip * STRIP_OUT - 4;
-  const int ja = g.slo + band * a.by, jb = min(ja + a.by, g.shi);
+  if (w >= a.nitems) return;
+  const Item it = a.items[w];
+  const int  c0 = it.strip * STRIP_OUT - 4;
+  const int  ja = it.ja, jb = it.jb;
   const int jlo = ja - (RESTRICT ? 3 : 1) - 1, jhi = jb + (RESTRICT ? 2 : 0) + 2; // first / last row touched
   const bool interior = c0 >= 1 && c0 + 127 <= g.nx - 2 && jlo >= 1 && jhi <= g.ny - 2 && jlo >= g.slo && jhi + 4 < g.shi;
   if (interior) run_warp<GUESS, RESTRICT, true>(a, ft, lane, c0 + 4 * lane, ja, jb);

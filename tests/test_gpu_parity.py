@@ -288,14 +288,21 @@ def test_gibbs_philox_mode_matches_oracle_philox(pmg, ctx, orc):
 
 
 # ---- a16: Cholesky sampler ---------------------------------------------------------------------------
+@pytest.mark.parametrize("solve", ["trsv", "gemv"])
 @pytest.mark.parametrize("dims", [(5, 5), (9, 9), (17, 17), (33, 20)])
-def test_cholsampler_bitexact(pmg, ctx, orc, dims):
+def test_cholsampler_bitexact(pmg, ctx, orc, dims, solve):
+    """trsv: the sequential substitution in dtrsv's order, bit-exact; gemv (default): explicit L^-1, two triangular
+    matrix-vector products, equal to rounding."""
     rng = np.random.default_rng(SEED)
     A = orc.laplace(2, dims[0], dims[1], kappa=1.0)
     n = A.n
     pc = pmg.PC(ctx, "cholsampler")
     pc.set_operator(make_mat(pmg, ctx, A))
+    pc.set_option("-pc_cholsampler_b200_solve", solve)
     pc.setup()
+
+    def same(a, b):
+        return np.array_equal(a, b) if solve == "trsv" else relerr(a, b) < RTOL
     assert f"size {n}" in pc.view()
     Lf = orc.potrf_lower(A.to_scipy().toarray())
     z, b = rng.standard_normal(4 * n), rng.standard_normal(n)
@@ -303,12 +310,12 @@ def test_cholsampler_bitexact(pmg, ctx, orc, dims):
     pc.set_noise_tape(z)
     y = np.zeros(n)
     pc.apply_richardson(b, y, its=1)
-    assert np.array_equal(y, orc.chol_sample(Lf, n, orc.Noise.tape(z[:n]), b))
+    assert same(y, orc.chol_sample(Lf, n, orc.Noise.tape(z[:n]), b))
     y3 = np.zeros(n)
     its_seen = []
     pc.set_sample_callback(lambda it, yy: its_seen.append(it))
     pc.apply_richardson(b, y3, its=3)
-    assert np.array_equal(y3, orc.chol_sample(Lf, n, orc.Noise.tape(z[3 * n:]), b))
+    assert same(y3, orc.chol_sample(Lf, n, orc.Noise.tape(z[3 * n:]), b))
     assert len(its_seen) == 3
     # exactness: mean of many samples -> A^-1 b is covered by the statistical test
 

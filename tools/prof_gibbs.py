@@ -13,7 +13,7 @@ pc = pmg.PC(ctx, "sorgibbs" if what == "gibbs" else "gamgmc")
 pc.set_operator(mat)
 if what != "gibbs":
     pc.set_option("-gamgmc_pc_mg_levels", 10)
-pc.set_option("-pc_b200_noise", "philox")
+pc.set_option("-pc_b200_noise", os.environ.get("NOISE", "philox"))
 pc.setup()
 y = torch.zeros(mat.n, dtype=torch.float64, device="cuda")
 b = torch.zeros(mat.n, dtype=torch.float64, device="cuda")
