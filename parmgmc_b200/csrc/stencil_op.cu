@@ -68,6 +68,47 @@ struct LapTab { // indexed by the number of existing neighbours
   double h;
 };
 
+// Launch geometry of the per-node kernels: x runs along the fastest grid dimension, y over grid rows, z over planes, so
+// that no thread has to recover (i, j, k) from a linear index with 64-bit divisions (which used to cost more than the
+// stencil itself).  Thread (tx, ty) of block (bx, by, bz): position tx + bx*blockDim.x in the row, row ty + by*blockDim.y.
+struct Plan {
+  dim3 grid, block;
+};
+static Plan plan3(int64_t ni, int64_t nrows, int64_t nplanes)
+{
+  unsigned bx = 32;
+  while (bx < ni && bx < 256) bx *= 2;
+  const unsigned by = 256 / bx;
+  Plan           p;
+  p.block = dim3(bx, by, 1);
+  p.grid  = dim3((unsigned)std::max<int64_t>(1, (ni + bx - 1) / bx), (unsigned)std::max<int64_t>(1, (nrows + by - 1) / by), (unsigned)std::max<int64_t>(1, nplanes));
+  return p;
+}
+static bool plan_ok(const Plan &p) { return p.grid.y <= 65535u && p.grid.z <= 65535u; }
+#define PMG_PLAN_CHECK(p) \
+  if (!plan_ok(p)) PMG_FAIL(PMG_ERR_SUP, "grid too large for one launch (%u x %u x %u blocks)", (p).grid.x, (p).grid.y, (p).grid.z)
+
+// node of this thread under plan3(n0, rows, planes): all owned nodes, natural order
+template <int DIM> __device__ __forceinline__ bool node_of_thread(const Geom &g, int64_t &i, int64_t &j, int64_t &k, int64_t &idx)
+{
+  i                = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t rj = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.n0) return false;
+  if (DIM == 2) {
+    if (rj >= g.shi - g.slo) return false;
+    j   = g.slo + rj;
+    k   = 0;
+    idx = i + g.n0 * rj;
+  } else {
+    if (rj >= g.n1) return false;
+    j   = rj;
+    k   = g.slo + blockIdx.z;
+    idx = i + g.n0 * (rj + g.n1 * (int64_t)blockIdx.z);
+  }
+  return true;
+}
+template <int DIM> static Plan plan_nodes(const Geom &g) { return DIM == 2 ? plan3(g.n0, g.shi - g.slo, 1) : plan3(g.n0, g.n1, g.shi - g.slo); }
+
 template <int DIM> __device__ __forceinline__ void decode(const Geom &g, int64_t idx, int64_t &i, int64_t &j, int64_t &k)
 {
   i               = idx % g.n0;
@@ -85,17 +126,19 @@ template <int DIM> __device__ __forceinline__ void decode(const Geom &g, int64_t
 // one thread per node of the colour; nodes of a colour in a grid row are i = s, s+2, ...
 template <int DIM> __global__ void __launch_bounds__(256) lap_sweep_kernel(Geom g, int color, LapTab tab, double omo, const double *__restrict__ b, double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, NoiseArgs na)
 {
-  const int64_t t    = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t half = (g.n0 + 1) >> 1, rows = g.nl / g.n0;
-  if (t >= half * rows) return;
-  const int64_t row = t / half, kk = t - row * half;
-  int64_t       j, k;
+  const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t rj = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; // 2D: local grid row; 3D: j
+  int64_t       j, k, row;
   if (DIM == 2) {
-    j = g.slo + row;
-    k = 0;
+    if (rj >= g.shi - g.slo) return;
+    j   = g.slo + rj;
+    k   = 0;
+    row = rj;
   } else {
-    j = row % g.n1;
-    k = g.slo + row / g.n1;
+    if (rj >= g.n1) return;
+    j   = rj;
+    k   = g.slo + blockIdx.z;
+    row = rj + g.n1 * blockIdx.z;
   }
   const int64_t i = 2 * kk + ((color + j + k) & 1);
   if (i >= g.n0) return;
@@ -126,10 +169,8 @@ template <int DIM> __global__ void __launch_bounds__(256) lap_sweep_kernel(Geom 
 // out = b - A x (residual) or A x (mult)
 template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_apply_kernel(Geom g, LapTab tab, const double *__restrict__ b, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, double *__restrict__ out)
 {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= g.nl) return;
-  int64_t i, j, k;
-  decode<DIM>(g, idx, i, j, k);
+  int64_t i, j, k, idx;
+  if (!node_of_thread<DIM>(g, i, j, k, idx)) return;
   const bool   W = i > 0, E = i < g.n0 - 1, S = j > 0, N = j < g.n1 - 1, D = DIM == 3 && k > 0, U = DIM == 3 && k < g.n2 - 1;
   const int    deg = (int)W + (int)E + (int)S + (int)N + (int)D + (int)U;
   const double mh  = -tab.h;
@@ -155,11 +196,10 @@ template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_app
 // natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
 template <bool TO_PITCHED> __global__ void __launch_bounds__(256) repitch_kernel(int64_t n0, int64_t rows, int64_t pitch, const double *__restrict__ src, double *__restrict__ dst)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n0 * rows) return;
-  const int64_t r = t / n0, i = t - r * n0;
-  if (TO_PITCHED) dst[r * pitch + i] = src[t];
-  else dst[t] = src[r * pitch + i];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n0 || r >= rows) return;
+  if (TO_PITCHED) dst[r * pitch + i] = src[r * n0 + i];
+  else dst[r * n0 + i] = src[r * pitch + i];
 }
 
 // ---- BoxOp kernels -------------------------------------------------------------------------------------
@@ -204,36 +244,32 @@ __device__ __forceinline__ double box_row(const Geom &g, const BoxConst &bc, con
   return acc;
 }
 
-template <int DIM> __device__ __forceinline__ bool box_colour_node(const Geom &g, int color, int64_t t, int64_t &idx, int64_t &i, int64_t &j, int64_t &k)
+// node of this thread among the nodes of one colour, under box_colour_plan
+template <int DIM> __device__ __forceinline__ bool box_colour_node(const Geom &g, int color, int64_t &idx, int64_t &i, int64_t &j, int64_t &k)
 {
   const int     ci = color & 1, cj = (color >> 1) & 1, ck = (color >> 2) & 1;
-  const int64_t ni = (g.n0 - ci + 1) >> 1;
-  if (ni <= 0) return false;
+  const int64_t tx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, ty = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  i = 2 * tx + ci;
+  if (i >= g.n0) return false;
   if (DIM == 2) {
-    const int64_t jf = g.slo + ((cj ^ g.slo) & 1), nj = jf < g.shi ? (g.shi - jf + 1) >> 1 : 0;
-    if (t >= ni * nj) return false;
-    i   = 2 * (t % ni) + ci;
-    j   = jf + 2 * (t / ni);
+    j = g.slo + ((cj ^ g.slo) & 1) + 2 * ty;
+    if (j >= g.shi) return false;
     k   = 0;
     idx = i + g.n0 * (j - g.slo);
   } else {
-    const int64_t nj = (g.n1 - cj + 1) >> 1;
-    const int64_t kf = g.slo + ((ck ^ g.slo) & 1), nk = kf < g.shi ? (g.shi - kf + 1) >> 1 : 0;
-    if (nj <= 0 || t >= ni * nj * nk) return false;
-    i                = 2 * (t % ni) + ci;
-    const int64_t t2 = t / ni;
-    j                = 2 * (t2 % nj) + cj;
-    k                = kf + 2 * (t2 / nj);
-    idx              = i + g.n0 * (j + g.n1 * (k - g.slo));
+    j = 2 * ty + cj;
+    k = g.slo + ((ck ^ g.slo) & 1) + 2 * (int64_t)blockIdx.z;
+    if (j >= g.n1 || k >= g.shi) return false;
+    idx = i + g.n0 * (j + g.n1 * (k - g.slo));
   }
   return true;
 }
+template <int DIM> static Plan box_colour_plan(const Geom &g) { return DIM == 2 ? plan3((g.n0 + 1) / 2, (g.shi - g.slo + 1) / 2, 1) : plan3((g.n0 + 1) / 2, (g.n1 + 1) / 2, (g.shi - g.slo + 1) / 2); }
 
 template <int DIM> __global__ void __launch_bounds__(256) box_sweep_kernel(Geom g, int color, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ idiag, const double *__restrict__ sqrtdiag, double omo, const double *__restrict__ b, double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, NoiseArgs na)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t       idx, i, j, k;
-  if (!box_colour_node<DIM>(g, color, t, idx, i, j, k)) return;
+  int64_t idx, i, j, k;
+  if (!box_colour_node<DIM>(g, color, idx, i, j, k)) return;
   const bool   interior = box_interior<DIM>(g, bc, i, j, k);
   const double sq = interior ? bc.sqrtdiag : sqrtdiag[idx], id = interior ? bc.idiag : idiag[idx];
   double       sum = noisy_rhs(na, idx, sq, b ? b[idx] : 0.0);
@@ -244,10 +280,8 @@ template <int DIM> __global__ void __launch_bounds__(256) box_sweep_kernel(Geom 
 
 template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) box_apply_kernel(Geom g, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ b, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, double *__restrict__ out)
 {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= g.nl) return;
-  int64_t i, j, k;
-  decode<DIM>(g, idx, i, j, k);
+  int64_t i, j, k, idx;
+  if (!node_of_thread<DIM>(g, i, j, k, idx)) return;
   const double ax = box_row<DIM, false, true>(g, bc, coef, stride, x, glo, ghi, idx, i, j, k, 0.0);
   out[idx]        = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
 }
@@ -281,10 +315,8 @@ template <int DIM> __global__ void box_uniform_kernel(Geom g, const double *__re
 // coarse node I sits on fine node 2I; nc = (nf + 1)/2 per direction
 template <int DIM> __global__ void __launch_bounds__(256) restrict_kernel(Geom gf, Geom gc, const double *__restrict__ r, const double *__restrict__ rlo, const double *__restrict__ rhi, double *__restrict__ bc)
 {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= gc.nl) return;
-  int64_t I, J, K;
-  decode<DIM>(gc, idx, I, J, K);
+  int64_t I, J, K, idx;
+  if (!node_of_thread<DIM>(gc, I, J, K, idx)) return;
   double acc = 0.0;
 #pragma unroll
   for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk)
@@ -303,10 +335,8 @@ template <int DIM> __global__ void __launch_bounds__(256) restrict_kernel(Geom g
 
 template <int DIM> __global__ void __launch_bounds__(256) prolong_kernel(Geom gf, Geom gc, const double *__restrict__ xc, const double *__restrict__ clo, const double *__restrict__ chi, double *__restrict__ xf)
 {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= gf.nl) return;
-  int64_t i, j, k;
-  decode<DIM>(gf, idx, i, j, k);
+  int64_t i, j, k, idx;
+  if (!node_of_thread<DIM>(gf, i, j, k, idx)) return;
   // per direction: even node -> one coarse parent (weight 1); odd node -> (p-1)/2 and (p+1)/2 (if it exists), weight 1/2
   const int     ci = (i & 1) ? 2 : 1, cj = (j & 1) ? 2 : 1, ck = (DIM == 3 && (k & 1)) ? 2 : 1;
   const int64_t I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
@@ -512,12 +542,13 @@ struct LapOp final : GridOp {
   {
     LapTab t;
     fill_tab(co.omega, t);
-    const int64_t half = (g.n0 + 1) >> 1, rows = g.nl / g.n0, nt = half * rows;
+    const Plan pl = g.dim == 2 ? plan3((g.n0 + 1) >> 1, g.shi - g.slo, 1) : plan3((g.n0 + 1) >> 1, g.n1, g.shi - g.slo);
+    PMG_PLAN_CHECK(pl);
     for (int s = 0; s < 2; ++s) {
       const int c = dir == PMG_SOR_FORWARD_SWEEP ? s : 1 - s;
       PMG_TRY(halo(y));
-      if (g.dim == 2) lap_sweep_kernel<2><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
-      else lap_sweep_kernel<3><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      if (g.dim == 2) lap_sweep_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      else lap_sweep_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, t, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
       PMG_CUDA(cudaGetLastError());
       ctx->launches++;
     }
@@ -572,14 +603,18 @@ struct LapOp final : GridOp {
   int64_t fused_size() const override { return pitch() * (g.shi - g.slo); }
   int     to_pitched(const double *natural, double *pitched) override
   {
-    repitch_kernel<true><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), natural, pitched);
+    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
+    PMG_PLAN_CHECK(pl);
+    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), natural, pitched);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
   }
   int from_pitched(const double *pitched, double *natural) override
   {
-    repitch_kernel<false><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), pitched, natural);
+    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
+    PMG_PLAN_CHECK(pl);
+    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), pitched, natural);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -640,8 +675,10 @@ struct LapOp final : GridOp {
   template <bool RES> int apply(const double *b, const double *x, double *out)
   {
     PMG_TRY(halo(x));
-    if (g.dim == 2) lap_apply_kernel<2, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
-    else lap_apply_kernel<3, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
+    const Plan pl = g.dim == 2 ? plan_nodes<2>(g) : plan_nodes<3>(g);
+    PMG_PLAN_CHECK(pl);
+    if (g.dim == 2) lap_apply_kernel<2, RES><<<pl.grid, pl.block, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
+    else lap_apply_kernel<3, RES><<<pl.grid, pl.block, 0, ctx->stream>>>(g, tab, b, x, ghost_lo.p, ghost_hi.p, out);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -731,13 +768,14 @@ struct BoxOp final : GridOp {
       k.idiag        = inv * co.omega;
       k.sqrtdiag     = std::sqrt(std::fabs(d)) * std::sqrt((2 - co.omega) / co.omega);
     }
-    const int     nc = ncolors();
-    const int64_t nt = ((g.n0 + 1) / 2) * (g.dim == 2 ? (g.shi - g.slo + 1) / 2 + 1 : ((g.n1 + 1) / 2) * ((g.shi - g.slo + 1) / 2 + 1));
+    const int  nc = ncolors();
+    const Plan pl = g.dim == 2 ? box_colour_plan<2>(g) : box_colour_plan<3>(g);
+    PMG_PLAN_CHECK(pl);
     for (int s = 0; s < nc; ++s) {
       const int c = dir == PMG_SOR_FORWARD_SWEEP ? s : nc - 1 - s;
       PMG_TRY(halo(y));
-      if (g.dim == 2) box_sweep_kernel<2><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
-      else box_sweep_kernel<3><<<nblocks(nt, 256), 256, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      if (g.dim == 2) box_sweep_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
+      else box_sweep_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
       PMG_CUDA(cudaGetLastError());
       ctx->launches++;
     }
@@ -747,8 +785,10 @@ struct BoxOp final : GridOp {
   template <bool RES> int apply(const double *b, const double *x, double *out)
   {
     PMG_TRY(halo(x));
-    if (g.dim == 2) box_apply_kernel<2, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
-    else box_apply_kernel<3, RES><<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
+    const Plan pl = g.dim == 2 ? plan_nodes<2>(g) : plan_nodes<3>(g);
+    PMG_PLAN_CHECK(pl);
+    if (g.dim == 2) box_apply_kernel<2, RES><<<pl.grid, pl.block, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
+    else box_apply_kernel<3, RES><<<pl.grid, pl.block, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -798,8 +838,10 @@ struct GridTransfer final : Transfer {
   {
     PMG_TRY(fine->halo(r));
     const Geom &gf = fine->g, &gc = coarse->g;
-    if (gf.dim == 2) restrict_kernel<2><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
-    else restrict_kernel<3><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
+    const Plan pl = gf.dim == 2 ? plan_nodes<2>(gc) : plan_nodes<3>(gc);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
+    else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, bcoarse);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -808,8 +850,10 @@ struct GridTransfer final : Transfer {
   {
     PMG_TRY(coarse->halo(xc));
     const Geom &gf = fine->g, &gc = coarse->g;
-    if (gf.dim == 2) prolong_kernel<2><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
-    else prolong_kernel<3><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
+    const Plan pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
+    else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -830,8 +874,10 @@ struct ReplicatingTransfer final : Transfer {
     PMG_TRY(fine->halo(r));
     const Geom &gf = fine->g;
     if (gc.nl > 0) {
-      if (gf.dim == 2) restrict_kernel<2><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
-      else restrict_kernel<3><<<nblocks(gc.nl, 256), 256, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
+      const Plan pl = gf.dim == 2 ? plan_nodes<2>(gc) : plan_nodes<3>(gc);
+      PMG_PLAN_CHECK(pl);
+      if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
+      else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, r, fine->ghost_lo.p, fine->ghost_hi.p, slab.p);
       PMG_CUDA(cudaGetLastError());
       ctx->launches++;
     }
@@ -841,8 +887,10 @@ struct ReplicatingTransfer final : Transfer {
   {
     const Geom   &gf = fine->g;
     const double *xc = xc_full + gc.row0(); // the neighbouring units are simply adjacent in the replica
-    if (gf.dim == 2) prolong_kernel<2><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
-    else prolong_kernel<3><<<nblocks(gf.nl, 256), 256, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
+    const Plan pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
+    else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
