@@ -176,6 +176,7 @@ struct LevelOp {
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
+  virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
   // The fused sweeps work on PITCHED copies of the level's vectors (row stride rounded up so that every row starts on a
   // 32-byte boundary): fused_size() elements each; to/from_pitched convert between the natural layout of the API and it.
   virtual int64_t fused_size() const { return n(); }

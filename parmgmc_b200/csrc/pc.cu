@@ -457,7 +457,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
 {
   pmg_ctx  ctx = pc->ctx;
   MgLevel &v   = pc->lv[l];
-  const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_ok() && v.x2.p;
+  const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p;
   if (!fused) {
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
     PMG_TRY(run_level_sampler(pc, v.smp, b, x));
@@ -598,7 +598,7 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(v.x.alloc(n));
     }
     if (l > 0) PMG_TRY(v.r.alloc(n));
-    if (l > 0 && l == L - 1 && v.op->fused_ok() && v.smp.kind != KIND_CHOL) {
+    if (l > 0 && l == L - 1 && v.op->fused_mg_ok() && v.smp.kind != KIND_CHOL) {
       PMG_TRY(v.x2.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_y.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_b.alloc((size_t)v.op->fused_size()));

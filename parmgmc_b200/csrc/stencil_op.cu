@@ -23,6 +23,7 @@
 #include "common.hpp"
 #include "philox.cuh"
 #include "stream2d.cuh"
+#include "stream3d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -196,8 +197,9 @@ template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_app
 // natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
 template <bool TO_PITCHED> __global__ void __launch_bounds__(256) repitch_kernel(int64_t n0, int64_t rows, int64_t pitch, const double *__restrict__ src, double *__restrict__ dst)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= n0 || r >= rows) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, ry = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n0 || ry >= rows) return;
+  const int64_t r = ry + rows * (int64_t)blockIdx.z; // rows = grid rows per plane (2D: one plane)
   if (TO_PITCHED) dst[r * pitch + i] = src[r * n0 + i];
   else dst[r * n0 + i] = src[r * pitch + i];
 }
@@ -559,8 +561,11 @@ struct LapOp final : GridOp {
   bool fused_ok() const override
   {
     static const bool off = std::getenv("PMG_NO_FUSED") != nullptr;
-    return !off && g.dim == 2 && !parallel && g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
+    if (off || parallel) return false;
+    if (g.dim == 2) return g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
+    return g.n0 >= 8 && g.n1 >= 2 && g.n2 >= 2 && g.n0 < (1 << 20) && g.n1 < (1 << 20) && g.n2 < (1 << 20);
   }
+  bool fused_mg_ok() const override { return fused_ok() && g.dim == 2; }
   // Work list of the streaming kernels.  Warps whose tile touches the physical boundary run the predicated loop, which
   // costs about 1.6x the interior loop per row (profiles/r1_summary.md), and the grid is a single wave, so those warps
   // get half-height bands: every warp then finishes at about the same time.  Bands start on even rows (the fused
@@ -600,28 +605,103 @@ struct LapOp final : GridOp {
   }
 
   int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
-  int64_t fused_size() const override { return pitch() * (g.shi - g.slo); }
+  int64_t slab_rows() const { return g.dim == 2 ? g.shi - g.slo : g.n1 * (g.shi - g.slo); }
+  int64_t fused_size() const override { return pitch() * slab_rows(); }
   int     to_pitched(const double *natural, double *pitched) override
   {
-    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
+    const Plan pl = g.dim == 2 ? plan3(g.n0, g.shi - g.slo, 1) : plan3(g.n0, g.n1, g.shi - g.slo);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), natural, pitched);
+    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), natural, pitched);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
   }
   int from_pitched(const double *pitched, double *natural) override
   {
-    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
+    const Plan pl = g.dim == 2 ? plan3(g.n0, g.shi - g.slo, 1) : plan3(g.n0, g.n1, g.shi - g.slo);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), pitched, natural);
+    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), pitched, natural);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
   }
   // b, xin, xout are pitched (fused_size() elements); xc / bc are the coarse level's natural-layout vectors
+  // ---- 3D: stream3d.cuh ----
+  DevBuf<stream3d::Item> items3;
+  int                    nitems3 = 0, items3_bz = 0, items3_nw = 0;
+  int build_items3(int bz, int NW3) // NW3 warps (grid rows) per CTA tile: NW3 - 2 output rows + 2 halo rows
+  {
+    using stream3d::Item;
+    const int         nstrips = (int)((g.n0 + stream3d::STRIP_OUT - 1) / stream3d::STRIP_OUT), ty = NW3 - 2;
+    std::vector<Item> slow, fast;
+    for (int64_t k = g.slo; k < g.shi;) {
+      const int64_t kb_full = std::min<int64_t>(k + bz, g.shi);
+      const bool    kin = k - 2 >= 1 && kb_full + 1 <= g.n2 - 2 && k - 2 >= g.slo && kb_full + 1 < g.shi;
+      const int64_t kb = kin ? kb_full : std::min<int64_t>(k + std::max(1, bz / 2), g.shi); // predicated tiles: half bands
+      for (int64_t ya = 0; ya < g.n1; ya += ty)
+        for (int s = 0; s < nstrips; ++s) {
+          const int  c0 = s * stream3d::STRIP_OUT - 4;
+          const bool interior = kin && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 2 >= 0 && ya + NW3 - 2 <= g.n1 - 2;
+          (interior ? fast : slow).push_back(Item{s, (int)ya, (int)k, (int)kb});
+        }
+      k = kb;
+    }
+    slow.insert(slow.end(), fast.begin(), fast.end());
+    nitems3 = (int)slow.size();
+    PMG_TRY(items3.upload(slow, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    items3_bz = bz;
+    items3_nw = NW3;
+    return 0;
+  }
+  template <int NW> int launch3(const stream3d::Args &a)
+  {
+    using namespace stream3d;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PMG_CUDA(cudaFuncSetAttribute(lap_stream3d_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<NW>()));
+      attr_set = true;
+    }
+    lap_stream3d_kernel<NW><<<(unsigned)nitems3, NW * 32, smem_bytes<NW>(), ctx->stream>>>(a);
+    return 0;
+  }
+  int fused_sweep3(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
+  {
+    using namespace stream3d;
+    if (!xin) PMG_FAIL(PMG_ERR_ARG, "fused 3D sweep needs an iterate");
+    LapTab t;
+    fill_tab(co.omega, t);
+    static const int bz_env = std::getenv("PMG_STREAM_BZ") ? std::atoi(std::getenv("PMG_STREAM_BZ")) : 0;
+    static const int nw_env = std::getenv("PMG_STREAM_NW") ? std::atoi(std::getenv("PMG_STREAM_NW")) : 0;
+    const int        bz     = bz_env > 0 ? bz_env : 32;
+    const int        nw     = (nw_env == 10 || nw_env == 16 || nw_env == 20) ? nw_env : (g.n1 >= 64 ? 20 : 10);
+    if (items3_bz != bz || items3_nw != nw) PMG_TRY(build_items3(bz, nw));
+    Args a;
+    a.g      = Geom3{(int)g.n0, (int)g.n1, (int)g.n2, (int)g.slo, (int)g.shi};
+    a.pitch  = (int)pitch();
+    a.pplane = (long long)pitch() * g.n1;
+    a.items  = items3.p;
+    a.flip   = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
+    a.xin = xin; a.b = b; a.xout = xout;
+    for (int d = 0; d < 7; ++d) { a.tab.diag[d] = t.diag[d]; a.tab.idiag[d] = t.idiag[d]; a.tab.sqrtdiag[d] = t.sqrtdiag[d]; }
+    a.tab.h   = t.h;
+    a.tab.omo = 1.0 - co.omega;
+    a.na      = na;
+    if (nw == 10) PMG_TRY(launch3<10>(a));
+    else if (nw == 16) PMG_TRY(launch3<16>(a));
+    else PMG_TRY(launch3<20>(a));
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+
   int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
   {
+    if (g.dim == 3) {
+      if (xc || bc) PMG_FAIL(PMG_ERR_SUP, "the 3D fused sweep does not include the grid transfers");
+      return fused_sweep3(dir, co, b, xin, xout, na);
+    }
     using namespace stream2d;
     LapTab t;
     fill_tab(co.omega, t);

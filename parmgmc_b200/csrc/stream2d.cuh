@@ -92,19 +92,11 @@ __device__ __forceinline__ void load4(const double *__restrict__ v, const Geom2 
   for (int m = 0; m < 4; ++m) out[m] = (rowok && c + m >= 0 && c + m < g.nx) ? p[m] : 0.0;
 }
 
-// the four normals of columns c..c+3 of row j (global rows g0 = c + nx j ...), one Philox quad per lane plus shuffles
-template <bool INTERIOR = false>
-__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom2 &g, int j, int c, double (&z)[4])
+// the four normals of global rows g0 .. g0+3 (g0 = 0 mod 4 is NOT required; it is warp-uniform mod 4 because a lane's first
+// column is a multiple of 4): one Philox quad per lane plus shuffles from the next lane
+__device__ __forceinline__ void philox_normals4(const fastnormal::Tables &ft, const NoiseArgs &na, long long g0, double (&z)[4])
 {
-  if (na.mode == PMG_NOISE_NONE) {
-    z[0] = z[1] = z[2] = z[3] = 0.0;
-    return;
-  }
-  if (na.mode == PMG_NOISE_INJECTED) { // the tape is the caller's: natural row stride, no alignment
-    load4<INTERIOR, false>(na.tape, g, g.nx, j, c, z);
-    return;
-  }
-  const long long g0 = (long long)j * g.nx + c; // may be negative for the left halo lane of the first strip
+  // g0 may be negative for the left halo lane of the first strip
   const int       s  = (int)(g0 & 3);           // warp uniform: c = 0 mod 4
   // lane l computes the quad that holds its first element; elements s+m >= 4 come from the next lane's quad.  The warp
   // spans 33 quads when s > 0; the 33rd is only needed (by lane 31's column 1) when s == 3, and then lane 0's own quad
@@ -126,6 +118,21 @@ __device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const Noise
   case 2: z[0] = q[2]; z[1] = q[3]; z[2] = n0; z[3] = n1; break;
   default: z[0] = q[3]; z[1] = n0; z[2] = n1; z[3] = n2; break;
   }
+}
+
+// the four normals of columns c..c+3 of row j (global rows g0 = c + nx j ...), one Philox quad per lane plus shuffles
+template <bool INTERIOR = false>
+__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom2 &g, int j, int c, double (&z)[4])
+{
+  if (na.mode == PMG_NOISE_NONE) {
+    z[0] = z[1] = z[2] = z[3] = 0.0;
+    return;
+  }
+  if (na.mode == PMG_NOISE_INJECTED) { // the tape is the caller's: natural row stride, no alignment
+    load4<INTERIOR, false>(na.tape, g, g.nx, j, c, z);
+    return;
+  }
+  philox_normals4(ft, na, (long long)j * g.nx + c, z);
 }
 
 // one node update (src/mc_sor.c:260-268): column M of `row` (row index j), south/north rows, west/east values for M = 0 / 3

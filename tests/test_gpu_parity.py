@@ -483,7 +483,7 @@ def test_ex1_mean_convergence_device_rng(pmg, ctx, orc, pctype, opts, nsamp):
 
 
 # ---- the matrix-free structured path (K1/K3/K4/K5 of SURVEY 8(d)) ------------------------------------------
-@pytest.mark.parametrize("dim,dims", [(2, (129, 129, 1)), (2, (64, 37, 1)), (2, (301, 197, 1)), (2, (9, 5, 1)), (3, (17, 12, 9)), (3, (16, 16, 16))])
+@pytest.mark.parametrize("dim,dims", [(2, (129, 129, 1)), (2, (64, 37, 1)), (2, (301, 197, 1)), (2, (9, 5, 1)), (3, (17, 12, 9)), (3, (16, 16, 16)), (3, (131, 21, 70)), (3, (250, 37, 9))])
 @pytest.mark.parametrize("omega,sweep", [(1.0, 1), (1.3, 3), (0.8, 2)])
 def test_matrix_free_laplace_gibbs_bitexact(pmg, ctx, orc, dim, dims, omega, sweep):
     """The matrix-free operator must reproduce the assembled one (src/problems.c:14-75) bit for bit."""
