@@ -252,7 +252,7 @@ def run_b200(args):
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(2 * 8 * nloc), "d2h_bytes_per_step": int(8 * nloc)},
                "gpu_launches": int(launches), "clocks": clk,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": "fine-level colour sweep (one launch per colour)", "algorithmic_bytes_per_dof_update": bytes_per_update,
+                            "kernel": "fine-level fused red-black sweep (sweep2d_kernel: both colours + Philox normals in one TMA-fed pass)", "algorithmic_bytes_per_dof_update": bytes_per_update,
                             "launch_ms": sweep_ms / launches_per_sweep, "peak_source": peak_src,
                             "frac_of_nominal_8TBs": achieved / 8000.0},
                "gibbs_dof_updates_per_s": world * nloc / (sweep_ms * 1e-3), "setup_s": setup_s,

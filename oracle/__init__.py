@@ -37,7 +37,8 @@ class Noise(C.Structure):
     """orc_noise: the single process-global stream of the reference (src/parmgmc.c:38-42)."""
 
     _fields_ = [("mode", C.c_int), ("tape_ptr", C.c_void_p), ("tape_len", C.c_int64), ("tape_pos", C.c_int64),
-                ("seed_", C.c_uint64), ("call", C.c_uint64), ("x48", C.c_uint64)]
+                ("seed_", C.c_uint64), ("call", C.c_uint64), ("x48", C.c_uint64),
+                ("grid_n", C.c_int64), ("grid_nx", C.c_int64), ("grid_pad", C.c_int64)]
 
     @staticmethod
     def tape(z) -> "Noise":
@@ -48,9 +49,14 @@ class Noise(C.Structure):
         return ns
 
     @staticmethod
-    def philox(seed: int) -> "Noise":
+    def philox(seed: int, grid=None) -> "Noise":
+        """grid = (nx, ny, nz) of a matrix-free grid operator: its blocks are keyed on the padded index
+        (k ny + j) pitch + i, pitch = nx rounded up to 4 (parmgmc_b200/csrc/philox.cuh)."""
         ns = Noise()
         lib().orc_noise_init_philox(C.byref(ns), seed)
+        if grid is not None:
+            nx, ny, nz = grid
+            ns.grid_n, ns.grid_nx, ns.grid_pad = nx * ny * nz, nx, (-nx) % 4
         return ns
 
     @staticmethod

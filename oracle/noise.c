@@ -11,7 +11,8 @@
  *   rander48  - the reference's default generator (statistics + CPU baseline timing)
  *
  * Philox normal definition (shared with parmgmc_b200/csrc/philox.cuh):
- *   quad q = global_row >> 2;  ctr = (lo32 q, hi32 q, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
+ *   id = global row (for the matrix-free grid operators: the padded natural index, see oracle.h orc_noise.grid_*)
+ *   quad q = id >> 2;  ctr = (lo32 q, hi32 q, lo32 call, hi32 call);  key = (lo32 seed, hi32 seed)
  *   (w0,w1,w2,w3) = philox4x32-10(ctr, key)
  *   rows 4q, 4q+1 use (u1,u2) = ((w0+0.5) 2^-32, (w1+0.5) 2^-32); rows 4q+2, 4q+3 use (w2, w3) likewise
  *   r = sqrt(-2 ln u1);  even row: z = r cospi(2 u2);  odd row: z = r sinpi(2 u2)
@@ -93,6 +94,17 @@ void orc_normal_philox(uint64_t seed, uint64_t call, int64_t row0, int64_t n, do
   }
 }
 
+/* rows of a grid operator: generator index = padded natural index */
+void orc_normal_philox_grid(uint64_t seed, uint64_t call, int64_t row0, int64_t n, int64_t nx, int64_t pad, double *out)
+{
+  for (int64_t g = row0; g < row0 + n; ++g) {
+    const uint64_t id = (uint64_t)(g + (g / nx) * pad);
+    double         zc, zs;
+    philox_pair(seed, call, id >> 1, &zc, &zs);
+    out[g - row0] = (id & 1) ? zs : zc;
+  }
+}
+
 /* rander48 = erand48 (PETSc rander48.c): X <- (0x5DEECE66D X + 0xB) mod 2^48, value X 2^-48 */
 static double rander48_next(uint64_t *x)
 {
@@ -131,7 +143,8 @@ int orc_noise_fill(orc_noise *ns, int64_t row0, int64_t n, double *out)
     memcpy(out, ns->tape + ns->tape_pos, sizeof(double) * (size_t)n);
     ns->tape_pos += n;
   } else if (ns->mode == 1) {
-    orc_normal_philox(ns->seed, ns->call, row0, n, out);
+    if (ns->grid_nx > 0 && ns->grid_pad > 0 && n == ns->grid_n) orc_normal_philox_grid(ns->seed, ns->call, row0, n, ns->grid_nx, ns->grid_pad, out);
+    else orc_normal_philox(ns->seed, ns->call, row0, n, out);
   } else {
     for (int64_t i = 0; i < n; i += 2) { /* parmgmc.c:100-110 */
       const double u1     = rander48_next(&ns->x48);

@@ -66,6 +66,7 @@ void      orc_part_ghost_index(const orc_part *p, int rank, int color, int64_t *
 /* ---- parmgmc.c RNG + noise sources ------------------------------------------------ */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_normal_philox(uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *out);
+void orc_normal_philox_grid(uint64_t seed, uint64_t call, int64_t row0, int64_t n, int64_t nx, int64_t pad, double *out);
 
 typedef struct {
   int           mode; /* 0 = tape (injected), 1 = philox, 2 = rander48 Box-Muller (parmgmc.c:100-110) */
@@ -73,6 +74,9 @@ typedef struct {
   int64_t       tape_len, tape_pos;
   uint64_t      seed, call;
   uint64_t      x48;
+  /* philox mode only: blocks of exactly grid_n rows belong to a matrix-free grid operator of row length grid_nx and are
+   * keyed on the PADDED index id = g + (g / grid_nx) * grid_pad (parmgmc_b200/csrc/philox.cuh); 0 = plain global rows */
+  int64_t grid_n, grid_nx, grid_pad;
 } orc_noise;
 void orc_noise_init_tape(orc_noise *ns, const double *tape, int64_t len);
 void orc_noise_init_philox(orc_noise *ns, uint64_t seed);

@@ -24,6 +24,7 @@
 #include "philox.cuh"
 #include "stream2d.cuh"
 #include "stream3d.cuh"
+#include "sweep2d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -123,6 +124,39 @@ template <int DIM> __device__ __forceinline__ void decode(const Geom &g, int64_t
   }
 }
 
+// ---- TMA descriptors ---------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*pfn_tensor_map_encode_tiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pfn_tensor_map_encode_tiled tensor_map_encoder()
+{
+  static pfn_tensor_map_encode_tiled fn = [] {
+    void                           *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (pfn_tensor_map_encode_tiled)p;
+  }();
+  return fn;
+}
+// FP64 tensor of `rank` dimensions (dims[0] fastest, strides in elements for dims 1..), box in elements; out-of-range
+// coordinates read as zero
+static int make_tensor_map(CUtensorMap &tm, const double *base, int rank, const int64_t *dims, const int64_t *strides, const int *box)
+{
+  pfn_tensor_map_encode_tiled enc = tensor_map_encoder();
+  if (!enc) PMG_FAIL(PMG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int d = 0; d < rank; ++d) {
+    gd[d] = (cuuint64_t)dims[d];
+    bx[d] = (cuuint32_t)box[d];
+    es[d] = 1;
+    if (d > 0) gs[d - 1] = (cuuint64_t)strides[d] * sizeof(double);
+  }
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) PMG_FAIL(PMG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 // ---- LapOp kernels -----------------------------------------------------------------------------------
 // one thread per node of the colour; nodes of a colour in a grid row are i = s, s+2, ...
 template <int DIM> __global__ void __launch_bounds__(256) lap_sweep_kernel(Geom g, int color, LapTab tab, double omo, const double *__restrict__ b, double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, NoiseArgs na)
@@ -147,7 +181,8 @@ template <int DIM> __global__ void __launch_bounds__(256) lap_sweep_kernel(Geom 
   const bool    W = i > 0, E = i < g.n0 - 1, S = j > 0, N = j < g.n1 - 1, D = DIM == 3 && k > 0, U = DIM == 3 && k < g.n2 - 1;
   const int     deg = (int)W + (int)E + (int)S + (int)N + (int)D + (int)U;
   const double  h   = tab.h;
-  double        sum = noisy_rhs(na, idx, tab.sqrtdiag[deg], b ? b[idx] : 0.0);
+  const uint64_t nid = (uint64_t)(((DIM == 3 ? k * g.n1 : 0) + j) * ((g.n0 + 3) & ~(int64_t)3) + i); // padded index (philox.cuh)
+  double         sum = noisy_rhs_id(na, idx, nid, tab.sqrtdiag[deg], b ? b[idx] : 0.0);
   // ascending column order of the assembled row: down, south, west | east, north, up; off-diagonal value -h
   if (DIM == 3) {
     if (D) sum = fma(h, ldg(x, glo, ghi, idx - g.unit, g), sum);
@@ -696,12 +731,118 @@ struct LapOp final : GridOp {
     return 0;
   }
 
+  // ---- 2D plain sweep: sweep2d.cuh (TMA-fed) ----
+  DevBuf<sweep2d::Item> items2;
+  int                   nitems2 = 0, items2_cfg = -1;
+  int build_items2(int by, std::vector<sweep2d::Item> &out) const
+  {
+    using sweep2d::Item;
+    const int         nstrips = (int)((g.n0 + sweep2d::STRIP_OUT - 1) / sweep2d::STRIP_OUT);
+    std::vector<Item> slow, fast;
+    for (int s = 0; s < nstrips; ++s) {
+      const int  c0 = s * sweep2d::STRIP_OUT - 4;
+      const bool edge_strip = !(c0 >= 1 && c0 + 127 <= g.n0 - 2);
+      int64_t    j = g.slo;
+      while (j < g.shi) {
+        const int64_t jb_full = std::min<int64_t>(j + by, g.shi);
+        const bool    interior = !edge_strip && j - 2 >= 1 && jb_full <= g.n1 - 2 && j - 3 >= g.slo && jb_full + 2 < g.shi; // sweep2d_kernel's test
+        const int64_t h  = interior ? by : std::max(2, (by * 3 / 4) & ~1); // edge warps run the table-driven loop: shorter bands
+        const int64_t jb = std::min<int64_t>(j + h, g.shi);
+        (interior ? fast : slow).push_back(Item{s, (int)j, (int)jb});
+        j = jb;
+      }
+    }
+    out = slow;
+    out.insert(out.end(), fast.begin(), fast.end());
+    return (int)out.size();
+  }
+  template <int NOISE, int WARPS, int STAGES, int MINB> int launch2(const sweep2d::Args &a, int &slots)
+  {
+    using namespace sweep2d;
+    auto          kern = sweep2d_kernel<NOISE, WARPS, STAGES, MINB>;
+    const size_t  sm   = smem_bytes<WARPS, STAGES>();
+    static bool   attr_set = false;
+    static int    occ      = 0;
+    if (!attr_set) {
+      PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      PMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, sm));
+      attr_set = true;
+    }
+    slots = occ * WARPS * ctx->sm_count;
+    if (a.nitems > 0) kern<<<(unsigned)((a.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a);
+    return 0;
+  }
+  template <int NOISE> int launch2_cfg(int cfg, const sweep2d::Args &a, int &slots)
+  {
+    switch (cfg) {
+    case 0: return launch2<NOISE, 4, 2, 4>(a, slots); // 128 registers, 16 warps / SM
+    case 1: return launch2<NOISE, 4, 3, 4>(a, slots);
+    case 2: return launch2<NOISE, 4, 2, 5>(a, slots); // 96 registers, 20 warps / SM
+    case 3: return launch2<NOISE, 8, 2, 2>(a, slots);
+    default: return launch2<NOISE, 8, 2, 3>(a, slots); // 80 registers, 24 warps / SM
+    }
+  }
+  int sweep2d_launch(int cfg, const sweep2d::Args &a, int mode, int &slots)
+  {
+    if (mode == PMG_NOISE_NONE) return launch2_cfg<sweep2d::NOISE_NONE>(cfg, a, slots);
+    if (mode == PMG_NOISE_INJECTED) return launch2_cfg<sweep2d::NOISE_TAPE>(cfg, a, slots);
+    return launch2_cfg<sweep2d::NOISE_PHILOX>(cfg, a, slots);
+  }
+  int fused_sweep2_tma(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
+  {
+    using namespace sweep2d;
+    LapTab t;
+    fill_tab(co.omega, t);
+    static const int cfg_env = std::getenv("PMG_SW2_CFG") ? std::atoi(std::getenv("PMG_SW2_CFG")) : 0;
+    static const int by_env  = std::getenv("PMG_SW2_BY") ? std::atoi(std::getenv("PMG_SW2_BY")) : 0;
+    const int        cfg     = std::getenv("PMG_SW2_CFG") && cfg_env >= 0 && cfg_env <= 4 ? cfg_env : 3;
+    Args a;
+    const int64_t dims[2] = {g.n0, g.shi - g.slo}, strides[2] = {1, pitch()};
+    const int     box[2]  = {128, STAGE_ROWS};
+    PMG_TRY(make_tensor_map(a.tm_x, xin, 2, dims, strides, box));
+    PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 2, dims, strides, box));
+    a.nx = (int)g.n0; a.ny = (int)g.n1; a.slo = (int)g.slo; a.shi = (int)g.shi;
+    a.pitch = (int)pitch();
+    a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
+    a.has_b = b ? 1 : 0;
+    a.xout  = xout;
+    a.tape  = na.tape;
+    a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega;
+    for (int d = 0; d < 5; ++d) a.coef[d] = Coef{t.idiag[d], t.sqrtdiag[d], 1.0 - co.omega, 0.0};
+    a.coef[5] = Coef{0.0, 0.0, 0.0, 0.0};
+    philox_expand_keys(na.seed, a.pk);
+    a.call_lo = (uint32_t)na.call; a.call_hi = (uint32_t)(na.call >> 32);
+    if (items2_cfg != cfg) { // size the bands so that the work list is one resident wave
+      a.items = nullptr; a.nitems = 0;
+      int slots = 0;
+      PMG_TRY(sweep2d_launch(cfg, a, na.mode, slots));
+      std::vector<Item> list;
+      const int         nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
+      int by = by_env > 0 ? by_env : std::max<int>(2, (int)(((g.shi - g.slo) * nstrips + slots - 1) / std::max(1, slots)));
+      by += by & 1;
+      while (build_items2(by, list) > slots && by_env <= 0 && by < g.shi - g.slo) by += 2;
+      nitems2 = (int)list.size();
+      PMG_TRY(items2.upload(list, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      items2_cfg = cfg;
+    }
+    a.items = items2.p; a.nitems = nitems2;
+    int slots = 0;
+    PMG_TRY(sweep2d_launch(cfg, a, na.mode, slots));
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+
   int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
   {
     if (g.dim == 3) {
       if (xc || bc) PMG_FAIL(PMG_ERR_SUP, "the 3D fused sweep does not include the grid transfers");
       return fused_sweep3(dir, co, b, xin, xout, na);
     }
+    static const bool no_tma = std::getenv("PMG_NO_TMA") != nullptr;
+    if (!xc && !bc && xin && !no_tma) return fused_sweep2_tma(dir, co, b, xin, xout, na);
     using namespace stream2d;
     LapTab t;
     fill_tab(co.omega, t);

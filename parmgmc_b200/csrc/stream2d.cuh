@@ -92,37 +92,19 @@ __device__ __forceinline__ void load4(const double *__restrict__ v, const Geom2 
   for (int m = 0; m < 4; ++m) out[m] = (rowok && c + m >= 0 && c + m < g.nx) ? p[m] : 0.0;
 }
 
-// the four normals of global rows g0 .. g0+3 (g0 = 0 mod 4 is NOT required; it is warp-uniform mod 4 because a lane's first
-// column is a multiple of 4): one Philox quad per lane plus shuffles from the next lane
+// the four normals of generator indices g0 .. g0+3, g0 = 0 mod 4 (padded indices, philox.cuh): one Philox call per lane
 __device__ __forceinline__ void philox_normals4(const fastnormal::Tables &ft, const NoiseArgs &na, long long g0, double (&z)[4])
 {
-  // g0 may be negative for the left halo lane of the first strip
-  const int       s  = (int)(g0 & 3);           // warp uniform: c = 0 mod 4
-  // lane l computes the quad that holds its first element; elements s+m >= 4 come from the next lane's quad.  The warp
-  // spans 33 quads when s > 0; the 33rd is only needed (by lane 31's column 1) when s == 3, and then lane 0's own quad
-  // is not needed by anyone, so lane 0 computes the 33rd one instead and the shuffle rotates.
-  const int       lane = threadIdx.x & 31;
-  const long long quad = (g0 >> 2) + ((s == 3 && lane == 0) ? 32 : 0);
-  double          q[4];
-  {
-    uint32_t w0, w1, w2, w3;
-    philox4x32_10((uint32_t)quad, (uint32_t)((uint64_t)quad >> 32), (uint32_t)na.call, (uint32_t)(na.call >> 32), (uint32_t)na.seed, (uint32_t)(na.seed >> 32), w0, w1, w2, w3);
-    fastnormal::box_muller(ft, w0, w1, q[0], q[1]);
-    fastnormal::box_muller(ft, w2, w3, q[2], q[3]);
-  }
-  const int    src = (lane + 1) & 31;
-  const double n0 = __shfl_sync(0xffffffffu, q[0], src), n1 = __shfl_sync(0xffffffffu, q[1], src), n2 = __shfl_sync(0xffffffffu, q[2], src);
-  switch (s) {
-  case 0: z[0] = q[0]; z[1] = q[1]; z[2] = q[2]; z[3] = q[3]; break;
-  case 1: z[0] = q[1]; z[1] = q[2]; z[2] = q[3]; z[3] = n0; break;
-  case 2: z[0] = q[2]; z[1] = q[3]; z[2] = n0; z[3] = n1; break;
-  default: z[0] = q[3]; z[1] = n0; z[2] = n1; z[3] = n2; break;
-  }
+  const long long quad = g0 >> 2; // may be negative for halo lanes outside the grid: those values are never used
+  uint32_t        w0, w1, w2, w3;
+  philox4x32_10((uint32_t)quad, (uint32_t)((uint64_t)quad >> 32), (uint32_t)na.call, (uint32_t)(na.call >> 32), (uint32_t)na.seed, (uint32_t)(na.seed >> 32), w0, w1, w2, w3);
+  fastnormal::box_muller(ft, w0, w1, z[0], z[1]);
+  fastnormal::box_muller(ft, w2, w3, z[2], z[3]);
 }
 
 // the four normals of columns c..c+3 of row j (global rows g0 = c + nx j ...), one Philox quad per lane plus shuffles
 template <bool INTERIOR = false>
-__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom2 &g, int j, int c, double (&z)[4])
+__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom2 &g, int pitch, int j, int c, double (&z)[4])
 {
   if (na.mode == PMG_NOISE_NONE) {
     z[0] = z[1] = z[2] = z[3] = 0.0;
@@ -132,7 +114,7 @@ __device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const Noise
     load4<INTERIOR, false>(na.tape, g, g.nx, j, c, z);
     return;
   }
-  philox_normals4(ft, na, (long long)j * g.nx + c, z);
+  philox_normals4(ft, na, (long long)j * pitch + c, z);
 }
 
 // one node update (src/mc_sor.c:260-268): column M of `row` (row index j), south/north rows, west/east values for M = 0 / 3
@@ -288,7 +270,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       if (a.b) prefetch_l1(a.b + (size_t)(jj + PF - g.slo) * a.pitch + c);
     }
     double z[4];
-    noise4<INTERIOR>(ft, a.na, g, jj, c, z);
+    noise4<INTERIOR>(ft, a.na, g, a.pitch, jj, c, z);
 
     const bool even = ((jj + a.flip) & 1) == 0; // first-colour columns of row jj are M = 0,2 (else 1,3)
     { // ---- phase A: first-colour nodes of row jj ----

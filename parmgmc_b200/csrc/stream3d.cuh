@@ -77,7 +77,7 @@ __device__ __forceinline__ void load4(const double *__restrict__ v, const Geom3 
 }
 
 template <bool INTERIOR>
-__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom3 &g, int y, int k, int c, double (&z)[4])
+__device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const NoiseArgs &na, const Geom3 &g, int pitch, int y, int k, int c, double (&z)[4])
 {
   if (na.mode == PMG_NOISE_NONE) {
     z[0] = z[1] = z[2] = z[3] = 0.0;
@@ -87,7 +87,7 @@ __device__ __forceinline__ void noise4(const fastnormal::Tables &ft, const Noise
     load4<INTERIOR, false>(na.tape, g, g.nx, (long long)g.nx * g.ny, y, k, c, z);
     return;
   }
-  stream2d::philox_normals4(ft, na, ((long long)k * g.ny + y) * g.nx + c, z);
+  stream2d::philox_normals4(ft, na, ((long long)k * g.ny + y) * pitch + c, z);
 }
 
 // one node update, column M of `row` = row (y, k); accumulation order of the assembled row: down, south, west, east, north, up
@@ -160,7 +160,7 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
     load4<INTERIOR, true>(a.b, g, a.pitch, a.pplane, y, kk, c, b0);
     if (halo_row) load4<INTERIOR, true>(a.xin, g, a.pitch, a.pplane, yo, kk, c, xo);
     double z[4];
-    noise4<INTERIOR>(ft, a.na, g, y, kk, c, z);
+    noise4<INTERIOR>(ft, a.na, g, a.pitch, y, kk, c, z);
 
     const bool even = ((y + kk + a.flip) & 1) == 0; // first-colour columns of row (y, kk) are M = 0,2 (else 1,3)
     { // ---- phase A: first-colour nodes of plane kk; every neighbour is still old ----
