@@ -602,6 +602,10 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(v.x2.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_y.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_b.alloc((size_t)v.op->fused_size()));
+      // the pad columns of the pitched vectors are read by the TMA as ordinary elements and must stay zero
+      PMG_TRY(v.x2.zero(ctx->stream));
+      PMG_TRY(pc->pit_y.zero(ctx->stream));
+      PMG_TRY(pc->pit_b.zero(ctx->stream));
     }
   }
   const std::string cyc = pc->get("pc_b200_cycle", "direct");
@@ -894,6 +898,10 @@ int pmg_pc_setup(pmg_pc pc)
       PMG_TRY(pc->scratch.alloc((size_t)pc->mat->op->fused_size()));
       PMG_TRY(pc->pit_y.alloc((size_t)pc->mat->op->fused_size()));
       PMG_TRY(pc->pit_b.alloc((size_t)pc->mat->op->fused_size()));
+      // the pad columns of the pitched vectors are read by the TMA as ordinary elements and must stay zero
+      PMG_TRY(pc->scratch.zero(ctx->stream));
+      PMG_TRY(pc->pit_y.zero(ctx->stream));
+      PMG_TRY(pc->pit_b.zero(ctx->stream));
     }
   }
   PMG_TRY(pc_alloc_staging(pc));

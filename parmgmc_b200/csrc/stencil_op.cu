@@ -23,8 +23,8 @@
 #include "common.hpp"
 #include "philox.cuh"
 #include "stream2d.cuh"
-#include "stream3d.cuh"
 #include "sweep2d.cuh"
+#include "sweep3d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -140,7 +140,7 @@ static pfn_tensor_map_encode_tiled tensor_map_encoder()
 }
 // FP64 tensor of `rank` dimensions (dims[0] fastest, strides in elements for dims 1..), box in elements; out-of-range
 // coordinates read as zero
-static int make_tensor_map(CUtensorMap &tm, const double *base, int rank, const int64_t *dims, const int64_t *strides, const int *box)
+static int make_tensor_map(CUtensorMap &tm, const double *base, int rank, const int64_t *dims, const int64_t *strides, const int *box, bool swizzle32 = false)
 {
   pfn_tensor_map_encode_tiled enc = tensor_map_encoder();
   if (!enc) PMG_FAIL(PMG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -152,7 +152,7 @@ static int make_tensor_map(CUtensorMap &tm, const double *base, int rank, const 
     es[d] = 1;
     if (d > 0) gs[d - 1] = (cuuint64_t)strides[d] * sizeof(double);
   }
-  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) PMG_FAIL(PMG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
@@ -662,21 +662,21 @@ struct LapOp final : GridOp {
   }
   // b, xin, xout are pitched (fused_size() elements); xc / bc are the coarse level's natural-layout vectors
   // ---- 3D: stream3d.cuh ----
-  DevBuf<stream3d::Item> items3;
-  int                    nitems3 = 0, items3_bz = 0, items3_nw = 0;
+  DevBuf<sweep3d::Item> items3;
+  int                   nitems3 = 0, items3_bz = 0, items3_nw = 0;
   int build_items3(int bz, int NW3) // NW3 warps (grid rows) per CTA tile: NW3 - 2 output rows + 2 halo rows
   {
-    using stream3d::Item;
-    const int         nstrips = (int)((g.n0 + stream3d::STRIP_OUT - 1) / stream3d::STRIP_OUT), ty = NW3 - 2;
+    using sweep3d::Item;
+    const int         nstrips = (int)((g.n0 + sweep3d::STRIP_OUT - 1) / sweep3d::STRIP_OUT), ty = NW3 - 2;
     std::vector<Item> slow, fast;
     for (int64_t k = g.slo; k < g.shi;) {
       const int64_t kb_full = std::min<int64_t>(k + bz, g.shi);
-      const bool    kin = k - 2 >= 1 && kb_full + 1 <= g.n2 - 2 && k - 2 >= g.slo && kb_full + 1 < g.shi;
-      const int64_t kb = kin ? kb_full : std::min<int64_t>(k + std::max(1, bz / 2), g.shi); // predicated tiles: half bands
+      const bool    kin = k - 1 >= 1 && kb_full <= g.n2 - 2 && k - 2 >= g.slo && kb_full + 1 < g.shi; // sweep3d_kernel's test
+      const int64_t kb = kin ? kb_full : std::min<int64_t>(k + std::max(1, bz * 3 / 4), g.shi); // edge tiles: shorter bands
       for (int64_t ya = 0; ya < g.n1; ya += ty)
         for (int s = 0; s < nstrips; ++s) {
-          const int  c0 = s * stream3d::STRIP_OUT - 4;
-          const bool interior = kin && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 2 >= 0 && ya + NW3 - 2 <= g.n1 - 2;
+          const int  c0 = s * sweep3d::STRIP_OUT - 4;
+          const bool interior = kin && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 1 >= 1 && ya + NW3 - 2 <= g.n1 - 2;
           (interior ? fast : slow).push_back(Item{s, (int)ya, (int)k, (int)kb});
         }
       k = kb;
@@ -689,42 +689,71 @@ struct LapOp final : GridOp {
     items3_nw = NW3;
     return 0;
   }
-  template <int NW> int launch3(const stream3d::Args &a)
+  template <int NOISE, int NW, int SX, int SB, int MINB> int launch3(sweep3d::Args &a, const double *b, const double *xin)
   {
-    using namespace stream3d;
-    static bool attr_set = false;
+    using namespace sweep3d;
+    auto         kern = sweep3d_kernel<NOISE, NW, SX, SB, MINB>;
+    const size_t sm   = Smem<NW, SX, SB>::total;
+    static bool  attr_set = false;
     if (!attr_set) {
-      PMG_CUDA(cudaFuncSetAttribute(lap_stream3d_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<NW>()));
+      PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       attr_set = true;
     }
-    lap_stream3d_kernel<NW><<<(unsigned)nitems3, NW * 32, smem_bytes<NW>(), ctx->stream>>>(a);
+    static const bool swz = std::getenv("PMG_SW3_PLAIN") == nullptr; // SWIZZLE_32B boxes: conflict-free shared-memory reads
+    a.swizzle = swz ? 1 : 0;
+    if (swz) {
+      const int64_t dims[4] = {4, pitch() / 4, g.n1, g.shi - g.slo}, strides[4] = {1, 4, pitch(), pitch() * g.n1};
+      const int     boxx[4] = {4, 32, NW + 2, 1}, boxb[4] = {4, 32, NW, 1};
+      PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, true));
+      PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, true));
+    } else {
+      const int64_t dims[4] = {pitch(), g.n1, g.shi - g.slo, 1}, strides[4] = {1, pitch(), pitch() * g.n1, pitch() * g.n1 * (g.shi - g.slo)};
+      const int     boxx[4] = {128, NW + 2, 1, 1}, boxb[4] = {128, NW, 1, 1};
+      PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, false));
+      PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, false));
+    }
+    static const int bz_env = std::getenv("PMG_SW3_BZ") ? std::atoi(std::getenv("PMG_SW3_BZ")) : 0;
+    const int        bz     = bz_env > 0 ? bz_env : 64;
+    if (items3_bz != bz || items3_nw != NW) PMG_TRY(build_items3(bz, NW));
+    a.items = items3.p;
+    kern<<<(unsigned)nitems3, NW * 32, sm, ctx->stream>>>(a);
     return 0;
+  }
+  template <int NOISE> int launch3_cfg(int cfg, sweep3d::Args &a, const double *b, const double *xin)
+  {
+    switch (cfg) {
+    case 0: return launch3<NOISE, 16, 3, 2, 1>(a, b, xin); // 512 threads, 128 registers, 1 CTA / SM
+    case 1: return launch3<NOISE, 8, 3, 2, 2>(a, b, xin);  // 256 threads, 128 registers, 2 CTAs / SM
+    case 2: return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);
+    case 3: return launch3<NOISE, 16, 5, 3, 1>(a, b, xin);
+    case 4: return launch3<NOISE, 16, 6, 4, 1>(a, b, xin);
+    default: return launch3<NOISE, 8, 5, 3, 2>(a, b, xin);
+    }
   }
   int fused_sweep3(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
   {
-    using namespace stream3d;
+    using namespace sweep3d;
     if (!xin) PMG_FAIL(PMG_ERR_ARG, "fused 3D sweep needs an iterate");
     LapTab t;
     fill_tab(co.omega, t);
-    static const int bz_env = std::getenv("PMG_STREAM_BZ") ? std::atoi(std::getenv("PMG_STREAM_BZ")) : 0;
-    static const int nw_env = std::getenv("PMG_STREAM_NW") ? std::atoi(std::getenv("PMG_STREAM_NW")) : 0;
-    const int        bz     = bz_env > 0 ? bz_env : 32;
-    const int        nw     = (nw_env == 10 || nw_env == 16 || nw_env == 20) ? nw_env : (g.n1 >= 64 ? 20 : 10);
-    if (items3_bz != bz || items3_nw != nw) PMG_TRY(build_items3(bz, nw));
+    static const int cfg_env = std::getenv("PMG_SW3_CFG") ? std::atoi(std::getenv("PMG_SW3_CFG")) : -1;
+    const int        cfg     = cfg_env >= 0 && cfg_env <= 5 ? cfg_env : (g.n1 >= 48 ? 2 : 1);
     Args a;
-    a.g      = Geom3{(int)g.n0, (int)g.n1, (int)g.n2, (int)g.slo, (int)g.shi};
+    a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.pitch  = (int)pitch();
     a.pplane = (long long)pitch() * g.n1;
-    a.items  = items3.p;
     a.flip   = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
-    a.xin = xin; a.b = b; a.xout = xout;
-    for (int d = 0; d < 7; ++d) { a.tab.diag[d] = t.diag[d]; a.tab.idiag[d] = t.idiag[d]; a.tab.sqrtdiag[d] = t.sqrtdiag[d]; }
-    a.tab.h   = t.h;
-    a.tab.omo = 1.0 - co.omega;
-    a.na      = na;
-    if (nw == 10) PMG_TRY(launch3<10>(a));
-    else if (nw == 16) PMG_TRY(launch3<16>(a));
-    else PMG_TRY(launch3<20>(a));
+    a.has_b  = b ? 1 : 0;
+    a.xout   = xout;
+    a.tape   = na.tape;
+    a.h = t.h; a.idiag = t.idiag[6]; a.sd = t.sqrtdiag[6]; a.omo = 1.0 - co.omega;
+    for (int d = 0; d < 7; ++d) a.coef[d] = sweep2d::Coef{t.idiag[d], t.sqrtdiag[d], 1.0 - co.omega, 0.0};
+    a.coef[7] = sweep2d::Coef{0.0, 0.0, 0.0, 0.0};
+    philox_expand_keys(na.seed, a.pk);
+    a.call_lo = (uint32_t)na.call; a.call_hi = (uint32_t)(na.call >> 32);
+    if (na.mode == PMG_NOISE_NONE) PMG_TRY(launch3_cfg<NOISE_NONE>(cfg, a, b, xin));
+    else if (na.mode == PMG_NOISE_INJECTED) PMG_TRY(launch3_cfg<NOISE_TAPE>(cfg, a, b, xin));
+    else PMG_TRY(launch3_cfg<NOISE_PHILOX>(cfg, a, b, xin));
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     ctx->dof_updates += g.nl;
@@ -797,10 +826,19 @@ struct LapOp final : GridOp {
     static const int by_env  = std::getenv("PMG_SW2_BY") ? std::atoi(std::getenv("PMG_SW2_BY")) : 0;
     const int        cfg     = std::getenv("PMG_SW2_CFG") && cfg_env >= 0 && cfg_env <= 4 ? cfg_env : 3;
     Args a;
-    const int64_t dims[2] = {g.n0, g.shi - g.slo}, strides[2] = {1, pitch()};
-    const int     box[2]  = {128, STAGE_ROWS};
-    PMG_TRY(make_tensor_map(a.tm_x, xin, 2, dims, strides, box));
-    PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 2, dims, strides, box));
+    static const bool swz = std::getenv("PMG_SW2_SWIZZLE") != nullptr;
+    a.swizzle = swz ? 1 : 0;
+    if (swz) {
+      const int64_t dims[3] = {4, pitch() / 4, g.shi - g.slo}, strides[3] = {1, 4, pitch()};
+      const int     box[3]  = {4, 32, STAGE_ROWS};
+      PMG_TRY(make_tensor_map(a.tm_x, xin, 3, dims, strides, box, true));
+      PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 3, dims, strides, box, true));
+    } else { // pad columns are real (zero) elements in both views
+      const int64_t dims[3] = {pitch(), g.shi - g.slo, 1}, strides[3] = {1, pitch(), pitch() * (g.shi - g.slo)};
+      const int     box[3]  = {128, STAGE_ROWS, 1};
+      PMG_TRY(make_tensor_map(a.tm_x, xin, 3, dims, strides, box, false));
+      PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 3, dims, strides, box, false));
+    }
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.pitch = (int)pitch();
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;

@@ -14,7 +14,7 @@
 //  * Rows arrive through the TMA: lane 0 of each warp issues cp.async.bulk.tensor.2d copies of 128 x 2 boxes of x and b
 //    into the warp's private ring of shared-memory stages and every lane waits on the stage's mbarrier.  In-flight data
 //    costs no registers, the prefetch distance is a ring depth, and out-of-grid coordinates are zero-filled by the
-//    hardware, so grid edges need no load predicates.
+//    hardware, so grid edges need no load predicates (the pad columns nx .. pitch-1 of the vectors are kept at zero).
 //  * The loop is unrolled over the two row parities: no colour selects, no divergent code.
 //  * Everything that does not change in the loop is a compile-time choice (noise mode, interior / edge warp).
 //  * The generator is keyed on the padded index (philox.cuh), so a thread's four columns are one Philox call.
@@ -46,7 +46,7 @@ struct Coef { // per-node coefficients of the edge warps, indexed by the number 
 };
 
 struct Args {
-  CUtensorMap   tm_x, tm_b; // {nx, local rows} FP64 tensors with row stride pitch, box 128 x 2
+  CUtensorMap   tm_x, tm_b; // {4, pitch/4, local rows} FP64 tensors (SWIZZLE_32B), box 4 x 32 x 2 = 128 columns x 2 rows
   int           nx, ny;     // global grid
   int           slo, shi;   // owned rows (the tensors' row 0 is grid row slo)
   const Item   *items;
@@ -54,6 +54,7 @@ struct Args {
   int           pitch; // row stride of xout (and of the tensors)
   int           flip;  // 0: forward sweep (colour (i+j) even first); 1: backward
   int           has_b;
+  int           swizzle; // 1: tensors are {4, pitch/4, rows} with SWIZZLE_32B; 0: {pitch, rows, 1}, plain rows
   double       *xout;
   const double *tape; // injected noise of this block: natural layout (row stride nx), local rows
   double        h, idiag, sd, omo; // interior coefficients
@@ -80,14 +81,21 @@ __device__ __forceinline__ void     mbar_wait(uint32_t bar, uint32_t parity)
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
+// The tensors are described to the TMA as {4, pitch/4, rows...} with SWIZZLE_32B: a row of 128 doubles lands in shared memory
+// as 32 lane segments of 32 bytes, with the two 16-byte halves of a segment exchanged in every other 128-byte line.  A
+// lane's LDS.128 of "its first half" then hits banks that the lanes 4 further do not (conflict-free row reads).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar)
 {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void lds256(uint32_t addr, double (&v)[4])
+__device__ __forceinline__ uint32_t lane_seg(int lane) { return (uint32_t)(lane * 32); }           // byte offset of the lane's segment in a row
+__device__ __forceinline__ uint32_t lane_swz(int lane) { return (uint32_t)(((lane >> 2) & 1) * 16); } // swizzle of that segment
+// the lane's four doubles of the row at `row` (shared-memory byte address of the row start, 1024-byte aligned)
+__device__ __forceinline__ void lds256(uint32_t row, int lane, double (&v)[4], bool swizzled = true)
 {
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(addr + 16));
+  const uint32_t a = row + lane_seg(lane), s = swizzled ? lane_swz(lane) : 0u;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a + s));
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + (16u - s)));
 }
 __device__ __forceinline__ void st256(double *p, const double (&v)[4]) { asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory"); }
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
@@ -194,7 +202,7 @@ template <int NOISE, bool INTERIOR> struct Warp {
 };
 
 // smem layout per CTA: [WARPS][STAGES] stages of STAGE_BYTES | tables | coef | mbarriers
-template <int WARPS, int STAGES> constexpr size_t smem_bytes() { return (size_t)WARPS * STAGES * STAGE_BYTES + sizeof(fastnormal::SharedTables) + 6 * sizeof(Coef) + (size_t)WARPS * (STAGES + 1) * 8 + 128; }
+template <int WARPS, int STAGES> constexpr size_t smem_bytes() { return (size_t)WARPS * STAGES * STAGE_BYTES + sizeof(fastnormal::SharedTables) + 6 * sizeof(Coef) + (size_t)WARPS * (STAGES + 1) * 8 + 1024; }
 
 template <int NOISE, bool INTERIOR, int STAGES>
 __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t ring, uint32_t bars, int lane, const Item it)
@@ -207,27 +215,34 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   const int T  = (N + 1) >> 1;    // stages: stage t feeds steps J0+2t, J0+2t+1 with x rows J0+2t+1, J0+2t+2 and b rows J0+2t, J0+2t+1
   const uint32_t bytes = a.has_b ? STAGE_BYTES : STAGE_BYTES / 2;
   const uint32_t bar_pro = bars + STAGES * 8;
+  const bool     swz     = a.swizzle != 0;
 
   auto issue = [&](int t) {
     const int      s   = t % STAGES;
     const uint32_t dst = ring + s * STAGE_BYTES, bar = bars + s * 8;
     mbar_expect_tx(bar, bytes);
-    tma_load_2d(dst, &a.tm_x, c0, J0 + 2 * t + 1 - a.slo, bar);
-    if (a.has_b) tma_load_2d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, c0, J0 + 2 * t - a.slo, bar);
+    if (a.swizzle) {
+      tma_load_3d(dst, &a.tm_x, 0, c0 >> 2, J0 + 2 * t + 1 - a.slo, bar);
+      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, 0, c0 >> 2, J0 + 2 * t - a.slo, bar);
+    } else {
+      tma_load_3d(dst, &a.tm_x, c0, J0 + 2 * t + 1 - a.slo, 0, bar);
+      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, c0, J0 + 2 * t - a.slo, 0, bar);
+    }
   };
   // prologue rows J0-1, J0 travel through the x half of the LAST ring slot, whose first real stage is issued afterwards
   if (lane == 0) {
     mbar_expect_tx(bar_pro, STAGE_ROWS * ROW_BYTES);
-    tma_load_2d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, J0 - 1 - a.slo, bar_pro);
+    if (a.swizzle) tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, 0, c0 >> 2, J0 - 1 - a.slo, bar_pro);
+    else tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, J0 - 1 - a.slo, 0, bar_pro);
     for (int t = 0; t < STAGES - 1 && t < T; ++t) issue(t);
   }
   double xss[4] = {0, 0, 0, 0}, xs[4], x0[4], wk[2] = {0, 0};
   int    cis[4] = {5, 5, 5, 5}; // coefficient classes of row jj-1
   mbar_wait(bar_pro, 0);
   {
-    const uint32_t p = ring + (STAGES - 1) * STAGE_BYTES + lane * 32;
-    lds256(p, xs);
-    lds256(p + ROW_BYTES, x0);
+    const uint32_t p = ring + (STAGES - 1) * STAGE_BYTES;
+    lds256(p, lane, xs, swz);
+    lds256(p + ROW_BYTES, lane, x0, swz);
   }
   __syncwarp();
   if (lane == 0 && STAGES - 1 < T) issue(STAGES - 1);
@@ -243,17 +258,17 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   int jj = J0;
   for (int t = 0; t < T; ++t, jj += 2) {
     const int      s   = t % STAGES;
-    const uint32_t src = ring + s * STAGE_BYTES + lane * 32;
+    const uint32_t src = ring + s * STAGE_BYTES;
     mbar_wait(bars + s * 8, (uint32_t)(t / STAGES) & 1u);
     double xa[4], ba[4] = {0, 0, 0, 0};
-    lds256(src, xa);
-    if (a.has_b) lds256(src + 2 * ROW_BYTES, ba);
+    lds256(src, lane, xa, swz);
+    if (a.has_b) lds256(src + 2 * ROW_BYTES, lane, ba, swz);
     W.template step<0>(jj, xss, xs, x0, xa, ba, wk, cis);
     row_classes(jj, cis);
     if (2 * t + 1 < N) {
       double xb[4], bb[4] = {0, 0, 0, 0};
-      lds256(src + ROW_BYTES, xb);
-      if (a.has_b) lds256(src + 3 * ROW_BYTES, bb);
+      lds256(src + ROW_BYTES, lane, xb, swz);
+      if (a.has_b) lds256(src + 3 * ROW_BYTES, lane, bb, swz);
       __syncwarp();
       if (lane == 0 && t + STAGES < T) issue(t + STAGES);
       W.template step<1>(jj + 1, xs, x0, xa, xb, bb, wk, cis);
@@ -271,7 +286,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
 template <int NOISE, int WARPS, int STAGES, int MINB> __global__ void __launch_bounds__(WARPS * 32, MINB) sweep2d_kernel(const __grid_constant__ Args a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char *base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  unsigned char *base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   fastnormal::SharedTables *fts  = reinterpret_cast<fastnormal::SharedTables *>(base + (size_t)WARPS * STAGES * STAGE_BYTES);
   Coef                     *coef = reinterpret_cast<Coef *>(fts + 1);
   unsigned long long       *bar  = reinterpret_cast<unsigned long long *>(coef + 6);

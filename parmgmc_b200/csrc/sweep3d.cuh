@@ -1,0 +1,307 @@
+// sweep3d.cuh -- TMA-fed fused red-black Gibbs sweep for the matrix-free 3D 7-point operator (K1 of SURVEY 8(d)): both
+// colours, the noise and the right-hand-side perturbation in ONE pass over memory (the reference needs
+// VecSetRandomStandardNormal, VecPointwiseMult, VecAXPY and the two colour phases of MCSORApply:
+// src/pc_mcgibbs.c:119-128, src/mc_sor.c:257-271).
+//
+// 2.5D blocking.  A CTA of NW warps owns a tile of 120 columns (x) by NW-2 rows (y) and walks along z through a band of
+// planes.  A warp is one grid row of the tile (lane l owns columns c0+4l .. c0+4l+3, lanes 0 / 31 are halo columns, as in
+// sweep2d.cuh); warps 0 and NW-1 are halo rows.  Along z a thread keeps a rolling window of three planes in registers.
+// At plane step k the first colour of plane k is updated (all its neighbours are still old), then the second colour of
+// plane k-1 (all its neighbours are new by then), and plane k-1 is written out of place: 8 B of x and 8 B of b read and
+// 8 B written per DOF-update instead of the 48 B a colour-by-colour sweep moves.
+//
+// Data movement: one elected thread feeds two shared-memory rings with the TMA -- 128 x (NW+2) x 1 boxes of x (plane k+1:
+// the "up" neighbours, and one step later the OLD north / south neighbours of plane k+1, read straight from the box) and
+// 128 x NW x 1 boxes of b; out-of-grid coordinates are zero-filled by the hardware.  The half-updated plane k is
+// published to the neighbouring rows through a double-buffered shared-memory array; one __syncthreads per plane.
+// East / west neighbours come from warp shuffles.  Arithmetic per node is exactly lap_sweep_kernel<3>'s (stencil_op.cu),
+// fma for fma (a missing neighbour adds h * 0, which is exact), so the result is bit-identical to the colour-by-colour path.
+#pragma once
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.hpp"
+#include "fastnormal.cuh"
+#include "philox.cuh"
+#include "sweep2d.cuh"
+
+namespace sweep3d {
+
+using sweep2d::lds256;
+using sweep2d::mbar_expect_tx;
+using sweep2d::mbar_init;
+using sweep2d::mbar_wait;
+using sweep2d::shfl_dn1;
+using sweep2d::shfl_up1;
+using sweep2d::smem_u32;
+using sweep2d::st256;
+using sweep2d::tma_load_3d;
+using sweep2d::Coef;
+
+constexpr int STRIP_OUT = 120;
+constexpr int ROW_BYTES = 128 * 8;
+enum { NOISE_NONE = 0, NOISE_TAPE = 1, NOISE_PHILOX = 2 };
+
+// one CTA's work: output columns of strip `strip`, output rows [ya, ya + NW - 2), output planes [ka, kb)
+struct Item {
+  int strip, ya, ka, kb;
+};
+
+struct Args {
+  CUtensorMap   tm_x, tm_b; // {4, pitch/4, ny, local planes} FP64 tensors (SWIZZLE_32B); boxes 4 x 32 x (NW+2) x 1 and 4 x 32 x NW x 1
+  int           nx, ny, nz;
+  int           slo, shi; // owned planes (the tensors' plane 0 is grid plane slo)
+  const Item   *items;
+  int           pitch;    // row stride of xout
+  long long     pplane;   // plane stride of xout = pitch * ny
+  int           flip;     // 0: forward sweep (colour (i+j+k) even first); 1: backward
+  int           has_b;
+  int           swizzle;  // 1: tensors {4, pitch/4, ny, planes} with SWIZZLE_32B; 0: {pitch, ny, planes, 1}, plain rows
+  double       *xout;
+  const double *tape;     // injected noise of this block: natural layout, local planes
+  double        h, idiag, sd, omo; // interior coefficients
+  Coef          coef[8];  // by number of existing neighbours; 7 = no such node
+  PhiloxKeys    pk;
+  uint32_t      call_lo, call_hi;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ double lds64(uint32_t addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+// byte offset of column M of the lane's segment inside a TMA row (SWIZZLE_32B layout, sweep2d.cuh)
+__device__ __forceinline__ uint32_t box_off(int lane, int M, bool swz) { return sweep2d::lane_seg(lane) + (((uint32_t)(M >> 1) * 16u) ^ (swz ? sweep2d::lane_swz(lane) : 0u)) + (uint32_t)(M & 1) * 8u; }
+// the half-updated planes are published component-major ([4][32] doubles per row): conflict-free 8-byte accesses
+__device__ __forceinline__ uint32_t new_off(int lane, int M) { return (uint32_t)(M * 256 + lane * 8); }
+
+template <int NW, int SX, int SB> struct Smem {
+  static constexpr int    XSTAGE = (NW + 2) * ROW_BYTES, BSTAGE = NW * ROW_BYTES, NEWBUF = NW * ROW_BYTES;
+  static constexpr size_t off_x = 0, off_b = off_x + (size_t)SX * XSTAGE, off_new = off_b + (size_t)SB * BSTAGE, off_tab = off_new + 2 * (size_t)NEWBUF;
+  static constexpr size_t off_coef = off_tab + sizeof(fastnormal::SharedTables), off_bar = off_coef + 8 * sizeof(Coef), total = off_bar + (SX + SB) * 8 + 1024;
+};
+
+// src/mc_sor.c:260-268 for column M of `row`: accumulation order of the assembled row (down, south, west, east, north, up)
+template <int M, bool INTERIOR>
+__device__ __forceinline__ void update(const Args &a, const Coef *coef, double (&row)[4], double down, double south, double north, double up, double west, double east, double w, int ci)
+{
+  const double xw = M == 0 ? west : row[M == 0 ? 0 : M - 1];
+  const double xe = M == 3 ? east : row[M == 3 ? 3 : M + 1];
+  double       sum = w;
+  sum = fma(a.h, down, sum);
+  sum = fma(a.h, south, sum);
+  sum = fma(a.h, xw, sum);
+  sum = fma(a.h, xe, sum);
+  sum = fma(a.h, north, sum);
+  sum = fma(a.h, up, sum);
+  if (INTERIOR) {
+    const double t0 = __dmul_rn(a.omo, row[M]);
+    row[M]          = fma(a.idiag, sum, t0);
+  } else {
+    const Coef   k  = coef[ci];
+    const double t0 = __dmul_rn(k.omo, row[M]);
+    row[M]          = fma(k.idiag, sum, t0);
+  }
+}
+
+// both colour phases of one plane step for row parity P (first-colour columns M = P, P+2)
+template <int P, bool INTERIOR>
+__device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane, bool swz, bool inner_row, const double (&xm2)[4], double (&xm1)[4], double (&x0)[4], const double (&xp1)[4], uint32_t old_s, uint32_t old_n, uint32_t new_s, uint32_t new_n,
+                                       const double (&w)[4], const double (&wk)[2], const int (&ci)[4], const int (&cis)[4])
+{
+  { // phase A: first colour of plane kk, every neighbour still old
+    const double west = P == 0 ? shfl_up1(x0[3]) : 0.0, east = P == 1 ? shfl_dn1(x0[0]) : 0.0;
+    update<P, INTERIOR>(a, coef, x0, xm1[P], lds64(old_s + box_off(lane, P, swz)), lds64(old_n + box_off(lane, P, swz)), xp1[P], west, east, w[P], ci[P]);
+    update<P + 2, INTERIOR>(a, coef, x0, xm1[P + 2], lds64(old_s + box_off(lane, P + 2, swz)), lds64(old_n + box_off(lane, P + 2, swz)), xp1[P + 2], west, east, w[P + 2], ci[P + 2]);
+  }
+  { // phase B: second colour of plane kk-1 (the same columns), every neighbour new; halo rows take part in the shuffles only
+    const double west = P == 0 ? shfl_up1(xm1[3]) : 0.0, east = P == 1 ? shfl_dn1(xm1[0]) : 0.0;
+    if (inner_row) {
+      update<P, INTERIOR>(a, coef, xm1, xm2[P], lds64(new_s + new_off(lane, P)), lds64(new_n + new_off(lane, P)), x0[P], west, east, wk[0], cis[P]);
+      update<P + 2, INTERIOR>(a, coef, xm1, xm2[P + 2], lds64(new_s + new_off(lane, P + 2)), lds64(new_n + new_off(lane, P + 2)), x0[P + 2], west, east, wk[1], cis[P + 2]);
+    }
+  }
+}
+
+template <int NOISE, bool INTERIOR, int NW, int SX, int SB>
+__device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t sm, const Item it)
+{
+  using L = Smem<NW, SX, SB>;
+  const int  lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int  c0 = it.strip * STRIP_OUT - 4, c = c0 + 4 * lane;
+  const int  y = it.ya - 1 + w;
+  const bool inner_row = w >= 1 && w <= NW - 2;
+  const bool out_thread = inner_row && lane >= 1 && lane <= 30 && (INTERIOR || (c < a.nx && y < a.ny));
+  const int  K0 = it.ka - 1, K1 = it.kb;         // plane steps; phase B planes K0 .. K1-1, of which ka .. kb-1 are stored
+  const int  nsteps = K1 - K0 + 1;
+  const uint32_t bar_x = sm + (uint32_t)L::off_bar, bar_b = bar_x + SX * 8;
+  const uint32_t xbytes = L::XSTAGE, bbytes = L::BSTAGE;
+  const bool     swz = a.swizzle != 0;
+
+  // x sequence q = 0, 1, ...: plane K0 - 1 + q;  b sequence r = 0, 1, ...: plane K0 + r
+  auto issue_x = [&](int q) {
+    const uint32_t bar = bar_x + (q % SX) * 8;
+    mbar_expect_tx(bar, xbytes);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, 0, c0 >> 2, it.ya - 2, K0 - 1 + q - a.slo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, c0, it.ya - 2, K0 - 1 + q - a.slo, 0, bar);
+  };
+  auto issue_b = [&](int r) {
+    const uint32_t bar = bar_b + (r % SB) * 8;
+    mbar_expect_tx(bar, bbytes);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, 0, c0 >> 2, it.ya - 1, K0 + r - a.slo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, c0, it.ya - 1, K0 + r - a.slo, 0, bar);
+  };
+  const int nq = nsteps + 2; // x planes K0-1 .. K1+1
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < SX && q < nq; ++q) issue_x(q);
+    if (a.has_b)
+      for (int r = 0; r < SB && r < nsteps; ++r) issue_b(r);
+  }
+
+  // column / row parts of the node classification (edge tiles)
+  int  colmiss[4] = {0, 0, 0, 0};
+  bool colok[4]   = {true, true, true, true};
+  const bool rowok   = y >= 0 && y < a.ny;
+  const int  rowmiss = (y == 0 ? 1 : 0) + (y == a.ny - 1 ? 1 : 0);
+  if (!INTERIOR) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      colok[m]   = c + m >= 0 && c + m < a.nx;
+      colmiss[m] = (c + m == 0 ? 1 : 0) + (c + m == a.nx - 1 ? 1 : 0);
+    }
+  }
+  auto classes = [&](int kk, int (&ci)[4]) {
+    if (INTERIOR) return;
+    const bool kok   = kk >= 0 && kk < a.nz;
+    const int  kmiss = (kk == 0 ? 1 : 0) + (kk == a.nz - 1 ? 1 : 0);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) ci[m] = (kok && rowok && colok[m]) ? 6 - colmiss[m] - rowmiss - kmiss : 7;
+  };
+
+  double A[4] = {0, 0, 0, 0}, B[4], C[4], D[4], wk[2] = {0, 0}; // rolling window: planes kk-2, kk-1, kk and the incoming kk+1
+  int    cis[4] = {7, 7, 7, 7};
+  const uint32_t own = (uint32_t)((w + 1) * ROW_BYTES); // this warp's row inside an x box
+  auto publish = [&](int plane, const double (&v)[4]) {
+    const uint32_t p = sm + (uint32_t)L::off_new + (plane & 1) * L::NEWBUF + w * ROW_BYTES;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) sts64(p + new_off(lane, m), v[m]);
+  };
+  mbar_wait(bar_x + 0 * 8, 0);
+  lds256(sm + (uint32_t)L::off_x + 0 * L::XSTAGE + own, lane, B, swz);
+  mbar_wait(bar_x + (1 % SX) * 8, 0);
+  lds256(sm + (uint32_t)L::off_x + (1 % SX) * L::XSTAGE + own, lane, C, swz);
+  publish(K0 - 1, B); // phase B of plane K0-1 is never stored: any finite values will do
+  __syncthreads();
+  if (threadIdx.x == 0 && SX < nq) issue_x(SX); // slot of q = 0 is free again
+
+  // one plane step for a row whose first-colour columns of plane kk are M = P, P+2; xp1 receives plane kk+1
+  auto step = [&](auto ptag, int s, const double (&xm2)[4], double (&xm1)[4], double (&x0)[4], double (&xp1)[4]) {
+    constexpr int P = decltype(ptag)::value;
+    const int kk = K0 + s;
+    const int q0 = s + 1, q1 = s + 2; // x sequence numbers of planes kk, kk+1
+    const uint32_t xs0 = sm + (uint32_t)L::off_x + (q0 % SX) * L::XSTAGE, xs1 = sm + (uint32_t)L::off_x + (q1 % SX) * L::XSTAGE;
+    double bb[4] = {0, 0, 0, 0};
+    mbar_wait(bar_x + (q1 % SX) * 8, (uint32_t)(q1 / SX) & 1u);
+    lds256(xs1 + own, lane, xp1, swz);
+    if (a.has_b) {
+      mbar_wait(bar_b + (s % SB) * 8, (uint32_t)(s / SB) & 1u);
+      lds256(sm + (uint32_t)L::off_b + (s % SB) * L::BSTAGE + w * ROW_BYTES, lane, bb, swz);
+    }
+    int ci[4] = {0, 0, 0, 0};
+    classes(kk, ci);
+    // w = b + sqrtdiag z (src/pc_mcgibbs.c:124-126: two roundings)
+    double wv[4];
+    if (NOISE == NOISE_NONE) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) wv[m] = bb[m];
+    } else {
+      double z[4];
+      if (NOISE == NOISE_TAPE) {
+        const bool    ok = INTERIOR || (rowok && kk >= a.slo && kk < a.shi);
+        const double *p  = a.tape + ((long long)(kk - a.slo) * a.ny + y) * a.nx + c;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) z[m] = (ok && (INTERIOR || colok[m])) ? p[m] : 0.0;
+      } else {
+        const long long quad = (((long long)kk * a.ny + y) * a.pitch + c) >> 2;
+        uint32_t        w0, w1, w2, w3;
+        philox4x32_10_keys((uint32_t)quad, (uint32_t)((unsigned long long)quad >> 32), a.call_lo, a.call_hi, a.pk, w0, w1, w2, w3);
+        fastnormal::box_muller(ft, w0, w1, z[0], z[1]);
+        fastnormal::box_muller(ft, w2, w3, z[2], z[3]);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double sd = INTERIOR ? a.sd : coef[ci[m]].sd;
+        wv[m]           = __dadd_rn(__dmul_rn(z[m], sd), bb[m]);
+      }
+    }
+    const uint32_t old_s = xs0 + own - ROW_BYTES, old_n = xs0 + own + ROW_BYTES;
+    const uint32_t nb    = sm + (uint32_t)L::off_new + ((kk - 1) & 1) * L::NEWBUF;
+    const uint32_t new_s = nb + (inner_row ? w - 1 : w) * ROW_BYTES, new_n = nb + (inner_row ? w + 1 : w) * ROW_BYTES;
+    phases<P, INTERIOR>(a, coef, lane, swz, inner_row, xm2, xm1, x0, xp1, old_s, old_n, new_s, new_n, wv, wk, ci, cis);
+    wk[0] = wv[1 - P];
+    wk[1] = wv[3 - P];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) cis[m] = ci[m];
+    const int ko = kk - 1; // plane kk-1 of this row is final
+    if (out_thread && ko >= it.ka && ko < it.kb) st256(a.xout + (long long)(ko - a.slo) * a.pplane + (long long)y * a.pitch + c, xm1);
+    publish(kk, x0); // the half-updated plane kk, for the neighbouring rows
+    __syncthreads();
+    if (threadIdx.x == 0) { // the boxes of plane kk (x) and of this step (b) are free
+      if (q0 + SX < nq) issue_x(q0 + SX);
+      if (a.has_b && s + SB < nsteps) issue_b(s + SB);
+    }
+  };
+  // the row parity alternates from plane to plane: steps are unrolled in pairs so that the colour pattern is a compile-time
+  // constant; every warp of the CTA runs the same number of steps (one barrier each)
+  auto pairs = [&](auto qtag) {
+    constexpr int Q = decltype(qtag)::value;
+    int           s = 0;
+    for (; s + 1 < nsteps; s += 2) {
+      step(std::integral_constant<int, Q>{}, s, A, B, C, D);
+      step(std::integral_constant<int, 1 - Q>{}, s + 1, B, C, D, A);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { // window (C, D, A) -> (A, B, C)
+        const double t = A[m];
+        A[m] = C[m];
+        B[m] = D[m];
+        C[m] = t;
+      }
+    }
+    if (s < nsteps) step(std::integral_constant<int, Q>{}, s, A, B, C, D);
+  };
+  if (((y + K0 + a.flip) & 1) == 0) pairs(std::integral_constant<int, 0>{});
+  else pairs(std::integral_constant<int, 1>{});
+}
+
+template <int NOISE, int NW, int SX, int SB, int MINB> __global__ void __launch_bounds__(NW * 32, MINB) sweep3d_kernel(const __grid_constant__ Args a)
+{
+  using L = Smem<NW, SX, SB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char *base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  fastnormal::SharedTables *fts  = reinterpret_cast<fastnormal::SharedTables *>(base + L::off_tab);
+  Coef                     *coef = reinterpret_cast<Coef *>(base + L::off_coef);
+  const fastnormal::Tables  ft   = fastnormal::load_tables(*fts);
+  if (threadIdx.x < 8) coef[threadIdx.x] = a.coef[threadIdx.x];
+  const uint32_t sm = smem_u32(base);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SX + SB; ++s) mbar_init(sm + (uint32_t)L::off_bar + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const Item it = a.items[blockIdx.x];
+  const int  c0 = it.strip * STRIP_OUT - 4;
+  // every node the CTA updates exists and has all six neighbours, and every row / plane it reads exists and is owned
+  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2 && it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.slo && it.kb + 1 < a.shi;
+  if (interior) run_cta<NOISE, true, NW, SX, SB>(a, ft, coef, sm, it);
+  else run_cta<NOISE, false, NW, SX, SB>(a, ft, coef, sm, it);
+}
+
+} // namespace sweep3d
