@@ -193,6 +193,7 @@ struct LevelOp {
 // grid transfer between level l (fine) and l-1 (coarse): SURVEY Appendix A.3
 struct Transfer {
   virtual ~Transfer() {}
+  virtual bool tail_ok() const { return false; } // matrix-free Q1 transfer between two whole grids on one device
   virtual int restrict_to(const double *r_fine, double *b_coarse) = 0; // b_c = P^T r
   virtual int prolong_add(const double *x_coarse, double *x_fine) = 0; // x_f += P x_c
 };
@@ -235,6 +236,25 @@ struct CholSampler {
   int forward(const double *b, double *v);                      // v = L^-1 b
   int backward_noise(const double *v, double *y, const NoiseArgs &na); // y = L^-T (v + z)
 };
+
+// ---- the coarse tail of a V-cycle in ONE launch (stencil_op.cu grid_tail_kernel) ----------------------------------
+// Levels 0 .. nlev-1 of a geometric hierarchy on one device: level 0 is the dense Cholesky sampler, levels >= 1 are
+// stencil-array operators smoothed by colour sweeps.  One thread-block cluster runs pre-sampling, residual, restriction,
+// the coarse sample, prolongation and post-sampling of all of them with cluster barriers in between, instead of ~11
+// launches per level (profiles/: the small levels were pure launch latency).
+struct TailNoise {
+  uint64_t      call;
+  const double *tape;
+};
+struct TailLevelSpec {
+  LevelOp           *op     = nullptr;
+  const SweepCoeffs *coeffs = nullptr;
+  int                ndirs  = 0;
+  int                dirs[8];
+  double            *b = nullptr, *x = nullptr, *r = nullptr;
+};
+bool grid_tail_level_ok(LevelOp *op);
+int  grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns);
 
 int launch_normal_fill(pmg_ctx ctx, const NoiseArgs &na, int64_t n, double *z_dev);
 int launch_axpy(pmg_ctx ctx, int64_t n, double a, const double *x, double *y); // y += a x

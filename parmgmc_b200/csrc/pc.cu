@@ -307,6 +307,7 @@ struct pmg_pc_s {
   std::vector<MgLevel> lv;
   DevBuf<double>       w, work;
   bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
+  int                  tail_top     = -1;   // levels 0 .. tail_top of the direct cycle run in one launch (mg_tail); -1: none
   DevBuf<double>       scratch;             // out-of-place partner of the iterate for the fused sweeps (pitched)
   DevBuf<double>       pit_y, pit_b;        // pitched copies of the caller's y and b (LevelOp::fused_size)
   // staging
@@ -453,10 +454,13 @@ static int sweep_dirs(const LevelSampler &s, std::vector<int> &dirs)
 // src/pc_gamgmc.c:253-256 disappear.  Levels whose operator has a fused streaming sweep run pre-smoothing + residual +
 // restriction in one pass over memory and prolongation + post-smoothing in another; on such a level b and x are the
 // PITCHED vectors of LevelOp::fused_size() elements (only the finest level can be one: the caller converts).
+static int mg_tail(pmg_pc pc, int lt);
+
 static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool zero_guess)
 {
   pmg_ctx  ctx = pc->ctx;
   MgLevel &v   = pc->lv[l];
+  if (l == pc->tail_top && zero_guess && b == v.b.p && x == v.x.p) return mg_tail(pc, l); // levels 0..l in one launch
   const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p;
   if (!fused) {
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
@@ -489,6 +493,41 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   }
   if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->fused_size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
+}
+
+// Levels 0 .. lt of the V-cycle in one cluster launch (stencil_op.cu grid_tail_kernel).  The noise blocks are handed out
+// here in the order the level-by-level path draws them, so counters, tapes and results do not depend on the choice.
+static int mg_tail(pmg_pc pc, int lt)
+{
+  pmg_ctx                    ctx = pc->ctx;
+  std::vector<TailLevelSpec> lv((size_t)lt + 1);
+  std::vector<TailNoise>     ns;
+  NoiseArgs                  na;
+  for (int l = 0; l <= lt; ++l) {
+    MgLevel &v = pc->lv[l];
+    lv[l].op = v.op;
+    lv[l].b = v.b.p; lv[l].x = v.x.p; lv[l].r = v.r.p;
+    if (l == 0) continue;
+    PMG_TRY(v.smp.gibbs.ensure());
+    lv[l].coeffs = &v.smp.gibbs.coeffs;
+    std::vector<int> dirs;
+    sweep_dirs(v.smp, dirs);
+    lv[l].ndirs = (int)dirs.size();
+    for (size_t q = 0; q < dirs.size(); ++q) lv[l].dirs[q] = dirs[q];
+  }
+  for (int l = lt; l >= 1; --l)
+    for (int q = 0; q < lv[l].ndirs; ++q) {
+      PMG_TRY(pc->noise.next(ctx, pc->lv[l].op->n(), 0, na));
+      ns.push_back(TailNoise{na.call, na.tape});
+    }
+  PMG_TRY(pc->noise.next(ctx, pc->lv[0].smp.chol.n, 0, na));
+  ns.push_back(TailNoise{na.call, na.tape});
+  for (int l = 1; l <= lt; ++l)
+    for (int q = 0; q < lv[l].ndirs; ++q) {
+      PMG_TRY(pc->noise.next(ctx, pc->lv[l].op->n(), 0, na));
+      ns.push_back(TailNoise{na.call, na.tape});
+    }
+  return grid_tail_cycle(ctx, lt + 1, lv.data(), pc->lv[0].smp.chol, pc->noise.mode, ctx->seed, ns.data(), (int)ns.size());
 }
 
 static int gamgmc_setup(pmg_pc pc)
@@ -611,6 +650,23 @@ static int gamgmc_setup(pmg_pc pc)
   const std::string cyc = pc->get("pc_b200_cycle", "direct");
   if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
   pc->direct_cycle = cyc == "direct";
+  // the coarse tail: the largest lt < L-1 such that levels 0..lt are whole-grid stencil-array levels on this device, level 0
+  // is the dense gemv sampler with one iteration, and level lt has at most -pc_b200_tail_max_n nodes
+  pc->tail_top = -1;
+  {
+    const char   *tm_env   = std::getenv("PMG_TAIL_MAX");
+    const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "20000").c_str());
+    MgLevel      &c0       = pc->lv[0];
+    if (pc->direct_cycle && L >= 3 && tail_max > 0 && c0.smp.kind == KIND_CHOL && c0.smp.its == 1 && c0.smp.chol.use_gemv && grid_tail_level_ok(c0.op)) {
+      int lt = 0;
+      for (int l = 1; l < L - 1; ++l) {
+        MgLevel &v = pc->lv[l];
+        if (v.smp.kind == KIND_CHOL || !grid_tail_level_ok(v.op) || !v.P || !v.P->tail_ok() || v.op->n() > tail_max || v.smp.its * (v.smp.gibbs.type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) > 8) break;
+        lt = l;
+      }
+      if (lt >= 1 && lt + 1 <= 10) pc->tail_top = lt;
+    }
+  }
   const size_t nf = (size_t)fine->n();
   PMG_TRY(pc->w.alloc(nf));
   PMG_TRY(pc->work.alloc(nf));

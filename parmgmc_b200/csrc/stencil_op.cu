@@ -256,7 +256,7 @@ template <int DIM> __device__ __forceinline__ bool box_interior(const Geom &g, c
 }
 
 // sum_{s != centre, ascending} (sign) c_s x[q_s] accumulated into acc with fma; INCLUDE_CENTRE adds the diagonal in place
-template <int DIM, bool NEG, bool INCLUDE_CENTRE>
+template <int DIM, bool NEG, bool INCLUDE_CENTRE, bool CG = false> // CG: x is read with ld.global.cg (written by other SMs in the same launch)
 __device__ __forceinline__ double box_row(const Geom &g, const BoxConst &bc, const double *__restrict__ coef, int64_t stride, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, int64_t idx, int64_t i, int64_t j, int64_t k, double acc)
 {
   constexpr int NST = DIM == 2 ? 9 : 27;
@@ -269,12 +269,12 @@ __device__ __forceinline__ double box_row(const Geom &g, const BoxConst &bc, con
     double        c, v;
     if (interior) {
       c = bc.c[s];
-      v = ldg(x, glo, ghi, q, g);
+      v = CG ? __ldcg(x + q) : ldg(x, glo, ghi, q, g);
     } else {
       const bool ex = i + di >= 0 && i + di < g.n0 && j + dj >= 0 && j + dj < g.n1 && (DIM == 2 || (k + dk >= 0 && k + dk < g.n2));
       if (!ex) continue; // structurally absent entry
       c = coef[(int64_t)s * stride + idx];
-      v = ldg(x, glo, ghi, q, g);
+      v = CG ? __ldcg(x + q) : ldg(x, glo, ghi, q, g);
     }
     acc = fma(NEG ? -c : c, v, acc);
   }
@@ -394,6 +394,168 @@ template <int DIM> __global__ void __launch_bounds__(256) prolong_kernel(Geom gf
     }
   }
   xf[idx] = s;
+}
+
+// ---- the coarse tail of the V-cycle in one launch (common.hpp: grid_tail_cycle) ---------------------------------------
+// Same node arithmetic as box_sweep_kernel / box_apply_kernel / restrict_kernel / prolong_kernel / tri_gemv_kernel, so the
+// result is bit-identical to the launch-per-colour path.  Vectors that change during the launch are read with
+// ld.global.cg (L2): the CTAs of the cluster sit on different SMs, whose L1s are not coherent.
+struct TailLevelDev {
+  Geom          g;
+  BoxConst      bc; // with idiag / sqrtdiag of the level's omega
+  const double *coef, *idiag, *sqrtdiag;
+  double        omo;
+  int           ndirs, dirs[8];
+  double       *b, *x, *r;
+};
+constexpr int TAIL_MAX_LEVELS = 10, TAIL_MAX_NOISE = 2 * TAIL_MAX_LEVELS * 8 + 1;
+struct TailArgs {
+  int           nlev;
+  TailLevelDev  lv[TAIL_MAX_LEVELS]; // lv[0]: geometry and vectors of the coarsest grid only
+  int           nc;                  // coarsest: v = W b + z, x = W^T v (chol.cu, gemv form)
+  const double *W, *WT;
+  double       *tmp0;
+  int           mode;
+  uint64_t      seed;
+  TailNoise     ns[TAIL_MAX_NOISE];
+  int           cluster; // CTAs per cluster (== gridDim.x), 1: plain block barrier
+};
+
+__device__ __forceinline__ void tail_sync(int cluster)
+{
+  if (cluster > 1) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else __syncthreads();
+}
+
+// One directional sweep.  The level's normals are generated first, four per Philox call (a node-at-a-time sweep would
+// use one of the four values each call returns), into the level's residual vector, which is free during smoothing.
+template <int DIM> __device__ __forceinline__ void tail_sweep(const TailLevelDev &L, int dir, const NoiseArgs &na, int gtid, int gsize, int cluster)
+{
+  const Geom &g  = L.g;
+  const int   nc = DIM == 3 ? 8 : 4;
+  double     *zb = L.r;
+  if (na.mode == PMG_NOISE_PHILOX) {
+    const int nq = ((int)g.nl + 3) >> 2;
+    for (int q = gtid; q < nq; q += gsize) {
+      double z[4];
+      philox_normal_quad(na.seed, na.call, (uint64_t)q, z);
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (4 * q + m < (int)g.nl) zb[4 * q + m] = z[m];
+    }
+    tail_sync(cluster);
+  }
+  for (int s = 0; s < nc; ++s) {
+    const int c  = dir == PMG_SOR_FORWARD_SWEEP ? s : nc - 1 - s;
+    const int ci = c & 1, cj = (c >> 1) & 1, ck = (c >> 2) & 1;
+    const int ni = ((int)g.n0 - ci + 1) / 2, nj = ((int)g.n1 - cj + 1) / 2, nk = DIM == 3 ? ((int)g.n2 - ck + 1) / 2 : 1;
+    const int total = ni * nj * nk;
+    for (int t = gtid; t < total; t += gsize) {
+      const int     tx = t % ni, u = t / ni, ty = u % nj, tz = u / nj;
+      const int64_t i = 2 * tx + ci, j = 2 * ty + cj, k = DIM == 3 ? 2 * tz + ck : 0;
+      const int64_t idx = i + g.n0 * (j + g.n1 * k);
+      const bool    interior = box_interior<DIM>(g, L.bc, i, j, k);
+      const double  sq = interior ? L.bc.sqrtdiag : L.sqrtdiag[idx], id = interior ? L.bc.idiag : L.idiag[idx];
+      const double  bv = __ldcg(L.b + idx);
+      double        sum = bv; // noisy_rhs: w = (z * sqrtdiag) + b
+      if (na.mode == PMG_NOISE_PHILOX) sum = __dadd_rn(__dmul_rn(__ldcg(zb + idx), sq), bv);
+      else if (na.mode == PMG_NOISE_INJECTED) sum = __dadd_rn(__dmul_rn(na.tape[idx], sq), bv);
+      sum               = box_row<DIM, true, false, true>(g, L.bc, L.coef, g.nl, L.x, nullptr, nullptr, idx, i, j, k, sum);
+      const double t0   = __dmul_rn(L.omo, __ldcg(L.x + idx));
+      L.x[idx]          = fma(id, sum, t0);
+    }
+    tail_sync(cluster);
+  }
+}
+
+template <int DIM> __global__ void __launch_bounds__(1024, 1) grid_tail_kernel(const __grid_constant__ TailArgs a)
+{
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  const int cl   = a.cluster;
+  int       kn   = 0; // cursor into the noise blocks, in the reference's consumption order (SURVEY 8(c) tape contract)
+  { // PCMG zeroes the iterate of the level it enters
+    const TailLevelDev &T = a.lv[a.nlev - 1];
+    for (int t = gtid; t < (int)T.g.nl; t += gsize) T.x[t] = 0.0;
+    tail_sync(cl);
+  }
+  for (int l = a.nlev - 1; l >= 1; --l) {
+    const TailLevelDev &F = a.lv[l], &C = a.lv[l - 1];
+    for (int d = 0; d < F.ndirs; ++d, ++kn) tail_sweep<DIM>(F, F.dirs[d], NoiseArgs{a.mode, a.ns[kn].tape, a.seed, a.ns[kn].call, 0}, gtid, gsize, cl);
+    for (int t = gtid; t < (int)F.g.nl; t += gsize) { // r = b - A x
+      const int     i = t % (int)F.g.n0, u = t / (int)F.g.n0, j = DIM == 3 ? u % (int)F.g.n1 : u, k = DIM == 3 ? u / (int)F.g.n1 : 0;
+      const double  ax = box_row<DIM, false, true, true>(F.g, F.bc, F.coef, F.g.nl, F.x, nullptr, nullptr, t, i, j, k, 0.0);
+      F.r[t]           = __dsub_rn(__ldcg(F.b + t), ax);
+    }
+    tail_sync(cl);
+    for (int t = gtid; t < (int)C.g.nl; t += gsize) { // b_c = P^T r, x_c = 0
+      const int I = t % (int)C.g.n0, u = t / (int)C.g.n0, J = DIM == 3 ? u % (int)C.g.n1 : u, K = DIM == 3 ? u / (int)C.g.n1 : 0;
+      double    acc = 0.0;
+#pragma unroll
+      for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+          for (int di = -1; di <= 1; ++di) {
+            const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+            if (i < 0 || i >= F.g.n0 || j < 0 || j >= F.g.n1 || k < 0 || k >= F.g.n2) continue;
+            const double w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+            acc            = fma(w, __ldcg(F.r + (i + F.g.n0 * (j + F.g.n1 * (int64_t)k))), acc);
+          }
+      C.b[t] = acc;
+      C.x[t] = 0.0;
+    }
+    tail_sync(cl);
+  }
+  { // coarsest level: y = W^T (W b + z), one warp per entry (tri_gemv_kernel's order)
+    const TailLevelDev &C = a.lv[0];
+    const NoiseArgs     na{a.mode, a.ns[kn].tape, a.seed, a.ns[kn].call, 0};
+    ++kn;
+    const int lane = threadIdx.x & 31, gw = gtid >> 5, nw = gsize >> 5, n = a.nc;
+    for (int i = gw; i < n; i += nw) {
+      const double *row = a.W + (size_t)i * n;
+      double        acc = 0.0;
+      for (int k = lane; k < i + 1; k += 32) acc = fma(row[k], __ldcg(C.b + k), acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) a.tmp0[i] = na.mode != PMG_NOISE_NONE ? __dadd_rn(acc, noise_value(na, i)) : acc;
+    }
+    tail_sync(cl);
+    for (int i = gw; i < n; i += nw) {
+      const double *row = a.WT + (size_t)i * n;
+      double        acc = 0.0;
+      for (int k = i + lane; k < n; k += 32) acc = fma(row[k], __ldcg(a.tmp0 + k), acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) C.x[i] = acc;
+    }
+    tail_sync(cl);
+  }
+  for (int l = 1; l < a.nlev; ++l) {
+    const TailLevelDev &F = a.lv[l], &C = a.lv[l - 1];
+    for (int t = gtid; t < (int)F.g.nl; t += gsize) { // x_f += P x_c
+      const int i = t % (int)F.g.n0, u = t / (int)F.g.n0, j = DIM == 3 ? u % (int)F.g.n1 : u, k = DIM == 3 ? u / (int)F.g.n1 : 0;
+      const int ci = (i & 1) ? 2 : 1, cj = (j & 1) ? 2 : 1, ck = (DIM == 3 && (k & 1)) ? 2 : 1;
+      const int I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
+      double    sacc = __ldcg(F.x + t);
+      for (int c = 0; c < ck; ++c) {
+        const int K = K0 + c;
+        if (K >= C.g.n2) continue;
+        for (int bq = 0; bq < cj; ++bq) {
+          const int J = J0 + bq;
+          if (J >= C.g.n1) continue;
+          for (int q = 0; q < ci; ++q) {
+            const int I = I0 + q;
+            if (I >= C.g.n0) continue;
+            const double w = (ci == 2 ? 0.5 : 1.0) * (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0);
+            sacc           = fma(w, __ldcg(C.x + (I + C.g.n0 * (J + C.g.n1 * (int64_t)K))), sacc);
+          }
+        }
+      }
+      F.x[t] = sacc;
+    }
+    tail_sync(cl);
+    for (int d = 0; d < F.ndirs; ++d, ++kn) tail_sweep<DIM>(F, F.dirs[d], NoiseArgs{a.mode, a.ns[kn].tape, a.seed, a.ns[kn].call, 0}, gtid, gsize, cl);
+  }
 }
 
 // ---- Galerkin product on the grid: A_c = P^T (A P), same accumulation order as the row-by-row sparse product ----
@@ -1093,6 +1255,7 @@ struct BoxOp final : GridOp {
 struct GridTransfer final : Transfer {
   pmg_ctx ctx;
   GridOp *fine, *coarse;
+  bool    tail_ok() const override { return !fine->parallel && !coarse->parallel; }
   int restrict_to(const double *r, double *bcoarse) override
   {
     PMG_TRY(fine->halo(r));
@@ -1157,6 +1320,87 @@ struct ReplicatingTransfer final : Transfer {
 };
 
 } // namespace
+
+bool grid_tail_level_ok(LevelOp *op)
+{
+  auto *bx = dynamic_cast<BoxOp *>(op);
+  return bx && !bx->parallel && bx->g.slo == 0 && bx->g.shi == bx->g.nslow() && bx->g.nl < (1 << 30);
+}
+
+int grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns)
+{
+  if (nlev < 2 || nlev > TAIL_MAX_LEVELS || nns > TAIL_MAX_NOISE) PMG_FAIL(PMG_ERR_SUP, "coarse tail: %d levels / %d noise blocks exceed the kernel's tables", nlev, nns);
+  static TailArgs a; // ~4 KB: filled per launch, passed by value
+  a.nlev = nlev;
+  int     dim = 2;
+  int64_t updates = 0;
+  for (int l = 0; l < nlev; ++l) {
+    auto *bx = dynamic_cast<BoxOp *>(lv[l].op);
+    if (!bx) PMG_FAIL(PMG_ERR_SUP, "coarse tail: level %d is not a stencil-array operator", l);
+    dim             = bx->g.dim;
+    TailLevelDev &d = a.lv[l];
+    d.g             = bx->g;
+    d.bc            = bx->bc;
+    d.coef          = bx->coef.p;
+    d.b = lv[l].b; d.x = lv[l].x; d.r = lv[l].r;
+    d.ndirs = 0;
+    if (l == 0) continue;
+    const SweepCoeffs &co = *lv[l].coeffs;
+    if (d.bc.on) { // BoxOp::sweep's interior coefficients
+      const double dd  = d.bc.c[bx->nst() / 2];
+      double       inv = 1.0 / dd;
+      d.bc.idiag       = inv * co.omega;
+      d.bc.sqrtdiag    = std::sqrt(std::fabs(dd)) * std::sqrt((2 - co.omega) / co.omega);
+    }
+    d.idiag = co.idiag.p; d.sqrtdiag = co.sqrtdiag.p;
+    d.omo   = 1.0 - co.omega;
+    d.ndirs = lv[l].ndirs;
+    for (int q = 0; q < d.ndirs; ++q) d.dirs[q] = lv[l].dirs[q];
+    updates += 2 * (int64_t)d.ndirs * bx->g.nl;
+  }
+  a.nc = (int)chol.n; a.W = chol.L.p; a.WT = chol.LT.p; a.tmp0 = chol.tmp.p;
+  a.mode = noise_mode; a.seed = seed;
+  for (int q = 0; q < nns; ++q) a.ns[q] = ns[q];
+  // one cluster of up to 8 CTAs x 1024 threads; small tails run in fewer CTAs (a barrier between fewer SMs is cheaper)
+  const int64_t big = a.lv[nlev - 1].g.nl;
+  static int cl_max = 0; // 16 CTAs per cluster where the device allows it (non-portable size), else the portable 8
+  if (!cl_max) {
+    cl_max = 8;
+    bool ok = cudaFuncSetAttribute(grid_tail_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess && cudaFuncSetAttribute(grid_tail_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(16); q.blockDim = dim3(1024);
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, grid_tail_kernel<2>, &q) == cudaSuccess && nclusters >= 1) cl_max = 16;
+    }
+    (void)cudaGetLastError();
+  }
+  int cl = big > 40000 ? cl_max : big > 9000 ? 8 : big > 2000 ? 4 : big > 500 ? 2 : 1;
+  static const int cl_env = std::getenv("PMG_TAIL_CLUSTER") ? std::atoi(std::getenv("PMG_TAIL_CLUSTER")) : 0;
+  if (cl_env >= 1 && cl_env <= cl_max) cl = cl_env;
+  a.cluster = cl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim  = dim3((unsigned)cl);
+  cfg.blockDim = dim3(1024);
+  cfg.stream   = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id               = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs    = at;
+  cfg.numAttrs = 1;
+  if (dim == 2) PMG_CUDA(cudaLaunchKernelEx(&cfg, grid_tail_kernel<2>, a));
+  else PMG_CUDA(cudaLaunchKernelEx(&cfg, grid_tail_kernel<3>, a));
+  PMG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  ctx->dof_updates += updates;
+  return 0;
+}
 
 int make_laplace_op(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, std::unique_ptr<LevelOp> &op)
 {

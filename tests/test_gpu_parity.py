@@ -547,3 +547,37 @@ def test_matrix_free_hierarchy_equals_assembled_hierarchy(pmg, ctx, orc, dim, di
     ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(n), 2)
     assert relerr(y, ref) < RTOL, relerr(y, ref)
     assert "shared" in pc.view() or min(dims[:dim]) < 9
+
+
+# ---- the coarse tail of the V-cycle in one cluster launch (stencil_op.cu grid_tail_kernel) ---------------------------
+@pytest.mark.parametrize("dim,dims,levels,extra", [
+    (2, (129, 129, 1), 5, {}),
+    (2, (257, 129, 1), 6, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    (2, (161, 97, 1), 4, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.3}),
+    (3, (33, 33, 33), 3, {}),
+    (3, (41, 25, 17), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+])
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+def test_coarse_tail_launch_is_bit_identical(pmg, ctx, dim, dims, levels, extra, noise):
+    """One cluster launch for levels 0..lt must give exactly the launch-per-colour result, with the same noise blocks."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for tail_max in (300000, 0):
+        lap = pmg.Mat.laplace(ctx, dim, *dims, kappa=1.0)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": tail_max}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(5).standard_normal(3 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(99)
+        y = y0.copy()
+        d0 = ctx.draw_counter
+        pc.apply_richardson(b, y, its=3)
+        out.append((y, pc.last_stats()["launches"], ctx.draw_counter - d0))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1] and out[0][2] == out[1][2]
