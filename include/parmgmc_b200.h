@@ -87,6 +87,11 @@ int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr_host, const
  * dim = 3 is the 7-point extension).  The grid is nx*ny*nz in natural order; this rank owns the
  * slab [slab_lo, slab_hi) of the slowest dimension (0, ny or nz for the whole grid). */
 int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, pmg_mat *mat);
+/* MatCreateLRC(A, B, S, NULL): the operator A + B diag(S) B^T with B dense n x k (column-major) and S of length k, as the
+ * reference's samplers receive it through MatLRCGetMats (src/mc_sor.c:565-595, src/pc_mcgibbs.c:236-244,
+ * src/pc_sorgibbs.c:204-223).  A is borrowed and must outlive the result; sweeps run on A and are followed by the
+ * rank-k correction y -= Bb (B^T y) of MCSORPostSOR_LRC (src/mc_sor.c:101-112). */
+int pmg_mat_create_lrc(pmg_mat A, int k, const double *B_host, const double *S_host, pmg_mat *mat);
 int pmg_mat_destroy(pmg_mat mat);
 int pmg_mat_get_size(pmg_mat mat, int64_t *n_local, int64_t *n_global, int64_t *row_start);
 /* ISColoring of MCSORGetISColoring (src/mc_sor.c:92-99): explicit colours (validated) or a policy */

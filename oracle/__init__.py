@@ -271,6 +271,51 @@ def gibbs_richardson(A: CSR, b, y, its, noise: Noise, coloring: Coloring | None 
     return y
 
 
+# ---- MATLRC operators A + B diag(S) B^T (parity of this part is UNPINNED: the PETSc stub of oracle/_ref has no MATLRC;
+#      tests/test_oracle.py validates it through exact invariance of N(0, (A + B S B^T)^-1)) ---------------------------------
+def lrc_build_correction(A: CSR, B, S, coloring: Coloring | None, omega: float, sweep: int):
+    """MCSORBuildLRCCorrection (src/mc_sor.c:480-544): Bb = M^-1 B (S^-1 + B^T M^-1 B)^-1, where M^-1 is one deterministic
+    sweep from zero (MCSORApplyAsDetSOR, :546-551) in direction `sweep`."""
+    B = np.asarray(B, np.float64)
+    n, k = B.shape
+    mc = MCSOR(A, coloring, omega, sweep)
+    Cm = np.empty((n, k))
+    for j in range(k):  # :499-510, column by column
+        Cm[:, j] = mc.apply(np.ascontiguousarray(B[:, j]), np.zeros(n))
+    T = B.T @ Cm + np.diag(1.0 / np.asarray(S, np.float64))  # :513-527
+    return Cm @ np.linalg.inv(T)  # :528-535
+
+
+def lrc_mcsor_apply(A: CSR, B, Bb, b, y, coloring, omega, sweep):
+    """MCSORApply with postsor = MCSORPostSOR_LRC (src/mc_sor.c:216-239, :101-112); Bb = {direction: matrix}."""
+    mc = MCSOR(A, coloring, omega, sweep)
+    for d in ((SOR_FORWARD, SOR_BACKWARD) if sweep == SOR_SYMMETRIC else (sweep,)):
+        mc.apply(b, y, d)
+        y -= Bb[d] @ (B.T @ y)
+    return y
+
+
+def lrc_gibbs_richardson(A: CSR, B, S, b, y, its, noise: Noise, coloring: Coloring | None = None, omega=1.0, sweep=SOR_FORWARD, omega_build=1.0):
+    """PCApplyRichardson_MulticolorGibbs (src/pc_mcgibbs.c:155-188) on a MATLRC operator: per directional sweep
+    w = b + sqrtdiag z + B (sqrt|S| eta) (PrepareRHS_LRC :130-140: n draws, then k), MCSORApply on the base matrix, then
+    y -= Bb_dir (B^T y).  Bb is built with a temporary MCSOR at its own default omega (src/mc_sor.c:583-593) = omega_build."""
+    B = np.asarray(B, np.float64)
+    S = np.asarray(S, np.float64)
+    n, k = B.shape
+    Bb = {d: lrc_build_correction(A, B, S, coloring, omega_build, d) for d in (SOR_FORWARD, SOR_BACKWARD)}
+    sd = sqrtdiag(A, omega)
+    sqrtS = np.sqrt(np.abs(S))
+    mc = MCSOR(A, coloring, omega, SOR_FORWARD)
+    b = np.zeros(n) if b is None else np.asarray(b, np.float64)
+    for _ in range(its):
+        for d in ((SOR_FORWARD, SOR_BACKWARD) if sweep == SOR_SYMMETRIC else (sweep,)):
+            w = noise_fill(noise, n) * sd + b
+            w = B @ (noise_fill(noise, k) * sqrtS) + w
+            mc.apply(w, y, d)
+            y -= Bb[d] @ (B.T @ y)
+    return y
+
+
 def normal_philox(seed, call, row0, n):
     out = np.empty(n, np.float64)
     lib().orc_normal_philox(seed, call, row0, n, out)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pmg_ctx_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pmg_mat_create_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
+    "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_destroy": (C.c_int, [_vp]),
     "pmg_mat_get_size": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pmg_mat_set_coloring": (C.c_int, [_vp, C.c_int, _i32p]),
@@ -246,6 +247,19 @@ class Mat:
         h = _vp()
         _check(lib().pmg_mat_create_laplace(ctx._h, dim, nx, ny, nz, kappa, lo, hi, C.byref(h)))
         return Mat(ctx, h)
+
+    @staticmethod
+    def lrc(A: "Mat", B, S) -> "Mat":
+        """MatCreateLRC(A, B, S, NULL): A + B diag(S) B^T with B dense n x k (src/mc_sor.c:565-595).  A is borrowed."""
+        B = np.asarray(B, np.float64)
+        S = np.ascontiguousarray(S, np.float64)
+        if B.ndim != 2 or B.shape[0] != A.n or B.shape[1] != S.size:
+            raise ValueError("B must be n x k and S of length k")
+        h = _vp()
+        _check(lib().pmg_mat_create_lrc(A._h, int(S.size), np.ascontiguousarray(B.T).ravel(), S, C.byref(h)))  # column-major
+        m = Mat(A.ctx, h)
+        m._base = A  # keep the borrowed base alive
+        return m
 
     @property
     def size(self):

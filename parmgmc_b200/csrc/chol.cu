@@ -131,7 +131,7 @@ __global__ void add_noise_kernel(int n, const double *__restrict__ v, double *__
 }
 } // namespace
 
-int CholSampler::setup(pmg_ctx c, const HostCsr &a)
+int CholSampler::setup(pmg_ctx c, const HostCsr &a, const LrcData *lrc)
 {
   ctx = c;
   n   = a.n;
@@ -139,6 +139,17 @@ int CholSampler::setup(pmg_ctx c, const HostCsr &a)
   std::vector<double> l((size_t)(n * n), 0.0), lt((size_t)(n * n), 0.0);
   for (int64_t r = 0; r < n; ++r)
     for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) l[(size_t)(r + (int64_t)a.col[k] * n)] = a.val[k];
+  if (lrc) { // P = A + B diag(S) B^T, assembled densely (src/pc_chols.c:119-157 forms it as a sparse product)
+    for (int j = 0; j < lrc->k; ++j) {
+      const double *bj = lrc->Bh.data() + (size_t)j * n;
+      const double  sj = lrc->Sh[(size_t)j];
+      for (int64_t cc = 0; cc < n; ++cc) {
+        const double f = sj * bj[cc];
+        if (f == 0.0) continue;
+        for (int64_t r = 0; r < n; ++r) l[(size_t)(r + cc * n)] += bj[r] * f;
+      }
+    }
+  }
   const int info = host_potrf_lower(n, l);
   if (info) PMG_FAIL(PMG_ERR_NOT_SPD, "Dense Cholesky failed: leading minor of order %d is not positive definite", info); // src/pc_chols.c:192
   for (int64_t i = 0; i < n; ++i)

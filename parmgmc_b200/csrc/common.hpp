@@ -152,6 +152,24 @@ struct SweepCoeffs {
   DevBuf<double> idiag, sqrtdiag; // layout is private to the operator that made them
 };
 
+// Low-rank part of an operator A + B diag(S) B^T (MATLRC) and its sweep corrections (lrc.cu).
+struct LevelOp;
+struct LrcData {
+  pmg_ctx             ctx = nullptr;
+  int64_t             n   = 0;
+  int                 k   = 0, nchunks = 0;
+  std::vector<double> Bh, Sh;                             // host copies (set-up)
+  DevBuf<double>      B, S, sqrtS, Bb_f, Bb_b, partial, rhs; // n x k column-major; k; k; n x k (forward / backward); chunk sums; n
+  bool                built       = false;
+  double              omega_built = 0;
+  int init(pmg_ctx ctx, int64_t n, int k, const double *B_host, const double *S_host);
+  int build(LevelOp *base, double omega_build);                      // MCSORBuildLRCCorrection, both directions
+  int prepare_rhs(const double *b, const NoiseArgs &na_eta, double *out); // out = b + B (sqrt|S| eta)
+  int post(int dir, double *y);                                      // y -= Bb_dir (B^T y)
+  int add_bsbt(const double *x, double sign, double *out);           // out += sign B (S o B^T x)
+  int bty(const double *M, const double *y);
+};
+
 // An operator on one level on one device.
 struct LevelOp {
   pmg_ctx ctx = nullptr;
@@ -173,6 +191,8 @@ struct LevelOp {
   virtual void describe(std::string &out) = 0;
   virtual bool structured(int &dim, int64_t dims[3]) const { (void)dim; (void)dims; return false; }
   virtual bool matrix_free() const { return false; } // true: hierarchy is built on the device (stencil_op.cu)
+  virtual LrcData *lrc_data() { return nullptr; }    // non-null: the operator is A + B diag(S) B^T and sweeps run on A
+  virtual LevelOp *lrc_base() { return nullptr; }    // ... and this is A
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
@@ -201,6 +221,7 @@ struct Transfer {
 struct pmg_mat_s {
   pmg_ctx                  ctx = nullptr;
   std::unique_ptr<LevelOp> op;
+  pmg_mat                  base = nullptr; // low-rank corrected operators borrow their base matrix (MatCreateLRC references A)
   explicit pmg_mat_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
   ~pmg_mat_s()
   {
@@ -208,6 +229,8 @@ struct pmg_mat_s {
     pmg_ctx_release(ctx);
   }
 };
+
+int make_lrc_op(pmg_ctx ctx, LevelOp *base, int k, const double *B_host, const double *S_host, std::unique_ptr<LevelOp> &op); // lrc.cu
 
 // host-side sparse helpers (host_sparse.cpp)
 void host_transpose(const HostCsr &a, HostCsr &t);
@@ -230,7 +253,7 @@ struct CholSampler {
   int64_t        n   = 0;
   DevBuf<double> L, LT, vcache, tmp;
   bool           use_gemv = true; // false: sequential substitution in dtrsv's order (-pc_cholsampler_b200_solve trsv)
-  int setup(pmg_ctx ctx, const HostCsr &a);
+  int setup(pmg_ctx ctx, const HostCsr &a, const LrcData *lrc = nullptr); // lrc: factor A + B diag(S) B^T (src/pc_chols.c:119-157)
   // y = L^-T (L^-1 b + z)
   int sample(const double *b, double *y, const NoiseArgs &na);
   int forward(const double *b, double *v);                      // v = L^-1 b

@@ -161,6 +161,18 @@ int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t
   return PMG_OK;
 }
 
+int pmg_mat_create_lrc(pmg_mat A, int k, const double *B_host, const double *S_host, pmg_mat *out)
+{
+  pmg_stale("pmg_mat_create_lrc");
+  if (!A || !B_host || !S_host || !out || k < 1) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_lrc: bad arguments");
+  PMG_CUDA(cudaSetDevice(A->ctx->device));
+  auto m  = std::make_unique<pmg_mat_s>(A->ctx);
+  m->base = A;
+  PMG_TRY(make_lrc_op(A->ctx, A->op.get(), k, B_host, S_host, m->op));
+  *out = m.release();
+  return PMG_OK;
+}
+
 int pmg_mat_destroy(pmg_mat m)
 {
   pmg_stale("pmg_mat_destroy");
@@ -235,9 +247,33 @@ struct GibbsCore {
     if (coeffs.omega != omega) PMG_TRY(op->make_coeffs(omega, coeffs)); // omega_changed, src/pc_mcgibbs.c:165
     return 0;
   }
+  // one directional sweep of an operator with a low-rank term: PrepareRHS_LRC (src/pc_mcgibbs.c:130-140: the k extra
+  // draws come after the n of the sweep), MCSORApply on the base matrix, MCSORPostSOR_LRC (src/mc_sor.c:101-112)
+  int sweep_lrc(LrcData *lrc, NoiseStream &ns, int dir, const double *b, double *y)
+  {
+    NoiseArgs na, na_eta;
+    PMG_TRY(lrc->build(op, lrc_omega_build));
+    PMG_TRY(ns.next(op->ctx, op->n(), op->row0(), na));
+    PMG_TRY(ns.next(op->ctx, lrc->k, 0, na_eta));
+    const double *rhs = b;
+    if (na_eta.mode != PMG_NOISE_NONE) {
+      PMG_TRY(lrc->prepare_rhs(b, na_eta, lrc->rhs.p));
+      rhs = lrc->rhs.p;
+    }
+    PMG_TRY(op->sweep(dir, coeffs, rhs, y, na));
+    return lrc->post(dir, y);
+  }
+  double lrc_omega_build = 1.0; // the reference builds Bb with a temporary MCSOR at its default omega (src/mc_sor.c:583-593)
   int sample(NoiseStream &ns, const double *b, double *y)
   {
     PMG_TRY(ensure());
+    if (LrcData *lrc = op->lrc_data()) {
+      if (type == PMG_SOR_SYMMETRIC_SWEEP) {
+        PMG_TRY(sweep_lrc(lrc, ns, PMG_SOR_FORWARD_SWEEP, b, y));
+        return sweep_lrc(lrc, ns, PMG_SOR_BACKWARD_SWEEP, b, y);
+      }
+      return sweep_lrc(lrc, ns, type == PMG_SOR_BACKWARD_SWEEP ? PMG_SOR_BACKWARD_SWEEP : PMG_SOR_FORWARD_SWEEP, b, y);
+    }
     NoiseArgs na;
     if (type == PMG_SOR_SYMMETRIC_SWEEP) { // forward with fresh noise, then backward with fresh noise (:172-182)
       PMG_TRY(ns.next(op->ctx, op->n(), op->row0(), na));
@@ -251,7 +287,7 @@ struct GibbsCore {
     }
     return 0;
   }
-  int64_t draws_per_sample() const { return (type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) * op->n(); }
+  int64_t draws_per_sample() const { return (type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) * (op->n() + (op->lrc_data() ? op->lrc_data()->k : 0)); }
 };
 
 struct pmg_mcsor_s {
@@ -282,6 +318,7 @@ struct LevelSampler {
 struct MgLevel {
   LevelOp                  *op = nullptr;
   std::unique_ptr<LevelOp>  owned;
+  std::unique_ptr<LevelOp>  lrc_owned; // A_l + B_l diag(S) B_l^T around `owned` (MATLRC hierarchies)
   std::unique_ptr<Transfer> P; // between this level and the next coarser one
   HostCsr                   interp;
   bool                      has_interp = false;
@@ -378,9 +415,9 @@ static int apply_coloring_policy(pmg_pc pc, LevelOp *op, bool is_user_mat)
 static int setup_level_sampler(pmg_ctx ctx, LevelSampler &s, LevelOp *op)
 {
   if (s.kind == KIND_CHOL) {
-    const HostCsr *a = op->host_csr();
+    const HostCsr *a = op->lrc_base() ? op->lrc_base()->host_csr() : op->host_csr();
     if (!a) PMG_FAIL(PMG_ERR_SUP, "cholsampler needs an assembled operator");
-    return s.chol.setup(ctx, *a);
+    return s.chol.setup(ctx, *a, op->lrc_data());
   }
   s.gibbs.op = op;
   return s.gibbs.ensure();
@@ -533,7 +570,8 @@ static int mg_tail(pmg_pc pc, int lt)
 static int gamgmc_setup(pmg_pc pc)
 {
   pmg_ctx  ctx  = pc->ctx;
-  LevelOp *fine = pc->mat->op.get();
+  LevelOp *top  = pc->mat->op.get();                      // what the user handed over (possibly A + B S B^T)
+  LevelOp *fine = top->lrc_base() ? top->lrc_base() : top; // the hierarchy is built from the base matrix (src/pc_gamgmc.c:296-353)
   // -pc_gamgmc_mg_type (src/pc_gamgmc.c:364): only the geometric hierarchy can be built without PETSc's GAMG
   const std::string mgtype = pc->get("pc_gamgmc_mg_type", "mg");
   bool              user_p = false;
@@ -617,6 +655,26 @@ static int gamgmc_setup(pmg_pc pc)
       if (grid_known) PMG_TRY(make_csr_grid_op(ctx, std::move(Ac), dim, d, pc->lv[l - 1].owned));
       else PMG_TRY(make_csr_op(ctx, std::move(Ac), pc->lv[l - 1].owned));
       pc->lv[l - 1].op = pc->lv[l - 1].owned.get();
+    }
+  }
+  if (LrcData *flrc = top->lrc_data()) {
+    // PCGAMGMC_SetUpHierarchy's MATLRC branch (src/pc_gamgmc.c:157-196): B_{l-1} = P_l^T B_l, every level samples from and
+    // computes residuals with A_l + B_l diag(S) B_l^T
+    const int           k = flrc->k;
+    std::vector<double> Bl = flrc->Bh, Bc;
+    DevBuf<double>      dBl, dBc;
+    pc->lv[L - 1].op = top;
+    for (int l = L - 1; l >= 1; --l) {
+      const int64_t nf = pc->lv[l].op->n(), nc = pc->lv[l - 1].op->n();
+      PMG_TRY(dBl.upload(Bl, ctx->stream));
+      PMG_TRY(dBc.alloc((size_t)nc * k));
+      for (int j = 0; j < k; ++j) PMG_TRY(pc->lv[l].P->restrict_to(dBl.p + (size_t)j * nf, dBc.p + (size_t)j * nc));
+      Bc.resize((size_t)nc * k);
+      PMG_CUDA(cudaMemcpyAsync(Bc.data(), dBc.p, Bc.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      PMG_TRY(make_lrc_op(ctx, pc->lv[l - 1].op, k, Bc.data(), flrc->Sh.data(), pc->lv[l - 1].lrc_owned));
+      pc->lv[l - 1].op = pc->lv[l - 1].lrc_owned.get();
+      Bl.swap(Bc);
     }
   }
   // samplers: defaults of src/pc_gamgmc.c:305-349 (levels: richardson + sorgibbs, 1 it; coarse: cholsampler)

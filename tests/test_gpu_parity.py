@@ -581,3 +581,155 @@ def test_coarse_tail_launch_is_bit_identical(pmg, ctx, dim, dims, levels, extra,
         out.append((y, pc.last_stats()["launches"], ctx.draw_counter - d0))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1] and out[0][2] == out[1][2]
+
+
+# ---- MATLRC operators A + B diag(S) B^T (SURVEY a1 / a9 / a10-LRC, config 5's low-rank observation update) -------------
+def _obs_matrix(rng, n, k):
+    """k sparse 'ball observation' columns like MakeObservationMats (src/obs.c:135-180): a few positive weights each."""
+    B = np.zeros((n, k))
+    for j in range(k):
+        idx = rng.choice(n, size=min(n, 12), replace=False)
+        B[idx, j] = rng.uniform(0.2, 1.0, idx.size)
+    return B
+
+
+@pytest.mark.parametrize("kind", ["csr", "grid"])
+@pytest.mark.parametrize("pctype,omega,sweep", [("mcgibbs", 1.0, 1), ("mcgibbs", 1.0, 3), ("mcgibbs", 1.0, 2), ("sorgibbs", 1.0, 1)])
+def test_lrc_gibbs_matches_oracle(pmg, ctx, orc, kind, pctype, omega, sweep):
+    rng = np.random.default_rng(SEED)
+    dims = (33, 21)
+    A = orc.laplace(2, *dims, kappa=1.5)
+    n, k = A.n, 5
+    B, S = _obs_matrix(rng, n, k), rng.uniform(50.0, 200.0, k)  # S = 1/sigma^2 of the observations
+    col = orc.Coloring.parity(dims)
+    base = make_mat(pmg, ctx, A, col) if kind == "csr" else pmg.Mat.laplace(ctx, 2, *dims, kappa=1.5)
+    mat = pmg.Mat.lrc(base, B, S)
+    x = rng.standard_normal(n)
+    assert relerr(mat.mult(x), A.to_scipy() @ x + B @ (S * (B.T @ x))) < 1e-13
+    pc = pmg.PC(ctx, pctype)
+    pc.set_operator(mat)
+    if pctype == "mcgibbs":
+        pc.mcgibbs_set_omega(omega)
+        pc.mcgibbs_set_sweep_type(sweep)
+    pc.setup()
+    its = 3
+    per = pc.noise_per_sample()
+    assert per == (n + k) * (2 if sweep == 3 else 1)
+    z = rng.standard_normal(its * per)
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(n), rng.standard_normal(n)
+    ref = orc.lrc_gibbs_richardson(A, B, S, b, y.copy(), its, orc.Noise.tape(z), col, omega, sweep)
+    pc.apply_richardson(b, y, its=its)
+    assert relerr(y, ref) < RTOL
+    # MCSORApply on the same operator: deterministic sweep + post-correction (src/mc_sor.c:216-239)
+    mc = pmg.MCSOR(mat)
+    mc.set_sweep_type(sweep)
+    y2 = rng.standard_normal(n)
+    Bb = {d: orc.lrc_build_correction(A, B, S, col, 1.0, d) for d in (orc.SOR_FORWARD, orc.SOR_BACKWARD)}
+    ref2 = orc.lrc_mcsor_apply(A, B, Bb, b, y2.copy(), col, 1.0, sweep)
+    mc.apply(b, y2)
+    assert relerr(y2, ref2) < RTOL
+
+
+def test_lrc_posterior_mean_device_rng(pmg, ctx, orc):
+    """Statistical acceptance in the style of examples/ex4.c: the sample mean approaches (A + B S B^T)^-1 b."""
+    rng = np.random.default_rng(SEED)
+    dims = (17, 17)
+    A = orc.laplace(2, *dims, kappa=3.0)
+    n, k = A.n, 6
+    B, S = _obs_matrix(rng, n, k), np.full(k, 100.0)
+    b = rng.standard_normal(n)
+    mat = pmg.Mat.lrc(pmg.Mat.laplace(ctx, 2, *dims, kappa=3.0), B, S)
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_mcgibbs_symmetric": "", "-pc_b200_noise": "philox"})
+    pc.setup()
+    ctx.set_seed(0xCAFE)
+    y, acc, nsamp = np.zeros(n), np.zeros(n), 6000
+    pc.apply_richardson(b, y, its=100)  # burn-in
+
+    def cb(it, ys):
+        acc[:] += ys
+
+    pc.set_sample_callback(cb)
+    pc.apply_richardson(b, y, its=nsamp)
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    mean = np.linalg.solve(P, b)
+    # Monte Carlo error of the mean ~ sqrt(trace(P^-1) / N) = 0.04 |mean| here; the reference's own acceptance is 5-10 % (ex4.c)
+    assert np.linalg.norm(acc / nsamp - mean) < 0.1 * np.linalg.norm(mean)
+
+
+def _q1_1d(nf):
+    nc = (nf + 1) // 2
+    P = np.zeros((nf, nc))
+    for i in range(nf):
+        if i % 2 == 0:
+            P[i, i // 2] = 1.0
+        else:
+            P[i, i // 2] = 0.5
+            if i // 2 + 1 < nc:
+                P[i, i // 2 + 1] = 0.5
+    return P
+
+
+@pytest.mark.parametrize("its_lv", [1, 2])
+def test_gamgmc_on_lrc_operator_matches_numpy_restatement(pmg, ctx, orc, its_lv):
+    """PCGAMGMC_SetUpHierarchy's MATLRC branch (src/pc_gamgmc.c:157-196): B_c = P^T B_f, every level samples from and
+    takes residuals with A_l + B_l S B_l^T, the coarsest level factors the assembled sum (src/pc_chols.c:119-157).
+    Checked against a numpy restatement of the V-cycle built from the oracle's LRC sampler."""
+    rng = np.random.default_rng(SEED)
+    dims = [(17, 17), (9, 9), (5, 5)]  # fine -> coarse
+    L = len(dims)
+    A = [orc.laplace(2, *dims[0], kappa=1.0)]
+    Ps = []
+    for l in range(1, L):
+        P = np.kron(_q1_1d(dims[l - 1][1]), _q1_1d(dims[l - 1][0]))  # natural order i + nx j: y index is the slow one
+        Ps.append(P)
+        Ad = P.T @ A[-1].to_scipy().toarray() @ P
+        import scipy.sparse as sp
+        m = sp.csr_matrix(Ad)
+        m.sort_indices()
+        A.append(orc.CSR(m.shape[0], m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float64)))
+    n, k = A[0].n, 4
+    B = [_obs_matrix(rng, n, k)]
+    S = rng.uniform(20.0, 80.0, k)
+    for l in range(1, L):
+        B.append(Ps[l - 1].T @ B[-1])
+    cols = [orc.Coloring.parity(dims[0])] + [orc.Coloring.parity(d, 2) for d in dims[1:]]
+    # the stencil-array levels sweep in 4 colours (i mod 2, j mod 2); the fine level is red-black
+    cols = [orc.Coloring.parity(dims[0])] + [orc.Coloring(np.array([(i % 2) + 2 * (j % 2) for j in range(d[1]) for i in range(d[0])], np.int32), 4) for d in dims[1:]]
+
+    lap = pmg.Mat.laplace(ctx, 2, *dims[0], kappa=1.0)
+    mat = pmg.Mat.lrc(lap, B[0], S)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(mat)
+    pc.set_options({"-gamgmc_pc_mg_levels": L, "-gamgmc_mg_levels_ksp_max_it": its_lv})
+    pc.setup()
+    nsamp = 2
+    per = pc.noise_per_sample()
+    z = rng.standard_normal(nsamp * per)
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(n), rng.standard_normal(n)
+
+    noise = orc.Noise.tape(z)
+    Pd = [A[l].to_scipy().toarray() + B[l] @ np.diag(S) @ B[l].T for l in range(L)]
+
+    def smooth(l, rhs, x):
+        return orc.lrc_gibbs_richardson(A[l], B[l], S, rhs, x, its_lv, noise, cols[l], 1.0, orc.SOR_FORWARD)
+
+    def cycle(l, rhs, x):
+        if l == L - 1:  # coarsest: y = L^-T (L^-1 b + z)
+            Lc = np.linalg.cholesky(Pd[l])
+            v = np.linalg.solve(Lc, rhs) + orc.noise_fill(noise, rhs.size)
+            return np.linalg.solve(Lc.T, v)
+        x = smooth(l, rhs, x)
+        r = rhs - Pd[l] @ x
+        xc = cycle(l + 1, Ps[l].T @ r, np.zeros(A[l + 1].n))
+        x = x + Ps[l] @ xc
+        return smooth(l, rhs, x)
+
+    ref = y.copy()
+    for _ in range(nsamp):  # y += MG(b - A y)  (src/pc_gamgmc.c:253-256)
+        ref = ref + cycle(0, b - Pd[0] @ ref, np.zeros(n))
+    pc.apply_richardson(b, y, its=nsamp)
+    assert relerr(y, ref) < 1e-10

@@ -395,3 +395,55 @@ def test_ex1_mean_convergence(orc, case):
         orc.gibbs_richardson(A, b, y, 600000, noise, None, 1.0, sw, callback=cb)
     rel = np.linalg.norm(acc["mean"] - ex_mean) / np.linalg.norm(ex_mean)
     assert rel <= 0.02, rel
+
+
+# ---- MATLRC operators: the restatement has no reference binary to be pinned against (the PETSc stub
+#      has no MATLRC), so it is validated by the property the construction exists for -----------------------------------
+@pytest.mark.parametrize("sweep", [1, 2, 3])
+@pytest.mark.parametrize("omega", [1.0])
+def test_lrc_sampler_leaves_posterior_invariant(orc, sweep, omega):
+    """One LRC-Gibbs sample is an affine-Gaussian map y' = G y + N z; N(0, (A + B S B^T)^-1) must be exactly stationary:
+    G Sigma G^T + N N^T = Sigma (src/mc_sor.c:456-479: 'enact the Sherman-Morrison-Woodbury correction')."""
+    A = orc.laplace(2, 6, 5, kappa=1.0)
+    n, k = A.n, 3
+    rng = np.random.default_rng(3)
+    B, S = rng.standard_normal((n, k)), rng.uniform(0.5, 2.0, k)
+    col = orc.Coloring.parity((6, 5))
+    per = (n + k) * (2 if sweep == orc.SOR_SYMMETRIC else 1)
+
+    def sample(y0, z):
+        return orc.lrc_gibbs_richardson(A, B, S, None, y0.copy(), 1, orc.Noise.tape(z), col, omega, sweep)
+
+    G = np.column_stack([sample(np.eye(n)[:, i], np.zeros(per)) for i in range(n)])
+    N = np.column_stack([sample(np.zeros(n), np.eye(per)[:, i]) for i in range(per)])
+    Sigma = np.linalg.inv(A.to_scipy().toarray() + B @ np.diag(S) @ B.T)
+    assert np.abs(G @ Sigma @ G.T + N @ N.T - Sigma).max() / np.abs(Sigma).max() < 1e-13
+
+
+def test_lrc_mean_converges_to_posterior_mean(orc):
+    """With a right-hand side the chain mean converges to (A + B S B^T)^-1 b (examples/benchmark: posterior sampling)."""
+    A = orc.laplace(2, 9, 9, kappa=2.0)
+    n, k = A.n, 4
+    rng = np.random.default_rng(11)
+    B, S = rng.standard_normal((n, k)) * 0.3, np.full(k, 5.0)
+    b = rng.standard_normal(n)
+    y = np.zeros(n)
+    # deterministic part only (zero noise): the fixed point of the map is the posterior mean
+    for _ in range(60):
+        y = orc.lrc_gibbs_richardson(A, B, S, b, y, 1, orc.Noise.tape(np.zeros(2 * (n + k))), orc.Coloring.parity((9, 9)), 1.0, orc.SOR_SYMMETRIC)
+    mean = np.linalg.solve(A.to_scipy().toarray() + B @ np.diag(S) @ B.T, b)
+    assert np.abs(y - mean).max() / np.abs(mean).max() < 1e-10
+
+
+def test_philox_grid_blocks_use_padded_index(orc):
+    """Blocks of a matrix-free grid operator are keyed on (k ny + j) pitch + i, pitch = nx rounded up to 4 (philox.cuh)."""
+    nx, ny = 13, 5
+    z = orc.noise_fill(orc.Noise.philox(0xCAFE, grid=(nx, ny, 1)), nx * ny)
+    pitch = 16
+    full = orc.normal_philox(0xCAFE, 0, 0, pitch * ny).reshape(ny, pitch)
+    assert np.array_equal(z.reshape(ny, nx), full[:, :nx])
+    # a block of another size (a coarse level) keeps plain global rows
+    ns = orc.Noise.philox(0xCAFE, grid=(nx, ny, 1))
+    assert np.array_equal(orc.noise_fill(ns, 21), orc.normal_philox(0xCAFE, 0, 0, 21))
+    # nx a multiple of 4: nothing changes
+    assert np.array_equal(orc.noise_fill(orc.Noise.philox(7, grid=(8, 3, 1)), 24), orc.normal_philox(7, 0, 0, 24))
