@@ -197,6 +197,7 @@ struct LevelOp {
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
   virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
+  virtual bool fused_tape_ok() const { return true; } // fused_sweep can take an injected noise tape
   // The fused sweeps work on PITCHED copies of the level's vectors (row stride rounded up so that every row starts on a
   // 32-byte boundary): fused_size() elements each; to/from_pitched convert between the natural layout of the API and it.
   virtual int64_t fused_size() const { return n(); }

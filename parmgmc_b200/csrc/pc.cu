@@ -810,7 +810,7 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
   } else { // mcgibbs: src/pc_mcgibbs.c:167-184; sorgibbs: src/pc_sorgibbs.c:125-129 (running sample_index from 0)
     if (pc->type == "sorgibbs") pc->sample_index = 0;
     LevelOp *op = pc->smp.gibbs.op;
-    if (op->fused_ok() && pc->scratch.p) { // one fused pass per directional sweep, ping-pong between y and scratch
+    if (op->fused_ok() && pc->scratch.p && (pc->noise.mode != PMG_NOISE_INJECTED || op->fused_tape_ok())) { // one fused pass per directional sweep, ping-pong between y and scratch
       std::vector<int> dirs;
       LevelSampler     one;
       one.its        = 1;

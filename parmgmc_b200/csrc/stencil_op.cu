@@ -667,9 +667,15 @@ struct GridOp : LevelOp {
       PMG_TRY(ghost_hi.alloc((size_t)g.unit));
       PMG_TRY(ghost_lo.zero(ctx->stream));
       PMG_TRY(ghost_hi.zero(ctx->stream));
+      // the thinnest slab of the partition (every rank must take the same code path: the exchanges are collective)
+      const int64_t        mine = g.shi - g.slo;
+      std::vector<int64_t> all((size_t)ctx->nranks, 0);
+      PMG_TRY(comm_allgather_i64(ctx, &mine, 1, all.data()));
+      min_units = *std::min_element(all.begin(), all.end());
     }
     return 0;
   }
+  int64_t min_units = (int64_t)1 << 40;
   // refresh the ghost units of x from the slab neighbours (replaces the per-colour VecScatter, src/mc_sor.c:318-319)
   int halo(const double *x)
   {
@@ -758,11 +764,26 @@ struct LapOp final : GridOp {
   bool fused_ok() const override
   {
     static const bool off = std::getenv("PMG_NO_FUSED") != nullptr;
-    if (off || parallel) return false;
+    if (off) return false;
+    if (parallel && (min_units < 2 || std::getenv("PMG_NO_FUSED_PARALLEL"))) return false; // two ghost units per side come from ONE neighbour
     if (g.dim == 2) return g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
     return g.n0 >= 8 && g.n1 >= 2 && g.n2 >= 2 && g.n0 < (1 << 20) && g.n1 < (1 << 20) && g.n2 < (1 << 20);
   }
-  bool fused_mg_ok() const override { return fused_ok() && g.dim == 2; }
+  bool fused_mg_ok() const override { return fused_ok() && g.dim == 2 && !parallel; }
+  bool fused_tape_ok() const override { return !parallel; } // the ghost units' noise is recomputed, which a tape of owned rows cannot supply
+  // On a slab the pitched vectors carry GH ghost units (grid rows in 2D, planes in 3D) on either side: one fused sweep
+  // updates both colours, so the boundary unit's second-colour update needs the neighbour's boundary unit AFTER its
+  // first-colour update, which is recomputed here from two old ghost units (and the ghost unit of b; the noise is a
+  // function of the global index).  One exchange of 2 units per sweep replaces the reference's per-colour scatters.
+  int     GH() const { return parallel ? 2 : 0; }
+  int64_t unit_rows() const { return g.dim == 2 ? 1 : g.n1; }
+  int     fused_halo(double *pitched)
+  {
+    if (!parallel) return 0;
+    const int64_t U = unit_rows() * pitch(), nu = g.shi - g.slo;
+    double       *own = pitched + GH() * U;
+    return comm_halo_exchange(ctx, own, pitched, own + (nu - GH()) * U, own + nu * U, (size_t)(GH() * U), (size_t)(GH() * U), ctx->stream);
+  }
   // Work list of the streaming kernels.  Warps whose tile touches the physical boundary run the predicated loop, which
   // costs about 1.6x the interior loop per row (profiles/r1_summary.md), and the grid is a single wave, so those warps
   // get half-height bands: every warp then finishes at about the same time.  Bands start on even rows (the fused
@@ -803,21 +824,21 @@ struct LapOp final : GridOp {
 
   int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
   int64_t slab_rows() const { return g.dim == 2 ? g.shi - g.slo : g.n1 * (g.shi - g.slo); }
-  int64_t fused_size() const override { return pitch() * slab_rows(); }
+  int64_t fused_size() const override { return pitch() * (slab_rows() + 2 * GH() * unit_rows()); }
   int     to_pitched(const double *natural, double *pitched) override
   {
     const Plan pl = g.dim == 2 ? plan3(g.n0, g.shi - g.slo, 1) : plan3(g.n0, g.n1, g.shi - g.slo);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), natural, pitched);
+    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), natural, pitched + GH() * unit_rows() * pitch());
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
-    return 0;
+    return fused_halo(pitched);
   }
   int from_pitched(const double *pitched, double *natural) override
   {
     const Plan pl = g.dim == 2 ? plan3(g.n0, g.shi - g.slo, 1) : plan3(g.n0, g.n1, g.shi - g.slo);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), pitched, natural);
+    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.dim == 2 ? g.shi - g.slo : g.n1, pitch(), pitched + GH() * unit_rows() * pitch(), natural);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -864,12 +885,12 @@ struct LapOp final : GridOp {
     static const bool swz = std::getenv("PMG_SW3_PLAIN") == nullptr; // SWIZZLE_32B boxes: conflict-free shared-memory reads
     a.swizzle = swz ? 1 : 0;
     if (swz) {
-      const int64_t dims[4] = {4, pitch() / 4, g.n1, g.shi - g.slo}, strides[4] = {1, 4, pitch(), pitch() * g.n1};
+      const int64_t dims[4] = {4, pitch() / 4, g.n1, g.shi - g.slo + 2 * GH()}, strides[4] = {1, 4, pitch(), pitch() * g.n1};
       const int     boxx[4] = {4, 32, NW + 2, 1}, boxb[4] = {4, 32, NW, 1};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, true));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, true));
     } else {
-      const int64_t dims[4] = {pitch(), g.n1, g.shi - g.slo, 1}, strides[4] = {1, pitch(), pitch() * g.n1, pitch() * g.n1 * (g.shi - g.slo)};
+      const int64_t dims[4] = {pitch(), g.n1, g.shi - g.slo + 2 * GH(), 1}, strides[4] = {1, pitch(), pitch() * g.n1, pitch() * g.n1 * (g.shi - g.slo + 2 * GH())};
       const int     boxx[4] = {128, NW + 2, 1, 1}, boxb[4] = {128, NW, 1, 1};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, false));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, false));
@@ -902,6 +923,9 @@ struct LapOp final : GridOp {
     const int        cfg     = cfg_env >= 0 && cfg_env <= 5 ? cfg_env : (g.n1 >= 48 ? 2 : 1);
     Args a;
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
+    a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();
+    if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "fused sweep on a slab cannot take an injected tape");
+    PMG_TRY(fused_halo(const_cast<double *>(xin)));
     a.pitch  = (int)pitch();
     a.pplane = (long long)pitch() * g.n1;
     a.flip   = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
@@ -991,17 +1015,20 @@ struct LapOp final : GridOp {
     static const bool swz = std::getenv("PMG_SW2_SWIZZLE") != nullptr;
     a.swizzle = swz ? 1 : 0;
     if (swz) {
-      const int64_t dims[3] = {4, pitch() / 4, g.shi - g.slo}, strides[3] = {1, 4, pitch()};
+      const int64_t dims[3] = {4, pitch() / 4, g.shi - g.slo + 2 * GH()}, strides[3] = {1, 4, pitch()};
       const int     box[3]  = {4, 32, STAGE_ROWS};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 3, dims, strides, box, true));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 3, dims, strides, box, true));
     } else { // pad columns are real (zero) elements in both views
-      const int64_t dims[3] = {pitch(), g.shi - g.slo, 1}, strides[3] = {1, pitch(), pitch() * (g.shi - g.slo)};
+      const int64_t dims[3] = {pitch(), g.shi - g.slo + 2 * GH(), 1}, strides[3] = {1, pitch(), pitch() * (g.shi - g.slo + 2 * GH())};
       const int     box[3]  = {128, STAGE_ROWS, 1};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 3, dims, strides, box, false));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 3, dims, strides, box, false));
     }
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.slo = (int)g.slo; a.shi = (int)g.shi;
+    a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();
+    if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "fused sweep on a slab cannot take an injected tape");
+    PMG_TRY(fused_halo(const_cast<double *>(xin)));
     a.pitch = (int)pitch();
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;

@@ -48,7 +48,8 @@ struct Coef { // per-node coefficients of the edge warps, indexed by the number 
 struct Args {
   CUtensorMap   tm_x, tm_b; // {4, pitch/4, local rows} FP64 tensors (SWIZZLE_32B), box 4 x 32 x 2 = 128 columns x 2 rows
   int           nx, ny;     // global grid
-  int           slo, shi;   // owned rows (the tensors' row 0 is grid row slo)
+  int           slo, shi;   // owned rows: the rows that are written, and the rows the injected tape covers
+  int           tlo, thi;   // rows held by the tensors and by xout: the owned rows plus two ghost rows per side on a slab
   const Item   *items;
   int           nitems;
   int           pitch; // row stride of xout (and of the tensors)
@@ -197,7 +198,7 @@ template <int NOISE, bool INTERIOR> struct Warp {
     wk[0] = w[1 - P];
     wk[1] = w[3 - P];
     const int jo = jj - 1; // row jj-1 is final
-    if (out_lane && jo >= ja && jo < jb) st256(a.xout + (long long)(jo - a.slo) * a.pitch + c, xs);
+    if (out_lane && jo >= ja && jo < jb) st256(a.xout + (long long)(jo - a.tlo) * a.pitch + c, xs);
   }
 };
 
@@ -222,18 +223,18 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     const uint32_t dst = ring + s * STAGE_BYTES, bar = bars + s * 8;
     mbar_expect_tx(bar, bytes);
     if (a.swizzle) {
-      tma_load_3d(dst, &a.tm_x, 0, c0 >> 2, J0 + 2 * t + 1 - a.slo, bar);
-      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, 0, c0 >> 2, J0 + 2 * t - a.slo, bar);
+      tma_load_3d(dst, &a.tm_x, 0, c0 >> 2, J0 + 2 * t + 1 - a.tlo, bar);
+      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, 0, c0 >> 2, J0 + 2 * t - a.tlo, bar);
     } else {
-      tma_load_3d(dst, &a.tm_x, c0, J0 + 2 * t + 1 - a.slo, 0, bar);
-      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, c0, J0 + 2 * t - a.slo, 0, bar);
+      tma_load_3d(dst, &a.tm_x, c0, J0 + 2 * t + 1 - a.tlo, 0, bar);
+      if (a.has_b) tma_load_3d(dst + STAGE_ROWS * ROW_BYTES, &a.tm_b, c0, J0 + 2 * t - a.tlo, 0, bar);
     }
   };
   // prologue rows J0-1, J0 travel through the x half of the LAST ring slot, whose first real stage is issued afterwards
   if (lane == 0) {
     mbar_expect_tx(bar_pro, STAGE_ROWS * ROW_BYTES);
-    if (a.swizzle) tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, 0, c0 >> 2, J0 - 1 - a.slo, bar_pro);
-    else tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, J0 - 1 - a.slo, 0, bar_pro);
+    if (a.swizzle) tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, 0, c0 >> 2, J0 - 1 - a.tlo, bar_pro);
+    else tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, J0 - 1 - a.tlo, 0, bar_pro);
     for (int t = 0; t < STAGES - 1 && t < T; ++t) issue(t);
   }
   double xss[4] = {0, 0, 0, 0}, xs[4], x0[4], wk[2] = {0, 0};
@@ -305,7 +306,7 @@ template <int NOISE, int WARPS, int STAGES, int MINB> __global__ void __launch_b
   const int  c0 = it.strip * STRIP_OUT - 4;
   const int  J0 = it.ja - 2; // lowest possible first step row
   // every node the warp updates exists and has all four neighbours, and every row it reads is owned
-  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && J0 >= 1 && it.jb <= a.ny - 2 && J0 - 1 >= a.slo && it.jb + 2 < a.shi;
+  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && J0 >= 1 && it.jb <= a.ny - 2 && J0 - 1 >= a.tlo && it.jb + 2 < a.thi;
   const uint32_t ring = smem_u32(base) + wl * STAGES * STAGE_BYTES, bars = smem_u32(bar + wl * (STAGES + 1));
   if (interior) run_warp<NOISE, true, STAGES>(a, ft, coef, ring, bars, lane, it);
   else run_warp<NOISE, false, STAGES>(a, ft, coef, ring, bars, lane, it);

@@ -51,7 +51,8 @@ struct Item {
 struct Args {
   CUtensorMap   tm_x, tm_b; // {4, pitch/4, ny, local planes} FP64 tensors (SWIZZLE_32B); boxes 4 x 32 x (NW+2) x 1 and 4 x 32 x NW x 1
   int           nx, ny, nz;
-  int           slo, shi; // owned planes (the tensors' plane 0 is grid plane slo)
+  int           slo, shi; // owned planes: the planes that are written, and the planes the injected tape covers
+  int           tlo, thi; // planes held by the tensors and by xout: the owned planes plus two ghost planes per side on a slab
   const Item   *items;
   int           pitch;    // row stride of xout
   long long     pplane;   // plane stride of xout = pitch * ny
@@ -149,14 +150,14 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
   auto issue_x = [&](int q) {
     const uint32_t bar = bar_x + (q % SX) * 8;
     mbar_expect_tx(bar, xbytes);
-    if (swz) tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, 0, c0 >> 2, it.ya - 2, K0 - 1 + q - a.slo, bar);
-    else tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, c0, it.ya - 2, K0 - 1 + q - a.slo, 0, bar);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, 0, c0 >> 2, it.ya - 2, K0 - 1 + q - a.tlo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, c0, it.ya - 2, K0 - 1 + q - a.tlo, 0, bar);
   };
   auto issue_b = [&](int r) {
     const uint32_t bar = bar_b + (r % SB) * 8;
     mbar_expect_tx(bar, bbytes);
-    if (swz) tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, 0, c0 >> 2, it.ya - 1, K0 + r - a.slo, bar);
-    else tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, c0, it.ya - 1, K0 + r - a.slo, 0, bar);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, 0, c0 >> 2, it.ya - 1, K0 + r - a.tlo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, c0, it.ya - 1, K0 + r - a.tlo, 0, bar);
   };
   const int nq = nsteps + 2; // x planes K0-1 .. K1+1
   if (threadIdx.x == 0) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
 #pragma unroll
     for (int m = 0; m < 4; ++m) cis[m] = ci[m];
     const int ko = kk - 1; // plane kk-1 of this row is final
-    if (out_thread && ko >= it.ka && ko < it.kb) st256(a.xout + (long long)(ko - a.slo) * a.pplane + (long long)y * a.pitch + c, xm1);
+    if (out_thread && ko >= it.ka && ko < it.kb) st256(a.xout + (long long)(ko - a.tlo) * a.pplane + (long long)y * a.pitch + c, xm1);
     publish(kk, x0); // the half-updated plane kk, for the neighbouring rows
     __syncthreads();
     if (threadIdx.x == 0) { // the boxes of plane kk (x) and of this step (b) are free
@@ -299,7 +300,7 @@ template <int NOISE, int NW, int SX, int SB, int MINB> __global__ void __launch_
   const Item it = a.items[blockIdx.x];
   const int  c0 = it.strip * STRIP_OUT - 4;
   // every node the CTA updates exists and has all six neighbours, and every row / plane it reads exists and is owned
-  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2 && it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.slo && it.kb + 1 < a.shi;
+  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2 && it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.tlo && it.kb + 1 < a.thi;
   if (interior) run_cta<NOISE, true, NW, SX, SB>(a, ft, coef, sm, it);
   else run_cta<NOISE, false, NW, SX, SB>(a, ft, coef, sm, it);
 }
