@@ -110,30 +110,64 @@ def cpu_baseline_leg(args, samples):
             "ms_per_sample": 1e3 * dt / samples}
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    n = args.n
+def _ref_worker(n, kappa, levels, per_step, warmup, steps, start_evt, ready_q, done_q):
+    """One independent chain of the reference's 1-rank CPU arithmetic (what a rank of `mpirun -np T` replicas would run)."""
     import oracle as orc
-    mg = orc.MG.geometric(2, n, n, 1, args.kappa, args.levels)
+    mg = orc.MG.geometric(2, n, n, 1, kappa, levels)
     mg.setup()
     b, y = np.zeros(n * n), np.zeros(n * n)
     ns = orc.Noise.rander48()
-    per_step = max(1, args.ref_samples_per_step)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         mg.richardson(ns, b, y, per_step)
+    ready_q.put(1)
+    start_evt.wait()
     t0 = time.time()
-    for _ in range(args.steps):
+    for _ in range(steps):
         mg.richardson(ns, b, y, per_step)
+    done_q.put(time.time() - t0)
+
+
+def run_reference(args):
+    """The reference's CPU path on the box's host cores.  PETSc + MPI cannot be built here, so the
+    arithmetic is the oracle port of the 1-rank reference; to use every host thread it runs T independent chains (the
+    replica-parallel pattern of examples/ex7.c:136-205), T = min(cores, --ref-procs, memory / 3 GB)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    n = args.n
+    per_step = max(1, args.ref_samples_per_step)
+    cores = os.cpu_count() or 1
+    try:
+        mem_gb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+    except (ValueError, OSError):
+        mem_gb = 16.0
+    per_proc_gb = 3.0 * (n / 4097.0) ** 2
+    T = max(1, min(cores, args.ref_procs if args.ref_procs > 0 else 16, int(mem_gb * 0.6 / per_proc_gb)))
+    mpc = mp.get_context("spawn")
+    start_evt, ready_q, done_q = mpc.Event(), mpc.Queue(), mpc.Queue()
+    procs = [mpc.Process(target=_ref_worker, args=(n, args.kappa, args.levels, per_step, args.warmup, args.steps, start_evt, ready_q, done_q)) for _ in range(T)]
+    for p in procs:
+        p.start()
+    for _ in range(T):
+        ready_q.get()
+    t0 = time.time()
+    start_evt.set()
+    times = [done_q.get() for _ in range(T)]
     dt = time.time() - t0
-    value = args.steps * per_step / dt
+    for p in procs:
+        p.join()
+    value = T * args.steps * per_step / dt
     cfg = workload_config(args, 1)
     cfg["samples_per_step"] = per_step
+    cfg["parallelism"] = f"{T} independent CPU chains (one per host thread used)"
+    cfg["noise"] = "rander48 Box-Muller (PETSc's default PetscRandom, src/parmgmc.c:100-110)"
+    cfg["workload"] = cfg["workload"].replace("SOR-Gibbs smoother (red-black)", "SOR-Gibbs smoother (lexicographic, the reference's 1-rank order)")
     out = {"impl": "reference", "metric": "mgmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-           "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "port",
-                            "sample": f"{per_step} sample(s) per step of the full {n}x{n} workload; the reference (PETSc+MPI) cannot be built here, so this is the oracle port of its 1-rank path"},
+           "cpu_baseline": {"value": value, "unit": "samples/s", "cores": T, "kind": "port", "host_cores": cores,
+                            "sample": f"{T} chains x {args.steps} steps x {per_step} sample(s) of the full {n}x{n} workload (slowest chain {max(times):.1f} s); the reference (PETSc+MPI) cannot be "
+                                      "built here, so each chain is the oracle port of its 1-rank path (one-colour lexicographic sweeps, rander48 Box-Muller)"},
            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -243,6 +277,42 @@ def run_b200(args):
     alg_bytes_launch = bytes_per_update * nloc / launches_per_sweep
     achieved = alg_bytes_launch / (sweep_ms * 1e-3 / launches_per_sweep) / 1e9
     peak, peak_src = measured_peaks()
+    # measured DRAM traffic of one launch of that kernel (ncu --set full, profiles/): only for the configuration it was taken on
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if world == 1 and os.path.exists(tj):
+        t = json.load(open(tj)).get("sweep2d_kernel", {})
+        if t.get("n") == n:
+            traffic = t.get("dram_bytes_per_launch")
+
+    # ---- BASELINE's target kernel: the fused 3D 7-point sweep on 512^3 per GPU (z-slabs, NCCL halo for N > 1) ----
+    gibbs3d = None
+    view = pc.view().strip().splitlines()[:2]
+    if not args.no_gibbs3d:
+        del gibbs, pc
+        n3 = args.n3
+        nz = n3 * world
+        slab3 = pmg.partition_slabs(nz, world)[rank] if world > 1 else None
+        mat3 = pmg.Mat.laplace(ctx, 3, n3, n3, nz, args.kappa, slab=slab3)
+        g3 = pmg.PC(ctx, "sorgibbs")
+        g3.set_operator(mat3)
+        g3.set_option("-pc_b200_noise", "philox")
+        g3.setup()
+        y3 = torch.zeros(mat3.n, dtype=torch.float64, device="cuda")
+        b3 = torch.zeros(mat3.n, dtype=torch.float64, device="cuda")
+        g3.apply_richardson_dev(b3, y3, its=3)
+        barrier()
+        e0.record(stream)
+        g3.apply_richardson_dev(b3, y3, its=10)
+        e1.record(stream)
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        ms3 = float(ms3.item())
+        ach3 = bytes_per_update * mat3.n / (ms3 * 1e-3) / 1e9
+        gibbs3d = {"workload": f"3D 7-point {n3}^3 per GPU, fused red-black sweep (sweep3d_kernel)", "sweep_ms": ms3, "dof_updates_per_s": world * mat3.n / (ms3 * 1e-3),
+                   "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak, "frac_of_nominal_8TBs": ach3 / 8000.0, "algorithmic_bytes_per_dof_update": bytes_per_update}}
 
     if rank == 0:
         cpu = cpu_baseline_leg(args, args.cpu_samples) if (world == 1 and not args.no_cpu_baseline) else None
@@ -251,12 +321,15 @@ def run_b200(args):
                "config": workload_config(args, world),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(2 * 8 * nloc), "d2h_bytes_per_step": int(8 * nloc)},
                "gpu_launches": int(launches), "clocks": clk,
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "note": "achieved = ALGORITHMIC bytes (32 B / DOF-update, SURVEY 8(d)) / time; the one-pass kernel actually moves ~24 B / update (traffic), so frac can exceed 1",
                             "kernel": "fine-level fused red-black sweep (sweep2d_kernel: both colours + Philox normals in one TMA-fed pass)", "algorithmic_bytes_per_dof_update": bytes_per_update,
                             "launch_ms": sweep_ms / launches_per_sweep, "peak_source": peak_src,
                             "frac_of_nominal_8TBs": achieved / 8000.0},
                "gibbs_dof_updates_per_s": world * nloc / (sweep_ms * 1e-3), "setup_s": setup_s,
-               "mgmc_ms_per_sample": ms / (args.steps * S), "view": pc.view().strip().splitlines()[:2]}
+               "mgmc_ms_per_sample": ms / (args.steps * S), "view": view}
+        if gibbs3d is not None:
+            out["gibbs3d"] = gibbs3d
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
@@ -271,10 +344,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4097)
+    ap.add_argument("--n3", type=int, default=512, help="edge of the 3D grid per GPU for the gibbs3d measurement")
     ap.add_argument("--levels", type=int, default=0, help="0: 9 + log2(gpus), i.e. the coarsest grid stays about 17 nodes wide in y as the grid grows")
     ap.add_argument("--kappa", type=float, default=1.0)
     ap.add_argument("--samples-per-step", type=int, default=5)
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
+    ap.add_argument("--ref-procs", type=int, default=0, help="CPU chains of the reference arm (0: min(cores, 16, memory / 3 GB))")
+    ap.add_argument("--no-gibbs3d", action="store_true", help="skip the 3D 7-point sweep measurement")
     ap.add_argument("--cpu-samples", type=int, default=4)
     ap.add_argument("--bytes-per-update", type=float, default=32.0, help="algorithmic bytes per DOF update of the fine sweep (DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
