@@ -198,6 +198,14 @@ struct LevelOp {
   virtual bool fused_ok() const { return false; }
   virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
   virtual bool fused_tape_ok() const { return true; } // fused_sweep can take an injected noise tape
+  // One directional sweep in a single out-of-place pass on the level's natural-layout vectors (box_stream.cuh)
+  virtual bool stream_ok() const { return false; }
+  virtual int  stream_sweep(int dir, const SweepCoeffs &c, const double *b, const double *xin, double *xout, const NoiseArgs &na)
+  {
+    (void)dir; (void)c; (void)b; (void)xin; (void)xout; (void)na;
+    pmg_set_error("streaming sweep not available for this operator");
+    return PMG_ERR_SUP;
+  }
   // The fused sweeps work on PITCHED copies of the level's vectors (row stride rounded up so that every row starts on a
   // 32-byte boundary): fused_size() elements each; to/from_pitched convert between the natural layout of the API and it.
   virtual int64_t fused_size() const { return n(); }

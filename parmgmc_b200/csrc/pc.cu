@@ -499,6 +499,32 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   MgLevel &v   = pc->lv[l];
   if (l == pc->tail_top && zero_guess && b == v.b.p && x == v.x.p) return mg_tail(pc, l); // levels 0..l in one launch
   const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p;
+  // stencil-array levels: each directional sweep is one out-of-place pass (box_stream.cuh); the level's iterate
+  // ping-pongs between v.x and v.x2, so the current one is always v.x.p
+  const bool bstream = !fused && l > 0 && v.smp.kind != KIND_CHOL && v.x2.p && x == v.x.p && v.op->stream_ok() &&
+                       (pc->noise.mode != PMG_NOISE_INJECTED || v.op->fused_tape_ok());
+  if (bstream) {
+    MgLevel         &c = pc->lv[l - 1];
+    std::vector<int> dirs;
+    sweep_dirs(v.smp, dirs);
+    PMG_TRY(v.smp.gibbs.ensure());
+    NoiseArgs na;
+    auto      smooth = [&]() -> int {
+      for (int d : dirs) {
+        PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+        PMG_TRY(v.op->stream_sweep(d, v.smp.gibbs.coeffs, b, v.x.p, v.x2.p, na));
+        std::swap(v.x, v.x2);
+      }
+      return 0;
+    };
+    if (zero_guess) PMG_CUDA(cudaMemsetAsync(v.x.p, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
+    PMG_TRY(smooth());
+    PMG_TRY(v.op->residual(b, v.x.p, v.r.p));
+    PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
+    PMG_TRY(v.P->prolong_add(pc->lv[l - 1].x.p, v.x.p));
+    return smooth();
+  }
   if (!fused) {
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
     PMG_TRY(run_level_sampler(pc, v.smp, b, x));
@@ -507,7 +533,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(v.op->residual(b, x, v.r.p));
     PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
     PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
-    PMG_TRY(v.P->prolong_add(c.x.p, x));
+    PMG_TRY(v.P->prolong_add(pc->lv[l - 1].x.p, x));
     return run_level_sampler(pc, v.smp, b, x);
   }
   MgLevel         &c = pc->lv[l - 1];
@@ -525,7 +551,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
   for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
-    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? c.x.p : nullptr, nullptr));
+    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? pc->lv[l - 1].x.p : nullptr, nullptr));
     std::swap(cur, oth);
   }
   if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->fused_size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -695,6 +721,7 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(v.x.alloc(n));
     }
     if (l > 0) PMG_TRY(v.r.alloc(n));
+    if (l > 0 && l < L - 1 && v.smp.kind != KIND_CHOL && v.op->stream_ok()) PMG_TRY(v.x2.alloc(n));
     if (l > 0 && l == L - 1 && v.op->fused_mg_ok() && v.smp.kind != KIND_CHOL) {
       PMG_TRY(v.x2.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_y.alloc((size_t)v.op->fused_size()));

@@ -25,6 +25,7 @@
 #include "stream2d.cuh"
 #include "sweep2d.cuh"
 #include "sweep3d.cuh"
+#include "box_stream.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -308,9 +309,10 @@ template <int DIM> __global__ void __launch_bounds__(256) box_sweep_kernel(Geom 
   int64_t idx, i, j, k;
   if (!box_colour_node<DIM>(g, color, idx, i, j, k)) return;
   const bool   interior = box_interior<DIM>(g, bc, i, j, k);
-  const double sq = interior ? bc.sqrtdiag : sqrtdiag[idx], id = interior ? bc.idiag : idiag[idx];
-  double       sum = noisy_rhs(na, idx, sq, b ? b[idx] : 0.0);
-  sum              = box_row<DIM, true, false>(g, bc, coef, stride, x, glo, ghi, idx, i, j, k, sum);
+  const double   sq = interior ? bc.sqrtdiag : sqrtdiag[idx], id = interior ? bc.idiag : idiag[idx];
+  const uint64_t nid = (uint64_t)(((DIM == 3 ? k * g.n1 : 0) + j) * ((g.n0 + 3) & ~(int64_t)3) + i); // padded index (philox.cuh)
+  double         sum = noisy_rhs_id(na, idx, nid, sq, b ? b[idx] : 0.0);
+  sum                = box_row<DIM, true, false>(g, bc, coef, stride, x, glo, ghi, idx, i, j, k, sum);
   const double t0  = __dmul_rn(omo, x[idx]);
   x[idx]           = fma(id, sum, t0);
 }
@@ -435,13 +437,14 @@ template <int DIM> __device__ __forceinline__ void tail_sweep(const TailLevelDev
   const int   nc = DIM == 3 ? 8 : 4;
   double     *zb = L.r;
   if (na.mode == PMG_NOISE_PHILOX) {
-    const int nq = ((int)g.nl + 3) >> 2;
+    const int qrow = ((int)g.n0 + 3) >> 2, nrows = (int)(g.nl / g.n0), nq = qrow * nrows; // quads of the padded index space
     for (int q = gtid; q < nq; q += gsize) {
-      double z[4];
+      const int row = q / qrow, qi = q - row * qrow;
+      double    z[4];
       philox_normal_quad(na.seed, na.call, (uint64_t)q, z);
 #pragma unroll
       for (int m = 0; m < 4; ++m)
-        if (4 * q + m < (int)g.nl) zb[4 * q + m] = z[m];
+        if (4 * qi + m < (int)g.n0) zb[(int64_t)row * g.n0 + 4 * qi + m] = z[m];
     }
     tail_sync(cluster);
   }
@@ -1230,6 +1233,69 @@ struct BoxOp final : GridOp {
     ctx->dof_updates += g.nl;
     return 0;
   }
+
+  // ---- fused four-colour sweep in one pass (box_stream.cuh): 2D, one device ----
+  DevBuf<boxstream::Item> sitems;
+  int                     nsitems = 0;
+  bool stream_ok() const override
+  {
+    if (std::getenv("PMG_NO_BOX_STREAM")) return false;
+    const char   *mn    = std::getenv("PMG_BOX_STREAM_MIN"); // smaller levels are launch-latency bound either way
+    const int64_t min_n = mn ? std::atoll(mn) : 20000;
+    return g.dim == 2 && !parallel && g.slo == 0 && g.shi == g.n1 && g.n0 >= 16 && g.n1 >= 8 && g.nl >= min_n && g.nl < ((int64_t)1 << 31);
+  }
+  int stream_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na) override
+  {
+    using namespace boxstream;
+    constexpr int WARPS = 4;
+    static const int mb_env = std::getenv("PMG_BOX_STREAM_MINB") ? std::atoi(std::getenv("PMG_BOX_STREAM_MINB")) : 4;
+    auto          kern  = mb_env == 6 ? box_stream_kernel<WARPS, 6> : mb_env == 5 ? box_stream_kernel<WARPS, 5> : box_stream_kernel<WARPS, 4>;
+    if (!nsitems) { // one resident wave: bands sized from the kernel's occupancy
+      int occ = 0;
+      PMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, 0));
+      const int         slots   = std::max(1, occ) * WARPS * ctx->sm_count;
+      const int         nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
+      static const int by_env = std::getenv("PMG_BOX_STREAM_BY") ? std::atoi(std::getenv("PMG_BOX_STREAM_BY")) : 0;
+      int              by     = by_env > 0 ? by_env : 2; // short bands: the per-step dependency chain is long, parallelism hides it (profiles/r1_summary.md)
+      by += by & 1;
+      std::vector<Item> list;
+      for (;; by += 2) {
+        list.clear();
+        for (int s = 0; s < nstrips; ++s)
+          for (int64_t j = 0; j < g.n1; j += by) list.push_back(Item{s, (int)j, (int)std::min<int64_t>(j + by, g.n1)});
+        if ((int)list.size() <= slots || by >= g.n1 || by_env > 0) break;
+      }
+      nsitems = (int)list.size();
+      PMG_TRY(sitems.upload(list, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    Args a;
+    a.nx = (int)g.n0; a.ny = (int)g.n1;
+    a.items = sitems.p; a.nitems = nsitems;
+    a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
+    a.xin = xin; a.b = b; a.xout = xout;
+    a.coef = coef.p; a.idiag = co.idiag.p; a.sqrtdiag = co.sqrtdiag.p;
+    for (int s = 0; s < 9; ++s) a.c[s] = bc.c[s];
+    a.has_const = bc.on; a.ring = bc.ring;
+    a.idiag_c = a.sd_c = 0.0;
+    if (bc.on) { // BoxOp::sweep's interior coefficients
+      const double d   = bc.c[4];
+      double       inv = 1.0 / d;
+      a.idiag_c        = inv * co.omega;
+      a.sd_c           = std::sqrt(std::fabs(d)) * std::sqrt((2 - co.omega) / co.omega);
+    }
+    a.omo  = 1.0 - co.omega;
+    a.mode = na.mode; a.tape = na.tape;
+    philox_expand_keys(na.seed, a.pk);
+    a.call_lo = (uint32_t)na.call; a.call_hi = (uint32_t)(na.call >> 32);
+    a.pitch4  = (int)((g.n0 + 3) & ~(int64_t)3);
+    kern<<<(unsigned)((nsitems + WARPS - 1) / WARPS), WARPS * 32, 0, ctx->stream>>>(a);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+
   template <bool RES> int apply(const double *b, const double *x, double *out)
   {
     PMG_TRY(halo(x));

@@ -733,3 +733,39 @@ def test_gamgmc_on_lrc_operator_matches_numpy_restatement(pmg, ctx, orc, its_lv)
         ref = ref + cycle(0, b - Pd[0] @ ref, np.zeros(n))
     pc.apply_richardson(b, y, its=nsamp)
     assert relerr(y, ref) < 1e-10
+
+
+# ---- the fused four-colour sweep of the stencil-array levels (box_stream.cuh) ------------------------------------------
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((257, 257, 1), 4, {}),
+    ((301, 173, 1), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    ((129, 513, 1), 4, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.4}),
+])
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+def test_box_stream_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, noise, monkeypatch):
+    """One pass per directional sweep on the 9-point levels must reproduce the launch-per-colour result exactly."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for stream in (True, False):
+        if stream:
+            monkeypatch.setenv("PMG_BOX_STREAM_MIN", "0")
+            monkeypatch.delenv("PMG_NO_BOX_STREAM", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_BOX_STREAM", "1")
+        lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=1.0)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(5).standard_normal(2 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(99)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
