@@ -1006,7 +1006,7 @@ struct LapOp final : GridOp {
     if (mode == PMG_NOISE_INJECTED) return launch2_cfg<sweep2d::NOISE_TAPE>(cfg, a, slots);
     return launch2_cfg<sweep2d::NOISE_PHILOX>(cfg, a, slots);
   }
-  int fused_sweep2_tma(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
+  int fused_sweep2_tma(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse = nullptr, const double *xc = nullptr)
   {
     using namespace sweep2d;
     LapTab t;
@@ -1036,6 +1036,13 @@ struct LapOp final : GridOp {
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;
     a.xout  = xout;
+    a.xc = nullptr; a.cnx = a.cny = 0;
+    if (xc) { // prolongation fused into the sweep: the coarse level is a whole grid on this device
+      int     cd;
+      int64_t cn[3];
+      if (!coarse || !coarse->structured(cd, cn) || parallel) PMG_FAIL(PMG_ERR_SUP, "fused prolongation needs a structured coarse level on one device");
+      a.xc = xc; a.cnx = (int)cn[0]; a.cny = (int)cn[1];
+    }
     a.tape  = na.tape;
     a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega;
     for (int d = 0; d < 5; ++d) a.coef[d] = Coef{t.idiag[d], t.sqrtdiag[d], 1.0 - co.omega, 0.0};
@@ -1072,7 +1079,8 @@ struct LapOp final : GridOp {
       return fused_sweep3(dir, co, b, xin, xout, na);
     }
     static const bool no_tma = std::getenv("PMG_NO_TMA") != nullptr;
-    if (!xc && !bc && xin && !no_tma) return fused_sweep2_tma(dir, co, b, xin, xout, na);
+    static const bool no_tma_prolong = std::getenv("PMG_NO_TMA_PROLONG") != nullptr;
+    if (!bc && xin && !no_tma && (!xc || !no_tma_prolong)) return fused_sweep2_tma(dir, co, b, xin, xout, na, coarse, xc);
     using namespace stream2d;
     LapTab t;
     fill_tab(co.omega, t);

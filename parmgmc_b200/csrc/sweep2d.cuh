@@ -57,6 +57,8 @@ struct Args {
   int           has_b;
   int           swizzle; // 1: tensors are {4, pitch/4, rows} with SWIZZLE_32B; 0: {pitch, rows, 1}, plain rows
   double       *xout;
+  const double *xc;   // non-null: the sweep starts from xin + P xc (MatInterpolateAdd fused into the post-smoother); xc is the
+  int           cnx, cny; // coarse level's natural-layout iterate on its cnx x cny grid (Q1)
   const double *tape; // injected noise of this block: natural layout (row stride nx), local rows
   double        h, idiag, sd, omo; // interior coefficients
   Coef          coef[6];
@@ -248,6 +250,55 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   __syncwarp();
   if (lane == 0 && STAGES - 1 < T) issue(STAGES - 1);
 
+  // x_old row j = xin row j + (P xc) row j, in MatInterpolateAdd's order: s = x; s = fma(w, xc_J, s) over ascending coarse index
+  auto prolong = [&](int j, double (&out)[4]) {
+    if (a.xc == nullptr) return; // warp-uniform
+    const int    Jlo = j >> 1, nJ = (j & 1) ? 2 : 1;
+    const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
+    const int    I0 = c >> 1; // c = 0 mod 4: fine columns c .. c+3 see coarse columns I0, I0+1, I0+2
+    if (INTERIOR) {
+      const double *p = a.xc + (long long)Jlo * a.cnx + I0;
+      for (int q = 0; q < nJ; ++q, p += a.cnx) {
+        const double c0v = p[0], c1v = p[1], c2v = p[2];
+        out[0] = fma(wj, c0v, out[0]);
+        out[1] = fma(wh, c1v, fma(wh, c0v, out[1]));
+        out[2] = fma(wj, c1v, out[2]);
+        out[3] = fma(wh, c2v, fma(wh, c1v, out[3]));
+      }
+      return;
+    }
+    if (j < 0 || j >= a.ny) return;
+    for (int q = 0; q < nJ; ++q) {
+      const int J = Jlo + q;
+      if (J >= a.cny) continue;
+      double        cv[3];
+      const double *p = a.xc + (long long)J * a.cnx + I0;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) cv[m] = (I0 + m >= 0 && I0 + m < a.cnx) ? p[m] : 0.0;
+      if (c >= 0 && c < a.nx) out[0] = fma(wj, cv[0], out[0]);
+      if (c + 1 >= 0 && c + 1 < a.nx) {
+        out[1] = fma(wh, cv[0], out[1]);
+        if (I0 + 1 < a.cnx) out[1] = fma(wh, cv[1], out[1]);
+      }
+      if (c + 2 >= 0 && c + 2 < a.nx) out[2] = fma(wj, cv[1], out[2]);
+      if (c + 3 >= 0 && c + 3 < a.nx) {
+        out[3] = fma(wh, cv[1], out[3]);
+        if (I0 + 2 < a.cnx) out[3] = fma(wh, cv[2], out[3]);
+      }
+    }
+  };
+  auto prefetch_coarse = [&](int j) { // the coarse rows that fine rows j, j+1 will read
+    if (!INTERIOR || a.xc == nullptr) return;
+    const double *p = a.xc + (long long)(j >> 1) * a.cnx + (c >> 1);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cnx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cnx + 2));
+  };
+  prolong(J0 - 1, xs);
+  prolong(J0, x0);
+  prefetch_coarse(J0 + 1);
+
   auto row_classes = [&](int jj, int (&ci)[4]) {
     if (INTERIOR) return;
     const bool rowok   = jj >= 0 && jj < a.ny;
@@ -264,12 +315,15 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     double xa[4], ba[4] = {0, 0, 0, 0};
     lds256(src, lane, xa, swz);
     if (a.has_b) lds256(src + 2 * ROW_BYTES, lane, ba, swz);
+    prolong(jj + 1, xa);
+    if (jj + 4 <= it.jb) prefetch_coarse(jj + 3);
     W.template step<0>(jj, xss, xs, x0, xa, ba, wk, cis);
     row_classes(jj, cis);
     if (2 * t + 1 < N) {
       double xb[4], bb[4] = {0, 0, 0, 0};
       lds256(src + ROW_BYTES, lane, xb, swz);
       if (a.has_b) lds256(src + 3 * ROW_BYTES, lane, bb, swz);
+      prolong(jj + 2, xb);
       __syncwarp();
       if (lane == 0 && t + STAGES < T) issue(t + STAGES);
       W.template step<1>(jj + 1, xs, x0, xa, xb, bb, wk, cis);

@@ -738,7 +738,7 @@ def test_gamgmc_on_lrc_operator_matches_numpy_restatement(pmg, ctx, orc, its_lv)
 # ---- the fused four-colour sweep of the stencil-array levels (box_stream.cuh) ------------------------------------------
 @pytest.mark.parametrize("dims,levels,extra", [
     ((257, 257, 1), 4, {}),
-    ((301, 173, 1), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    ((301, 173, 1), 4, {"-gamgmc_mg_levels_ksp_max_it": 2}),
     ((129, 513, 1), 4, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.4}),
 ])
 @pytest.mark.parametrize("noise", ["philox", "tape"])
