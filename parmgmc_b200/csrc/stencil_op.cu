@@ -875,11 +875,11 @@ struct LapOp final : GridOp {
     items3_nw = NW3;
     return 0;
   }
-  template <int NOISE, int NW, int SX, int SB, int MINB> int launch3(sweep3d::Args &a, const double *b, const double *xin)
+  template <int NOISE, int NW, int SX, int SB, int MINB, bool WS = false> int launch3(sweep3d::Args &a, const double *b, const double *xin)
   {
     using namespace sweep3d;
-    auto         kern = sweep3d_kernel<NOISE, NW, SX, SB, MINB>;
-    const size_t sm   = Smem<NW, SX, SB>::total;
+    auto         kern = sweep3d_kernel<NOISE, NW, SX, SB, MINB, WS>;
+    const size_t sm   = Smem<NW, SX, SB, WS>::total;
     static bool  attr_set = false;
     if (!attr_set) {
       PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -902,7 +902,7 @@ struct LapOp final : GridOp {
     const int        bz     = bz_env > 0 ? bz_env : 64;
     if (items3_bz != bz || items3_nw != NW) PMG_TRY(build_items3(bz, NW));
     a.items = items3.p;
-    kern<<<(unsigned)nitems3, NW * 32, sm, ctx->stream>>>(a);
+    kern<<<(unsigned)nitems3, NW * 32 * (WS ? 2 : 1), sm, ctx->stream>>>(a);
     return 0;
   }
   template <int NOISE> int launch3_cfg(int cfg, sweep3d::Args &a, const double *b, const double *xin)
@@ -913,7 +913,10 @@ struct LapOp final : GridOp {
     case 2: return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);
     case 3: return launch3<NOISE, 16, 5, 3, 1>(a, b, xin);
     case 4: return launch3<NOISE, 16, 6, 4, 1>(a, b, xin);
-    default: return launch3<NOISE, 8, 5, 3, 2>(a, b, xin);
+    case 5: return launch3<NOISE, 8, 5, 3, 2>(a, b, xin);
+    default:
+      if (NOISE == sweep3d::NOISE_PHILOX) return launch3<sweep3d::NOISE_PHILOX, 16, 4, 2, 1, true>(a, b, xin); // warp-specialised
+      return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);
     }
   }
   int fused_sweep3(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
@@ -923,7 +926,7 @@ struct LapOp final : GridOp {
     LapTab t;
     fill_tab(co.omega, t);
     static const int cfg_env = std::getenv("PMG_SW3_CFG") ? std::atoi(std::getenv("PMG_SW3_CFG")) : -1;
-    const int        cfg     = cfg_env >= 0 && cfg_env <= 5 ? cfg_env : (g.n1 >= 48 ? 2 : 1);
+    const int        cfg     = cfg_env >= 0 && cfg_env <= 6 ? cfg_env : (g.n1 >= 48 ? 2 : 1);
     Args a;
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();

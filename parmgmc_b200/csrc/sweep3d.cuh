@@ -83,9 +83,10 @@ __device__ __forceinline__ uint32_t box_off(int lane, int M, bool swz) { return 
 // the half-updated planes are published component-major ([4][32] doubles per row): conflict-free 8-byte accesses
 __device__ __forceinline__ uint32_t new_off(int lane, int M) { return (uint32_t)(M * 256 + lane * 8); }
 
-template <int NW, int SX, int SB> struct Smem {
+template <int NW, int SX, int SB, bool WS = false> struct Smem {
   static constexpr int    XSTAGE = (NW + 2) * ROW_BYTES, BSTAGE = NW * ROW_BYTES, NEWBUF = NW * ROW_BYTES;
-  static constexpr size_t off_x = 0, off_b = off_x + (size_t)SX * XSTAGE, off_new = off_b + (size_t)SB * BSTAGE, off_tab = off_new + 2 * (size_t)NEWBUF;
+  static constexpr size_t off_x = 0, off_b = off_x + (size_t)SX * XSTAGE, off_new = off_b + (size_t)SB * BSTAGE, off_z = off_new + 2 * (size_t)NEWBUF; // z: WS only
+  static constexpr size_t off_tab = off_z + (WS ? 2 * (size_t)NEWBUF : 0);
   static constexpr size_t off_coef = off_tab + sizeof(fastnormal::SharedTables), off_bar = off_coef + 8 * sizeof(Coef), total = off_bar + (SX + SB) * 8 + 1024;
 };
 
@@ -131,11 +132,16 @@ __device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane
   }
 }
 
-template <int NOISE, bool INTERIOR, int NW, int SX, int SB>
+// WS (warp-specialised, Philox only): warps NW .. 2NW-1 are noise producers.  Producer i generates sqrtdiag * z of row i one
+// plane ahead into a double-buffered shared-memory array, stencil warp i reads it: the long FP64 transcendental chains and
+// the latency-sensitive stencil part run in different warps, and twice as many warps are resident (setmaxnreg gives the
+// producers 40 registers and the stencil warps 88).
+template <int NOISE, bool INTERIOR, int NW, int SX, int SB, bool WS>
 __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t sm, const Item it)
 {
-  using L = Smem<NW, SX, SB>;
-  const int  lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  using L = Smem<NW, SX, SB, WS>;
+  const int  lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = WS ? warp % NW : warp;
+  const bool producer = WS && warp >= NW;
   const int  c0 = it.strip * STRIP_OUT - 4, c = c0 + 4 * lane;
   const int  y = it.ya - 1 + w;
   const bool inner_row = w >= 1 && w <= NW - 2;
@@ -185,6 +191,34 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
 #pragma unroll
     for (int m = 0; m < 4; ++m) ci[m] = (kok && rowok && colok[m]) ? 6 - colmiss[m] - rowmiss - kmiss : 7;
   };
+  // sqrtdiag * z of row (y, kk), the first rounding of w = b + sqrtdiag z (src/pc_mcgibbs.c:124-126)
+  auto scaled_normals = [&](int kk, const int (&ci)[4], double (&zs)[4]) {
+    const long long quad = (((long long)kk * a.ny + y) * a.pitch + c) >> 2;
+    uint32_t        w0, w1, w2, w3;
+    double          z[4];
+    philox4x32_10_keys((uint32_t)quad, (uint32_t)((unsigned long long)quad >> 32), a.call_lo, a.call_hi, a.pk, w0, w1, w2, w3);
+    fastnormal::box_muller(ft, w0, w1, z[0], z[1]);
+    fastnormal::box_muller(ft, w2, w3, z[2], z[3]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) zs[m] = __dmul_rn(z[m], INTERIOR ? a.sd : coef[ci[m]].sd);
+  };
+  if (producer) { // ---- noise producers: z of step s goes to buffer s & 1, one step ahead of its use ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int s = 0; s <= nsteps; ++s) { // iteration s produces step s, then joins the barrier that ends step s-1 (s = 0: the prologue's)
+      if (s < nsteps) {
+        int    ci[4] = {0, 0, 0, 0};
+        double zs[4];
+        classes(K0 + s, ci);
+        scaled_normals(K0 + s, ci, zs);
+        const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * ROW_BYTES;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) sts64(p + new_off(lane, m), zs[m]);
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  if (WS) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 
   double A[4] = {0, 0, 0, 0}, B[4], C[4], D[4], wk[2] = {0, 0}; // rolling window: planes kk-2, kk-1, kk and the incoming kk+1
   int    cis[4] = {7, 7, 7, 7};
@@ -222,6 +256,10 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
     if (NOISE == NOISE_NONE) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) wv[m] = bb[m];
+    } else if (WS) {
+      const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * ROW_BYTES;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) wv[m] = __dadd_rn(lds64(p + new_off(lane, m)), bb[m]);
     } else {
       double z[4];
       if (NOISE == NOISE_TAPE) {
@@ -281,9 +319,9 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
   else pairs(std::integral_constant<int, 1>{});
 }
 
-template <int NOISE, int NW, int SX, int SB, int MINB> __global__ void __launch_bounds__(NW * 32, MINB) sweep3d_kernel(const __grid_constant__ Args a)
+template <int NOISE, int NW, int SX, int SB, int MINB, bool WS = false> __global__ void __launch_bounds__(NW * 32 * (WS ? 2 : 1), MINB) sweep3d_kernel(const __grid_constant__ Args a)
 {
-  using L = Smem<NW, SX, SB>;
+  using L = Smem<NW, SX, SB, WS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   fastnormal::SharedTables *fts  = reinterpret_cast<fastnormal::SharedTables *>(base + L::off_tab);
@@ -301,8 +339,8 @@ template <int NOISE, int NW, int SX, int SB, int MINB> __global__ void __launch_
   const int  c0 = it.strip * STRIP_OUT - 4;
   // every node the CTA updates exists and has all six neighbours, and every row / plane it reads exists and is owned
   const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2 && it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.tlo && it.kb + 1 < a.thi;
-  if (interior) run_cta<NOISE, true, NW, SX, SB>(a, ft, coef, sm, it);
-  else run_cta<NOISE, false, NW, SX, SB>(a, ft, coef, sm, it);
+  if (interior) run_cta<NOISE, true, NW, SX, SB, WS>(a, ft, coef, sm, it);
+  else run_cta<NOISE, false, NW, SX, SB, WS>(a, ft, coef, sm, it);
 }
 
 } // namespace sweep3d
