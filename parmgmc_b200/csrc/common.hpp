@@ -223,6 +223,14 @@ struct LevelOp {
 struct Transfer {
   virtual ~Transfer() {}
   virtual bool tail_ok() const { return false; } // matrix-free Q1 transfer between two whole grids on one device
+  // b_c = P^T (b - A x) in one kernel, without storing the residual (same arithmetic as residual + restrict_to)
+  virtual bool fused_residual_ok() const { return false; }
+  virtual int  restrict_residual(const double *b_fine, const double *x_fine, double *b_coarse)
+  {
+    (void)b_fine; (void)x_fine; (void)b_coarse;
+    pmg_set_error("fused residual + restriction not available for this transfer");
+    return PMG_ERR_SUP;
+  }
   virtual int restrict_to(const double *r_fine, double *b_coarse) = 0; // b_c = P^T r
   virtual int prolong_add(const double *x_coarse, double *x_fine) = 0; // x_f += P x_c
 };

@@ -519,8 +519,11 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     };
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(v.x.p, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
     PMG_TRY(smooth());
-    PMG_TRY(v.op->residual(b, v.x.p, v.r.p));
-    PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    if (v.P->fused_residual_ok() && !v.op->lrc_data()) PMG_TRY(v.P->restrict_residual(b, v.x.p, c.b.p));
+    else {
+      PMG_TRY(v.op->residual(b, v.x.p, v.r.p));
+      PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    }
     PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
     PMG_TRY(v.P->prolong_add(pc->lv[l - 1].x.p, v.x.p));
     return smooth();
@@ -530,8 +533,11 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(run_level_sampler(pc, v.smp, b, x));
     if (l == 0) return 0;
     MgLevel &c = pc->lv[l - 1];
-    PMG_TRY(v.op->residual(b, x, v.r.p));
-    PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    if (v.P->fused_residual_ok() && !v.op->lrc_data()) PMG_TRY(v.P->restrict_residual(b, x, c.b.p));
+    else {
+      PMG_TRY(v.op->residual(b, x, v.r.p));
+      PMG_TRY(v.P->restrict_to(v.r.p, c.b.p));
+    }
     PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
     PMG_TRY(v.P->prolong_add(pc->lv[l - 1].x.p, x));
     return run_level_sampler(pc, v.smp, b, x);

@@ -1356,10 +1356,53 @@ struct BoxOp final : GridOp {
   }
 };
 
+// b_c = P^T (b - A x) for a stencil-array fine level on one device: every coarse node recomputes the residuals of its (up
+// to 3^d) fine nodes -- same box_row order and same ascending-fine-index accumulation as box_apply_kernel + restrict_kernel,
+// so the result is bit-identical, but the residual is never written or read back (the level is L2-resident: the extra
+// reads of x hit the cache).
+template <int DIM> __global__ void __launch_bounds__(256) box_restrict_residual_kernel(Geom gf, Geom gc, const double *__restrict__ coef, BoxConst bc, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ bcoarse)
+{
+  int64_t I, J, K, idx;
+  if (!node_of_thread<DIM>(gc, I, J, K, idx)) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int dk = (DIM == 3 ? -1 : 0); dk <= (DIM == 3 ? 1 : 0); ++dk)
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+      for (int di = -1; di <= 1; ++di) {
+        const int64_t i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+        if (i < 0 || i >= gf.n0 || j < 0 || j >= gf.n1 || k < 0 || k >= gf.n2) continue;
+        const double  w  = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+        const int64_t q  = i + gf.n0 * (j + gf.n1 * k);
+        const double  ax = box_row<DIM, false, true>(gf, bc, coef, gf.nl, x, nullptr, nullptr, q, i, j, k, 0.0);
+        acc              = fma(w, __dsub_rn(b[q], ax), acc);
+      }
+  bcoarse[idx] = acc;
+}
+
 struct GridTransfer final : Transfer {
   pmg_ctx ctx;
   GridOp *fine, *coarse;
   bool    tail_ok() const override { return !fine->parallel && !coarse->parallel; }
+  bool    fused_residual_ok() const override
+  {
+    // opt-in: bit-identical but not faster than residual + restriction on B200 (each fine residual is recomputed by up to
+    // 2^d coarse nodes; measured 1.02 vs 1.01 ms per V-cycle sample, profiles/r1_summary.md)
+    return std::getenv("PMG_FUSED_RESIDUAL") && !fine->parallel && !coarse->parallel && dynamic_cast<BoxOp *>(fine) != nullptr && fine->g.slo == 0 && fine->g.shi == fine->g.nslow();
+  }
+  int restrict_residual(const double *b, const double *x, double *bcoarse) override
+  {
+    auto       *bx = static_cast<BoxOp *>(fine);
+    const Geom &gf = fine->g, &gc = coarse->g;
+    const Plan  pl = gf.dim == 2 ? plan_nodes<2>(gc) : plan_nodes<3>(gc);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) box_restrict_residual_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, bx->coef.p, bx->bc, b, x, bcoarse);
+    else box_restrict_residual_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, bx->coef.p, bx->bc, b, x, bcoarse);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
   int restrict_to(const double *r, double *bcoarse) override
   {
     PMG_TRY(fine->halo(r));

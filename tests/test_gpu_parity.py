@@ -769,3 +769,28 @@ def test_box_stream_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, noise,
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1]
+
+
+@pytest.mark.parametrize("dim,dims,levels", [(2, (129, 97, 1), 4), (3, (33, 25, 17), 3)])
+def test_fused_residual_restriction_is_bit_identical(pmg, ctx, dim, dims, levels, monkeypatch):
+    """b_c = P^T (b - A x) in one kernel (box_restrict_residual_kernel) vs residual + restriction."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.setenv("PMG_FUSED_RESIDUAL", "1")
+        else:
+            monkeypatch.delenv("PMG_FUSED_RESIDUAL", raising=False)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(pmg.Mat.laplace(ctx, dim, *dims, kappa=1.0))
+        pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0})
+        pc.setup()
+        pc.set_noise_mode(pmg.NOISE_PHILOX)
+        ctx.set_seed(17)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
