@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4097)
     ap.add_argument("--n3", type=int, default=512, help="edge of the 3D grid per GPU for the gibbs3d measurement")
-    ap.add_argument("--levels", type=int, default=0, help="0: 9 + log2(gpus), i.e. the coarsest grid stays about 17 nodes wide in y as the grid grows")
+    ap.add_argument("--levels", type=int, default=0, help="0: 8 + log2(gpus): the coarsest grid is 33 nodes wide (SURVEY 8(d): cut at <= 33x33 + dense Cholesky) as the grid grows")
     ap.add_argument("--kappa", type=float, default=1.0)
     ap.add_argument("--samples-per-step", type=int, default=5)
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.levels <= 0:
-        args.levels = 9 + max(0, (max(1, args.gpus) - 1).bit_length())
+        args.levels = 8 + max(0, (max(1, args.gpus) - 1).bit_length())
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
