@@ -766,8 +766,7 @@ struct LapOp final : GridOp {
   // ---- fused streaming path (stream2d.cuh): 2D, single device ----
   bool fused_ok() const override
   {
-    static const bool off = std::getenv("PMG_NO_FUSED") != nullptr;
-    if (off) return false;
+    if (std::getenv("PMG_NO_FUSED")) return false; // read per call: the tests switch paths inside one process
     if (parallel && (min_units < 2 || std::getenv("PMG_NO_FUSED_PARALLEL"))) return false; // two ghost units per side come from ONE neighbour
     if (g.dim == 2) return g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
     return g.n0 >= 8 && g.n1 >= 2 && g.n2 >= 2 && g.n0 < (1 << 20) && g.n1 < (1 << 20) && g.n2 < (1 << 20);
