@@ -794,3 +794,68 @@ def test_fused_residual_restriction_is_bit_identical(pmg, ctx, dim, dims, levels
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1]
+
+
+# ---- estimators on device-RNG chains vs reference-RNG chains (BASELINE north star: mean, covariance and IACT within
+#      Monte Carlo error; estimators of src/stats.c:94-117 and src/iact.c:17-92 as restated in oracle/stats.c) -------------
+@pytest.mark.parametrize("pctype,kappa", [("mcgibbs", 0.05), ("gamgmc", 0.05)])
+def test_device_rng_covariance_and_iact_match_reference_rng_chain(pmg, ctx, orc, pctype, kappa):
+    """The same sampler, once on the device with Philox noise and once in the oracle with the reference's rander48
+    Box-Muller stream: the covariance estimate converges to A^-1 at the same rate and the integrated autocorrelation time
+    of a QOI agrees.  kappa = 0.05 makes A ill-conditioned (cond ~ 50), so plain Gibbs mixes slowly (IACT >> 1) and the
+    V-cycle does not (IACT ~ 1): the comparison would notice a wrong noise scale or a correlated generator."""
+    dims, N, burn = (9, 9), 40000, 2000
+    A = orc.laplace(2, *dims, kappa=kappa)
+    n = A.n
+    Ad = A.to_scipy().toarray()
+    q = np.zeros(n)
+    q[n // 2] = 1.0  # QOI: the centre node
+    # --- device chain ---
+    lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=kappa)
+    pc = pmg.PC(ctx, pctype)
+    pc.set_operator(lap)
+    pc.set_options({"-pc_mcgibbs_symmetric": ""} if pctype == "mcgibbs" else {"-gamgmc_pc_mg_levels": 3})
+    pc.set_option("-pc_b200_noise", "philox")
+    pc.setup()
+    ctx.set_seed(0xCAFE)
+    y = np.zeros(n)
+    pc.apply_richardson(np.zeros(n), y, its=burn)
+    dev = np.empty((N, n))
+
+    def cb(it, ys):
+        dev[it] = ys
+
+    pc.set_sample_callback(cb)
+    pc.apply_richardson(np.zeros(n), y, its=N)
+    # --- reference-RNG chain (oracle) ---
+    ref = np.empty((N, n))
+
+    def ocb(it, ys):
+        if it >= burn:
+            ref[it - burn] = ys
+
+    if pctype == "mcgibbs":
+        orc.gibbs_richardson(A, np.zeros(n), np.zeros(n), burn + N, orc.Noise.rander48(), orc.Coloring.parity(dims), 1.0, orc.SOR_SYMMETRIC, callback=ocb)
+    else:
+        omg = orc.MG.geometric(2, dims[0], dims[1], 1, kappa, 3)
+        omg.set_smoother(0, orc.KIND_CHOL, 1.0, 1, 1, None)
+        for l in (1, 2):
+            d = omg.level_dims(l)
+            omg.set_smoother(l, orc.KIND_SORGIBBS, 1.0, orc.SOR_FORWARD, 1, orc.Coloring.parity(d[:2], 2 if l == 2 else 4))
+        omg.setup()
+        omg.richardson(orc.Noise.rander48(), np.zeros(n), np.zeros(n), burn + N, callback=ocb)
+    # covariance (EstimateCovarianceMatErrors, src/stats.c:94-117): relative Frobenius error against A^-1
+    e_dev = orc.cov_errors(Ad, dev[None])[0]
+    e_ref = orc.cov_errors(Ad, ref[None])[0]
+    tau_dev, ok_dev = orc.iact(dev @ q)
+    tau_ref, ok_ref = orc.iact(ref @ q)
+    assert ok_dev and ok_ref
+    assert abs(tau_dev - tau_ref) < 0.3 * tau_ref + 0.3, (tau_dev, tau_ref)
+    if pctype == "gamgmc":
+        assert tau_dev < 2.0  # the multigrid sampler decorrelates in about one cycle
+    else:
+        assert tau_dev > 3.0  # plain Gibbs does not, on this operator
+    # Monte Carlo error of a covariance estimate from N / tau effective samples; both chains must sit at that level
+    bound = 6.0 * np.sqrt(max(tau_ref, 1.0) / N) * np.sqrt(n) / 3.0
+    assert e_dev < bound and e_ref < bound, (e_dev, e_ref, bound)
+    assert e_dev < 3.0 * e_ref + 0.02 and e_ref < 3.0 * e_dev + 0.02, (e_dev, e_ref)
