@@ -87,6 +87,13 @@ int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr_host, const
  * dim = 3 is the 7-point extension).  The grid is nx*ny*nz in natural order; this rank owns the
  * slab [slab_lo, slab_hi) of the slowest dimension (0, ny or nz for the whole grid). */
 int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, pmg_mat *mat);
+/* A row-partitioned operator, one call per rank (collective): this rank owns rows [row_start, row_start + n_local) of an
+ * n_global x n_global matrix and passes them with GLOBAL column indices, as MatCreateMPIAIJWithArrays would.  The library
+ * splits them into the diagonal block, the off-diagonal block and its column map exactly as the reference reads them
+ * from MatMPIAIJGetSeqAIJ (src/mc_sor.c:308-310) and gathers the ghost values before every colour (src/mc_sor.c:318-319).
+ * The colouring must be a distance-1 colouring of the GLOBAL graph (src/mc_sor.c:383-395): pmg_mat_set_coloring checks it
+ * across ranks; the automatic one offsets a local greedy colouring by rank (parity) instead of PETSc's Jones-Plassmann. */
+int pmg_mat_create_csr_dist(pmg_ctx ctx, int64_t n_global, int64_t row_start, int64_t n_local, const int64_t *rowptr_host, const int64_t *col_global_host, const double *val_host, pmg_mat *mat);
 /* MatCreateLRC(A, B, S, NULL): the operator A + B diag(S) B^T with B dense n x k (column-major) and S of length k, as the
  * reference's samplers receive it through MatLRCGetMats (src/mc_sor.c:565-595, src/pc_mcgibbs.c:236-244,
  * src/pc_sorgibbs.c:204-223).  A is borrowed and must outlive the result; sweeps run on A and are followed by the

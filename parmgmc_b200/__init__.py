@@ -64,6 +64,7 @@ SIGNATURES = {
     "pmg_mat_create_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
+    "pmg_mat_create_csr_dist": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_destroy": (C.c_int, [_vp]),
     "pmg_mat_get_size": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pmg_mat_set_coloring": (C.c_int, [_vp, C.c_int, _i32p]),
@@ -238,6 +239,14 @@ class Mat:
         rowptr = np.ascontiguousarray(rowptr, np.int64)
         h = _vp()
         _check(lib().pmg_mat_create_csr(ctx._h, rowptr.size - 1, rowptr, np.ascontiguousarray(col, np.int32), _f64(val), C.byref(h)))
+        return Mat(ctx, h)
+
+    @staticmethod
+    def from_csr_dist(ctx: Context, n_global, row_start, rowptr, col_global, val) -> "Mat":
+        """This rank's rows [row_start, row_start + len(rowptr) - 1) with GLOBAL column indices (MPIAIJ-style; collective)."""
+        rowptr = np.ascontiguousarray(rowptr, np.int64)
+        h = _vp()
+        _check(lib().pmg_mat_create_csr_dist(ctx._h, n_global, row_start, rowptr.size - 1, rowptr, np.ascontiguousarray(col_global, np.int64), _f64(val), C.byref(h)))
         return Mat(ctx, h)
 
     @staticmethod

@@ -146,3 +146,21 @@ int comm_allgatherv(pmg_ctx ctx, const double *send, double *recv, const int64_t
   PMG_NCCL(nccl().GroupEnd());
   return 0;
 }
+
+// personalised exchange: send + send_off[r] .. send_off[r+1] goes to rank r, recv + recv_off[r] .. recv_off[r+1] comes from
+// rank r (the per-colour ghost gather of MCSORApply_MPIAIJ, src/mc_sor.c:318-319, for row-partitioned CSR operators)
+int comm_exchange_v(pmg_ctx ctx, const double *send, const int64_t *send_off, double *recv, const int64_t *recv_off, cudaStream_t stream)
+{
+  if (ctx->nranks == 1) return 0;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  if (!comm) PMG_FAIL(PMG_ERR_COMM, "communicator not initialised");
+  PMG_NCCL(nccl().GroupStart());
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) continue;
+    const int64_t ns = send_off[r + 1] - send_off[r], nr = recv_off[r + 1] - recv_off[r];
+    if (ns) PMG_NCCL(nccl().Send(send + send_off[r], (size_t)ns, ncclDouble, r, comm, stream));
+    if (nr) PMG_NCCL(nccl().Recv(recv + recv_off[r], (size_t)nr, ncclDouble, r, comm, stream));
+  }
+  PMG_NCCL(nccl().GroupEnd());
+  return 0;
+}

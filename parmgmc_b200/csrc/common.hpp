@@ -247,6 +247,10 @@ struct pmg_mat_s {
   }
 };
 
+int comm_exchange_v(pmg_ctx ctx, const double *send, const int64_t *send_off, double *recv, const int64_t *recv_off, cudaStream_t stream);
+int comm_allgather_i64(pmg_ctx ctx, const int64_t *local_host, int count, int64_t *all_host);
+// row-partitioned CSR operator: this rank's rows [row_start, row_start + n_local) with GLOBAL column indices (csr_op.cu)
+int make_csr_dist_op(pmg_ctx ctx, int64_t n_global, int64_t row_start, int64_t n_local, const int64_t *rowptr, const int64_t *col_global, const double *val, std::unique_ptr<LevelOp> &op);
 int make_lrc_op(pmg_ctx ctx, LevelOp *base, int k, const double *B_host, const double *S_host, std::unique_ptr<LevelOp> &op); // lrc.cu
 
 // host-side sparse helpers (host_sparse.cpp)

@@ -79,7 +79,11 @@ int build_sell(pmg_ctx ctx, const HostCsr &a, const std::vector<int32_t> &rows, 
 
 // ---- the fused colour sweep ---------------------------------------------------------------------
 // one warp per slice, one row per lane
-__global__ void __launch_bounds__(256) sell_sweep_kernel(const int64_t *__restrict__ slice_off, const int32_t *__restrict__ col, const double *__restrict__ val, const int32_t *__restrict__ rows, const double *__restrict__ idiag, const double *__restrict__ sqrtdiag, const double *__restrict__ b, double *__restrict__ y, double one_minus_omega, NoiseArgs na, int64_t slice0, int64_t nslices)
+// Row-partitioned operators (MCSORApply_MPIAIJ, src/mc_sor.c:298-381): column indices >= nl address the ghost values
+// gathered from the other ranks (`ghost`, one slot per distinct off-rank column); nl = INT32_MAX on one device.
+__device__ __forceinline__ double ext_load(const double *__restrict__ y, const double *__restrict__ ghost, int32_t nl, int32_t c) { return c < nl ? y[c] : ghost[c - nl]; }
+
+__global__ void __launch_bounds__(256) sell_sweep_kernel(const int64_t *__restrict__ slice_off, const int32_t *__restrict__ col, const double *__restrict__ val, const int32_t *__restrict__ rows, const double *__restrict__ idiag, const double *__restrict__ sqrtdiag, const double *__restrict__ b, double *__restrict__ y, double one_minus_omega, NoiseArgs na, int64_t slice0, int64_t nslices, int32_t nl, const double *__restrict__ ghost)
 {
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int     lane = threadIdx.x & 31;
@@ -94,9 +98,16 @@ __global__ void __launch_bounds__(256) sell_sweep_kernel(const int64_t *__restri
   const int32_t *cp = col + off + lane;
   const double  *vp = val + off + lane;
 #pragma unroll 4
-  for (int k = 0; k < w; ++k) sum = fma(-vp[(int64_t)k * 32], y[cp[(int64_t)k * 32]], sum);
+  for (int k = 0; k < w; ++k) sum = fma(-vp[(int64_t)k * 32], ext_load(y, ghost, nl, cp[(int64_t)k * 32]), sum);
   const double t = __dmul_rn(one_minus_omega, y[r]);
   y[r]           = fma(idiag[p], sum, t);
+}
+
+// pack the locally owned values the other ranks need (send list grouped by destination rank)
+__global__ void gather_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ y, double *__restrict__ out)
+{
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = y[idx[q]];
 }
 
 enum ApplyMode { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2 };
@@ -104,7 +115,7 @@ enum ApplyMode { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2 };
 // out_r = sum_k a_k x[c_k]          (SPMV: MatMult / MatMultTranspose with the transposed matrix)
 // out_r = b_r - sum_k a_k x[c_k]    (RESIDUAL: MatMult then VecAYPX(-1, b))
 // out_r = out_r + sum ... started from out_r (ADD: MatMultAdd, MatInterpolateAdd)
-template <int MODE> __global__ void __launch_bounds__(256) sell_apply_kernel(const int64_t *__restrict__ slice_off, const int32_t *__restrict__ col, const double *__restrict__ val, const int32_t *__restrict__ rows, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ out, int64_t nslices)
+template <int MODE> __global__ void __launch_bounds__(256) sell_apply_kernel(const int64_t *__restrict__ slice_off, const int32_t *__restrict__ col, const double *__restrict__ val, const int32_t *__restrict__ rows, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ out, int64_t nslices, int32_t nl, const double *__restrict__ ghost)
 {
   const int64_t s    = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int     lane = threadIdx.x & 31;
@@ -117,18 +128,18 @@ template <int MODE> __global__ void __launch_bounds__(256) sell_apply_kernel(con
   const double  *vp  = val + off + lane;
   double         sum = MODE == MODE_ADD ? out[r] : 0.0;
 #pragma unroll 4
-  for (int k = 0; k < w; ++k) sum = fma(vp[(int64_t)k * 32], x[cp[(int64_t)k * 32]], sum);
+  for (int k = 0; k < w; ++k) sum = fma(vp[(int64_t)k * 32], ext_load(x, ghost, nl, cp[(int64_t)k * 32]), sum);
   out[r] = MODE == MODE_RESIDUAL ? __dsub_rn(b[r], sum) : sum;
 }
 
-int launch_apply(pmg_ctx ctx, int mode, const Sell &s, const double *x, const double *b, double *out)
+int launch_apply(pmg_ctx ctx, int mode, const Sell &s, const double *x, const double *b, double *out, int32_t nl = INT32_MAX, const double *ghost = nullptr)
 {
   if (s.nslices == 0) return 0;
   const int  wpb  = 8;
   const dim3 grid((unsigned)((s.nslices + wpb - 1) / wpb)), block(wpb * 32);
-  if (mode == MODE_SPMV) sell_apply_kernel<MODE_SPMV><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices);
-  else if (mode == MODE_RESIDUAL) sell_apply_kernel<MODE_RESIDUAL><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices);
-  else sell_apply_kernel<MODE_ADD><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices);
+  if (mode == MODE_SPMV) sell_apply_kernel<MODE_SPMV><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices, nl, ghost);
+  else if (mode == MODE_RESIDUAL) sell_apply_kernel<MODE_RESIDUAL><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices, nl, ghost);
+  else sell_apply_kernel<MODE_ADD><<<grid, block, 0, ctx->stream>>>(s.slice_off.p, s.col.p, s.val.p, s.rows.p, x, b, out, s.nslices, nl, ghost);
   PMG_CUDA(cudaGetLastError());
   ctx->launches++;
   return 0;
@@ -153,6 +164,61 @@ struct CsrOp final : LevelOp {
   int                  gdim        = 0; // > 0: rows are the nodes of a gdims[0] x gdims[1] x gdims[2] grid, natural order
   int64_t              gdims[3]    = {0, 0, 0};
 
+  // ---- row-partitioned operator (MatMPIAIJGetSeqAIJ's diagonal block, off-diagonal block and column map,
+  //      src/mc_sor.c:308-310): A holds this rank's rows with LOCAL column indices, columns >= n_local are ghosts ----
+  bool                 dist = false;
+  int64_t              row_start = 0, n_global = 0, n_local = 0, n_ghost = 0;
+  HostCsr              Aloc; // the diagonal block alone (local graph: colouring)
+  std::vector<int64_t> ghost_gid, send_off, recv_off; // sorted global ids of the ghost columns; per-rank offsets
+  DevBuf<int32_t>      send_idx;
+  DevBuf<double>       send_buf, ghost;
+  int32_t              nl() const { return dist ? (int32_t)n_local : INT32_MAX; }
+  int64_t              nglobal() const override { return dist ? n_global : A.n; }
+  int64_t              row0() const override { return row_start; }
+  // gather the current values of the ghost columns (the reference does this per colour with one VecScatter per colour
+  // holding only that colour's columns, src/mc_sor.c:152-214; one plan for all ghost columns moves a superset)
+  int halo(const double *y)
+  {
+    if (!dist || ctx->nranks == 1) return 0;
+    const int64_t ns = send_off.back();
+    if (ns) {
+      gather_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(ns, send_idx.p, y, send_buf.p);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return comm_exchange_v(ctx, send_buf.p, send_off.data(), ghost.p, recv_off.data(), ctx->stream);
+  }
+  // colours of the ghost columns (for validating / building a GLOBAL distance-1 colouring)
+  int ghost_colours(const std::vector<int32_t> &mine, std::vector<int32_t> &gc)
+  {
+    gc.assign((size_t)n_ghost, -1);
+    if (!dist || ctx->nranks == 1) return 0;
+    std::vector<double> h((size_t)n_local);
+    for (int64_t r = 0; r < n_local; ++r) h[(size_t)r] = (double)mine[(size_t)r];
+    DevBuf<double> d;
+    PMG_TRY(d.upload(h, ctx->stream));
+    PMG_TRY(halo(d.p));
+    std::vector<double> g((size_t)n_ghost);
+    if (n_ghost) PMG_CUDA(cudaMemcpyAsync(g.data(), ghost.p, sizeof(double) * (size_t)n_ghost, cudaMemcpyDeviceToHost, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t q = 0; q < n_ghost; ++q) gc[(size_t)q] = (int32_t)g[(size_t)q];
+    return 0;
+  }
+  // adjacent same-colour pairs, local and across ranks, summed over all ranks (every rank gets the same number)
+  int global_violations(const std::vector<int32_t> &cand, int64_t &bad)
+  {
+    bad = host_coloring_violations(Aloc, cand);
+    std::vector<int32_t> gc;
+    PMG_TRY(ghost_colours(cand, gc));
+    for (int64_t r = 0; r < n_local; ++r)
+      for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k)
+        if (A.col[k] >= n_local && gc[(size_t)(A.col[k] - n_local)] == cand[(size_t)r]) ++bad;
+    std::vector<int64_t> all((size_t)ctx->nranks);
+    PMG_TRY(comm_allgather_i64(ctx, &bad, 1, all.data()));
+    bad = std::accumulate(all.begin(), all.end(), (int64_t)0);
+    return 0;
+  }
+
   bool structured(int &dim, int64_t dims[3]) const override
   {
     if (!gdim) return false;
@@ -163,7 +229,7 @@ struct CsrOp final : LevelOp {
 
   int64_t        n() const override { return A.n; }
   int            ncolors() const override { return ncol; }
-  const HostCsr *host_csr() override { return &A; }
+  const HostCsr *host_csr() override { return dist ? nullptr : &A; } // a slab of rows is not an operator on its own
 
   int init()
   {
@@ -175,6 +241,54 @@ struct CsrOp final : LevelOp {
     }
     PMG_TRY(build_sell(ctx, A, natural_rows(A.n), false, full));
     return set_coloring_auto(PMG_COLORING_GREEDY);
+  }
+
+  // set-up of the ghost plan: who owns my ghost columns, and which of my rows the others need
+  int init_dist(const std::vector<int64_t> &gids)
+  {
+    const int P = ctx->nranks, me = ctx->rank;
+    ghost_gid = gids;
+    n_ghost   = (int64_t)gids.size();
+    std::vector<int64_t> mine{row_start, n_local, n_ghost}, all((size_t)3 * P);
+    PMG_TRY(comm_allgather_i64(ctx, mine.data(), 3, all.data()));
+    std::vector<int64_t> starts((size_t)P + 1);
+    int64_t              max_ghost = 0;
+    for (int r = 0; r < P; ++r) {
+      starts[(size_t)r] = all[(size_t)3 * r];
+      max_ghost         = std::max(max_ghost, all[(size_t)3 * r + 2]);
+      if (r > 0 && all[(size_t)3 * r] != all[(size_t)3 * (r - 1)] + all[(size_t)3 * (r - 1) + 1]) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: the row ranges of ranks %d and %d are not contiguous", r - 1, r);
+    }
+    starts[(size_t)P] = all[(size_t)3 * (P - 1)] + all[(size_t)3 * (P - 1) + 1];
+    if (starts[0] != 0 || starts[(size_t)P] != n_global) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: the row ranges do not tile 0 .. %lld", (long long)n_global);
+    // the ghost ids are sorted, the ownership ranges ascending: the ghost array is grouped by owner in rank order
+    recv_off.assign((size_t)P + 1, 0);
+    for (int64_t g : ghost_gid) {
+      if (g < 0 || g >= n_global || (g >= row_start && g < row_start + n_local)) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: bad ghost column %lld", (long long)g);
+      const int owner = (int)(std::upper_bound(starts.begin(), starts.end(), g) - starts.begin()) - 1;
+      recv_off[(size_t)owner + 1]++;
+    }
+    for (int r = 0; r < P; ++r) recv_off[(size_t)r + 1] += recv_off[(size_t)r];
+    // everybody learns everybody's ghost list (set-up only), and keeps the ids it owns as its send list for that rank
+    std::vector<int64_t> padded((size_t)std::max<int64_t>(1, max_ghost), -1), lists((size_t)std::max<int64_t>(1, max_ghost) * P);
+    std::copy(ghost_gid.begin(), ghost_gid.end(), padded.begin());
+    PMG_TRY(comm_allgather_i64(ctx, padded.data(), (int)padded.size(), lists.data()));
+    std::vector<int32_t> sidx;
+    send_off.assign((size_t)P + 1, 0);
+    for (int r = 0; r < P; ++r) {
+      if (r != me)
+        for (int64_t q = 0; q < all[(size_t)3 * r + 2]; ++q) {
+          const int64_t g = lists[(size_t)r * padded.size() + (size_t)q];
+          if (g >= row_start && g < row_start + n_local) sidx.push_back((int32_t)(g - row_start));
+        }
+      send_off[(size_t)r + 1] = (int64_t)sidx.size();
+    }
+    if (sidx.empty()) sidx.push_back(0);
+    PMG_TRY(send_idx.upload(sidx, ctx->stream));
+    PMG_TRY(send_buf.alloc(sidx.size()));
+    PMG_TRY(ghost.alloc((size_t)std::max<int64_t>(1, n_ghost)));
+    PMG_TRY(ghost.zero(ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
   }
 
   int rebuild_sweep()
@@ -203,14 +317,40 @@ struct CsrOp final : LevelOp {
     std::vector<int32_t> cand(c, c + A.n);
     for (int64_t r = 0; r < A.n; ++r)
       if (cand[r] < 0 || cand[r] >= nc) PMG_FAIL(PMG_ERR_ARG, "colour of row %lld out of range", (long long)r);
-    const int64_t bad = host_coloring_violations(A, cand);
+    int64_t bad = 0;
+    if (dist) PMG_TRY(global_violations(cand, bad)); // collective: the colouring must be valid ACROSS ranks (src/mc_sor.c:383-395)
+    else bad = host_coloring_violations(A, cand);
     if (bad) PMG_FAIL(PMG_ERR_COLORING, "not a distance-1 colouring: %lld adjacent same-colour pairs (a parallel sweep would race)", (long long)bad);
     color = std::move(cand);
     ncol  = nc;
     return rebuild_sweep();
   }
+  // A global distance-1 colouring without PETSc's Jones-Plassmann (which is PETSc-internal and unpinned):
+  // greedy on the local graph with K = the largest local colour count, then colour + K (rank mod 2) when every rank's
+  // ghost owners have the other parity (contiguous row blocks of banded matrices), else colour + K rank.
+  int set_coloring_auto_dist(int policy)
+  {
+    if (policy != PMG_COLORING_GREEDY && policy != PMG_COLORING_LEXICOGRAPHIC) PMG_FAIL(PMG_ERR_SUP, "row-partitioned operators: greedy colouring only");
+    std::vector<int32_t> loc;
+    const int            P = ctx->nranks, me = ctx->rank;
+    int64_t              kloc = host_coloring_greedy(Aloc, loc), parity_ok = 1;
+    for (int r = 0; r < P; ++r)
+      if (recv_off[(size_t)r + 1] > recv_off[(size_t)r] && ((r ^ me) & 1) == 0) parity_ok = 0;
+    std::vector<int64_t> mine{kloc, parity_ok}, all((size_t)2 * P);
+    PMG_TRY(comm_allgather_i64(ctx, mine.data(), 2, all.data()));
+    int64_t K = 1;
+    bool    par = true;
+    for (int r = 0; r < P; ++r) {
+      K   = std::max(K, all[(size_t)2 * r]);
+      par = par && all[(size_t)2 * r + 1] != 0;
+    }
+    const int64_t shift = par ? K * (me & 1) : K * me;
+    for (auto &c : loc) c = (int32_t)(c + shift);
+    return set_coloring((int)(par ? 2 * K : K * P), loc.data());
+  }
   int set_coloring_auto(int policy) override
   {
+    if (dist) return set_coloring_auto_dist(policy);
     if (policy == PMG_COLORING_GREEDY) ncol = host_coloring_greedy(A, color);
     else if (policy == PMG_COLORING_LEXICOGRAPHIC) ncol = host_coloring_levelset(A, color);
     else if (policy == PMG_COLORING_PARITY) {
@@ -252,11 +392,12 @@ struct CsrOp final : LevelOp {
 
   int sweep_colour(int c, const SweepCoeffs &co, const double *b, double *y, const NoiseArgs &na)
   {
+    PMG_TRY(halo(y)); // collective: every rank takes part for every colour, also for colours it has no rows of
     const int64_t s0 = color_slice[c], ns = color_slice[c + 1] - s0;
     if (ns == 0) return 0;
     const int  wpb = 8;
     const dim3 grid((unsigned)((ns + wpb - 1) / wpb)), block(wpb * 32);
-    sell_sweep_kernel<<<grid, block, 0, ctx->stream>>>(sw_sell.slice_off.p, sw_sell.col.p, sw_sell.val.p, sw_sell.rows.p, co.idiag.p, co.sqrtdiag.p, b, y, 1.0 - co.omega, na, s0, ns);
+    sell_sweep_kernel<<<grid, block, 0, ctx->stream>>>(sw_sell.slice_off.p, sw_sell.col.p, sw_sell.val.p, sw_sell.rows.p, co.idiag.p, co.sqrtdiag.p, b, y, 1.0 - co.omega, na, s0, ns, nl(), ghost.p);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -272,13 +413,25 @@ struct CsrOp final : LevelOp {
     ctx->dof_updates += A.n;
     return 0;
   }
-  int residual(const double *b, const double *x, double *r) override { return launch_apply(ctx, MODE_RESIDUAL, full, x, b, r); }
-  int mult(const double *x, double *y) override { return launch_apply(ctx, MODE_SPMV, full, x, nullptr, y); }
+  int residual(const double *b, const double *x, double *r) override
+  {
+    PMG_TRY(halo(x));
+    return launch_apply(ctx, MODE_RESIDUAL, full, x, b, r, nl(), ghost.p);
+  }
+  int mult(const double *x, double *y) override
+  {
+    PMG_TRY(halo(x));
+    return launch_apply(ctx, MODE_SPMV, full, x, nullptr, y, nl(), ghost.p);
+  }
   void describe(std::string &out) override
   {
     char buf[256];
     snprintf(buf, sizeof buf, "CSR operator (SELL-32 on device): %lld rows, %lld nonzeros, %d colours", (long long)A.n, (long long)A.nnz(), ncol);
     out = buf;
+    if (dist) {
+      snprintf(buf, sizeof buf, "; rows %lld..%lld of %lld, %lld ghost columns", (long long)row_start, (long long)(row_start + n_local), (long long)n_global, (long long)n_ghost);
+      out += buf;
+    }
   }
 };
 
@@ -302,6 +455,64 @@ int make_csr_op(pmg_ctx ctx, HostCsr &&a, std::unique_ptr<LevelOp> &op)
   auto o = std::make_unique<CsrOp>();
   o->ctx = ctx;
   o->A   = std::move(a);
+  PMG_TRY(o->init());
+  op = std::move(o);
+  return 0;
+}
+
+int make_csr_dist_op(pmg_ctx ctx, int64_t n_global, int64_t row_start, int64_t n_local, const int64_t *rowptr, const int64_t *col_global, const double *val, std::unique_ptr<LevelOp> &op)
+{
+  if (n_local <= 0 || n_global >= INT32_MAX || row_start < 0 || row_start + n_local > n_global || rowptr[0] != 0) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: bad sizes");
+  const int64_t nnz = rowptr[n_local];
+  // distinct off-rank columns, sorted = the column map of the off-diagonal block (src/mc_sor.c:308-310, `colmap`)
+  std::vector<int64_t> gids;
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t c = col_global[k];
+    if (c < 0 || c >= n_global) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: column index %lld out of range", (long long)c);
+    if (c < row_start || c >= row_start + n_local) gids.push_back(c);
+  }
+  std::sort(gids.begin(), gids.end());
+  gids.erase(std::unique(gids.begin(), gids.end()), gids.end());
+  if (n_local + (int64_t)gids.size() >= INT32_MAX) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: too many local + ghost columns");
+  // local numbering: own columns first (ascending), ghost columns after them (ascending global id); per row this is the
+  // reference's accumulation order: diagonal block, then off-diagonal block (src/mc_sor.c:323-334)
+  HostCsr a, aloc;
+  a.n = n_local;
+  a.m = n_local + (int64_t)gids.size();
+  a.rowptr.assign(rowptr, rowptr + n_local + 1);
+  a.col.resize((size_t)nnz);
+  a.val.resize((size_t)nnz);
+  aloc.n = aloc.m = n_local;
+  aloc.rowptr.assign((size_t)n_local + 1, 0);
+  std::vector<std::pair<int32_t, double>> row;
+  for (int64_t r = 0; r < n_local; ++r) {
+    row.clear();
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int64_t c = col_global[k];
+      const int32_t lc = (c >= row_start && c < row_start + n_local) ? (int32_t)(c - row_start) : (int32_t)(n_local + (std::lower_bound(gids.begin(), gids.end(), c) - gids.begin()));
+      row.emplace_back(lc, val[k]);
+    }
+    std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double> &x, const std::pair<int32_t, double> &y) { return x.first < y.first; });
+    for (size_t q = 0; q < row.size(); ++q) {
+      if (q > 0 && row[q].first == row[q - 1].first) PMG_FAIL(PMG_ERR_ARG, "row-partitioned CSR: duplicate column in local row %lld", (long long)r);
+      a.col[(size_t)rowptr[r] + q] = row[q].first;
+      a.val[(size_t)rowptr[r] + q] = row[q].second;
+      if (row[q].first < n_local) {
+        aloc.col.push_back(row[q].first);
+        aloc.val.push_back(row[q].second);
+      }
+    }
+    aloc.rowptr[(size_t)r + 1] = (int64_t)aloc.col.size();
+  }
+  auto o       = std::make_unique<CsrOp>();
+  o->ctx       = ctx;
+  o->dist      = true;
+  o->row_start = row_start;
+  o->n_global  = n_global;
+  o->n_local   = n_local;
+  o->A         = std::move(a);
+  o->Aloc      = std::move(aloc);
+  PMG_TRY(o->init_dist(gids));
   PMG_TRY(o->init());
   op = std::move(o);
   return 0;

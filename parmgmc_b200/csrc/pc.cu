@@ -150,6 +150,17 @@ int pmg_mat_create_csr(pmg_ctx ctx, int64_t n, const int64_t *rowptr, const int3
   return PMG_OK;
 }
 
+int pmg_mat_create_csr_dist(pmg_ctx ctx, int64_t n_global, int64_t row_start, int64_t n_local, const int64_t *rowptr, const int64_t *col_global, const double *val, pmg_mat *out)
+{
+  pmg_stale("pmg_mat_create_csr_dist");
+  if (!ctx || !rowptr || !col_global || !val || !out) PMG_FAIL(PMG_ERR_ARG, "pmg_mat_create_csr_dist: bad arguments");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  auto m = std::make_unique<pmg_mat_s>(ctx);
+  PMG_TRY(make_csr_dist_op(ctx, n_global, row_start, n_local, rowptr, col_global, val, m->op));
+  *out = m.release();
+  return PMG_OK;
+}
+
 int pmg_mat_create_laplace(pmg_ctx ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, int64_t slab_lo, int64_t slab_hi, pmg_mat *out)
 {
   pmg_stale("pmg_mat_create_laplace");
