@@ -126,7 +126,10 @@ int pmg_mcsor_apply_dev(pmg_mcsor mc, const double *b_dev, double *y_dev);
  *   pmg_pc_set_option(pc, "-gamgmc_pc_mg_levels", "10"); pmg_pc_set_option(pc, "-gamgmc_mg_levels_ksp_max_it", "2");
  * plus "-pc_b200_coloring greedy|lexicographic|parity", "-pc_b200_noise philox|injected|none",
  * "-pc_b200_cycle direct|literal" and "-pc_b200_grid nx,ny[,nz]" (grid of an assembled operator, what PCSetDM tells the
- * reference's geometric PCMG). */
+ * reference's geometric PCMG).
+ * type "woodbury" (src/woodbury.c) needs a MATLRC operator (pmg_mat_create_lrc) and the options "-pc_woodbury_sampler
+ * mcgibbs|sorgibbs|gamgmc|cholsampler" and "-pc_woodbury_solver cholesky|<sampler type>"; options of the two inner PCs are
+ * passed with the prefixes "pc_woodbury_sampler_" / "pc_woodbury_solver_" (src/woodbury.c:189-252). */
 typedef int (*pmg_sample_cb)(int64_t it, const double *y_host, int64_t n, void *ctx);
 typedef int (*pmg_ctx_deleter)(void *ctx);
 

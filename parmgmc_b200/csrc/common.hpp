@@ -119,9 +119,11 @@ struct NoiseStream {
   int            mode = PMG_NOISE_PHILOX;
   DevBuf<double> tape;
   int64_t        tape_len = 0, tape_pos = 0;
+  NoiseStream   *parent = nullptr; // a sampler nested in another PC (PCWOODBURY) draws from the outer PC's stream
   // next block of n local rows
   int next(pmg_ctx ctx, int64_t n, int64_t row0, NoiseArgs &na)
   {
+    if (parent) return parent->next(ctx, n, row0, na);
     na.mode = mode;
     na.tape = nullptr;
     na.seed = ctx->seed;
@@ -166,6 +168,8 @@ struct LrcData {
   int build(LevelOp *base, double omega_build);                      // MCSORBuildLRCCorrection, both directions
   int prepare_rhs(const double *b, const NoiseArgs &na_eta, double *out); // out = b + B (sqrt|S| eta)
   int post(int dir, double *y);                                      // y -= Bb_dir (B^T y)
+  int post_with(const double *M, double *y);                         // y -= M (B^T y), M dense n x k
+  int correction_from(const std::vector<double> &C_host, DevBuf<double> &out); // out = C (S^-1 + B^T C)^-1 (src/mc_sor.c:513-535)
   int add_bsbt(const double *x, double sign, double *out);           // out += sign B (S o B^T x)
   int bty(const double *M, const double *y);
 };

@@ -150,33 +150,40 @@ int LrcData::build(LevelOp *base, double omega_build)
   NoiseArgs      none{PMG_NOISE_NONE, nullptr, 0, 0, 0};
   DevBuf<double> C;
   PMG_TRY(C.alloc((size_t)n * k));
-  std::vector<double> Ch((size_t)n * k), bb((size_t)n * k);
+  std::vector<double> Ch((size_t)n * k);
   for (int d = 0; d < 2; ++d) {
     const int dir = d == 0 ? PMG_SOR_FORWARD_SWEEP : PMG_SOR_BACKWARD_SWEEP;
     PMG_TRY(C.zero(ctx->stream));
     for (int j = 0; j < k; ++j) PMG_TRY(base->sweep(dir, co, B.p + (size_t)j * n, C.p + (size_t)j * n, none)); // column j of M^-1 B
     PMG_CUDA(cudaMemcpyAsync(Ch.data(), C.p, Ch.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<double> t((size_t)k * k, 0.0); // S^-1 + B^T C
-    for (int a = 0; a < k; ++a)
-      for (int b2 = 0; b2 < k; ++b2) {
-        const double *ba = Bh.data() + (size_t)a * n, *cb = Ch.data() + (size_t)b2 * n;
-        double        s = 0.0;
-        for (int64_t i = 0; i < n; ++i) s += ba[i] * cb[i];
-        t[(size_t)a * k + b2] = s + (a == b2 ? 1.0 / Sh[(size_t)a] : 0.0);
-      }
-    if (!host_invert(k, t)) PMG_FAIL(PMG_ERR_NOT_SPD, "low-rank correction: S^-1 + B^T M^-1 B is singular");
-    for (int j = 0; j < k; ++j) // Bb = C Sb
-      for (int64_t i = 0; i < n; ++i) {
-        double s = 0.0;
-        for (int q = 0; q < k; ++q) s += Ch[(size_t)q * n + i] * t[(size_t)q * k + j];
-        bb[(size_t)j * n + i] = s;
-      }
-    PMG_TRY((d == 0 ? Bb_f : Bb_b).upload(bb, ctx->stream));
-    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    PMG_TRY(correction_from(Ch, d == 0 ? Bb_f : Bb_b));
   }
   built       = true;
   omega_built = omega_build;
+  return 0;
+}
+
+// out = C (S^-1 + B^T C)^-1 for a host copy of C = M^-1 B (n x k, column-major)
+int LrcData::correction_from(const std::vector<double> &Ch, DevBuf<double> &out)
+{
+  std::vector<double> t((size_t)k * k, 0.0), bb((size_t)n * k); // t = S^-1 + B^T C
+  for (int a = 0; a < k; ++a)
+    for (int b2 = 0; b2 < k; ++b2) {
+      const double *ba = Bh.data() + (size_t)a * n, *cb = Ch.data() + (size_t)b2 * n;
+      double        s = 0.0;
+      for (int64_t i = 0; i < n; ++i) s += ba[i] * cb[i];
+      t[(size_t)a * k + b2] = s + (a == b2 ? 1.0 / Sh[(size_t)a] : 0.0);
+    }
+  if (!host_invert(k, t)) PMG_FAIL(PMG_ERR_NOT_SPD, "low-rank correction: S^-1 + B^T M^-1 B is singular");
+  for (int j = 0; j < k; ++j)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int q = 0; q < k; ++q) s += Ch[(size_t)q * n + i] * t[(size_t)q * k + j];
+      bb[(size_t)j * n + i] = s;
+    }
+  PMG_TRY(out.upload(bb, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -197,10 +204,11 @@ int LrcData::prepare_rhs(const double *b, const NoiseArgs &na_eta, double *out)
 }
 
 // MCSORPostSOR_LRC: y -= Bb_dir (B^T y)
-int LrcData::post(int dir, double *y)
+int LrcData::post(int dir, double *y) { return post_with(dir == PMG_SOR_BACKWARD_SWEEP ? Bb_b.p : Bb_f.p, y); }
+int LrcData::post_with(const double *M, double *y)
 {
   PMG_TRY(bty(B.p, y));
-  lrc_rank_update_kernel<<<(unsigned)((n + LRC_THREADS - 1) / LRC_THREADS), LRC_THREADS, 0, ctx->stream>>>(n, k, dir == PMG_SOR_BACKWARD_SWEEP ? Bb_b.p : Bb_f.p, partial.p, nchunks, nullptr, -1.0, y);
+  lrc_rank_update_kernel<<<(unsigned)((n + LRC_THREADS - 1) / LRC_THREADS), LRC_THREADS, 0, ctx->stream>>>(n, k, M, partial.p, nchunks, nullptr, -1.0, y);
   PMG_CUDA(cudaGetLastError());
   ctx->launches++;
   return 0;

@@ -356,6 +356,9 @@ struct pmg_pc_s {
   DevBuf<double>       w, work;
   bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
   int                  tail_top     = -1;   // levels 0 .. tail_top of the direct cycle run in one launch (mg_tail); -1: none
+  // PCWOODBURY (src/woodbury.c): a sampler on the base matrix A of a MATLRC operator + the correction G
+  pmg_pc               wb_sampler = nullptr;
+  DevBuf<double>       wb_G;
   DevBuf<double>       scratch;             // out-of-place partner of the iterate for the fused sweeps (pitched)
   DevBuf<double>       pit_y, pit_b;        // pitched copies of the caller's y and b (LevelOp::fused_size)
   // staging
@@ -368,6 +371,8 @@ struct pmg_pc_s {
   explicit pmg_pc_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
   ~pmg_pc_s()
   {
+    delete wb_sampler;
+    wb_G.release();
     if (deleter) deleter(cbctx);
     if (h_pinned) cudaFreeHost(h_pinned);
     if (ev0) cudaEventDestroy(ev0);
@@ -390,6 +395,14 @@ static bool opt_true(const std::string &v) { return v.empty() || v == "1" || v =
 
 // PCSetFromOptions_MulticolorGibbs (src/pc_mcgibbs.c:190-211) / _SORGibbs (src/pc_sorgibbs.c:264-278) for the
 // sampler configured under `prefix` ("" for a stand-alone PC, "gamgmc_mg_levels_" / "gamgmc_mg_coarse_" inside MG)
+// the mode of the stream a PC really draws from (a sampler nested in PCWOODBURY draws from the outer PC's stream)
+static int noise_mode(pmg_pc pc)
+{
+  const NoiseStream *ns = &pc->noise;
+  while (ns->parent) ns = ns->parent;
+  return ns->mode;
+}
+
 static int configure_sampler(pmg_pc pc, const std::string &prefix, const std::string &pctype, LevelSampler &s)
 {
   if (pctype == "mcgibbs") {
@@ -513,7 +526,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   // stencil-array levels: each directional sweep is one out-of-place pass (box_stream.cuh); the level's iterate
   // ping-pongs between v.x and v.x2, so the current one is always v.x.p
   const bool bstream = !fused && l > 0 && v.smp.kind != KIND_CHOL && v.x2.p && x == v.x.p && v.op->stream_ok() &&
-                       (pc->noise.mode != PMG_NOISE_INJECTED || v.op->fused_tape_ok());
+                       (noise_mode(pc) != PMG_NOISE_INJECTED || v.op->fused_tape_ok());
   if (bstream) {
     MgLevel         &c = pc->lv[l - 1];
     std::vector<int> dirs;
@@ -607,7 +620,7 @@ static int mg_tail(pmg_pc pc, int lt)
       PMG_TRY(pc->noise.next(ctx, pc->lv[l].op->n(), 0, na));
       ns.push_back(TailNoise{na.call, na.tape});
     }
-  return grid_tail_cycle(ctx, lt + 1, lv.data(), pc->lv[0].smp.chol, pc->noise.mode, ctx->seed, ns.data(), (int)ns.size());
+  return grid_tail_cycle(ctx, lt + 1, lv.data(), pc->lv[0].smp.chol, noise_mode(pc), ctx->seed, ns.data(), (int)ns.size());
 }
 
 static int gamgmc_setup(pmg_pc pc)
@@ -800,13 +813,43 @@ static int pc_notify(pmg_pc pc, int64_t it, const double *y_dev)
   return 0;
 }
 
+static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero);
+
 static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero)
 {
   pmg_ctx ctx = pc->ctx;
   if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
-  const int64_t n  = pc->mat->op->n();
   const int64_t l0 = ctx->launches, u0 = ctx->dof_updates;
   PMG_CUDA(cudaEventRecord(pc->ev0, ctx->stream));
+  PMG_TRY(richardson_body(pc, b, y, its, guesszero));
+  PMG_CUDA(cudaEventRecord(pc->ev1, ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  PMG_CUDA(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+  pc->last_ms       = ms;
+  pc->last_launches = ctx->launches - l0;
+  pc->last_updates  = ctx->dof_updates - u0;
+  return 0;
+}
+
+// the samples themselves, asynchronous on the context's stream
+static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, int guesszero)
+{
+  pmg_ctx ctx = pc->ctx;
+  if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
+  const int64_t n = pc->mat->op->n();
+  if (pc->type == "woodbury") { // PCApplyRichardson_Woodbury, src/woodbury.c:259-286
+    LrcData *lrc = pc->mat->op->lrc_data();
+    NoiseArgs na_eta;
+    for (int64_t it = 0; it < its; ++it) {
+      PMG_TRY(pc->noise.next(ctx, lrc->k, 0, na_eta));              // wk ~ N(0, I_k), scaled by sqrt|S|
+      PMG_TRY(lrc->prepare_rhs(b, na_eta, lrc->rhs.p));             // w = b + B wk
+      PMG_TRY(richardson_body(pc->wb_sampler, lrc->rhs.p, y, 1, 0)); // one sample of the inner sampler on A
+      PMG_TRY(lrc->post_with(pc->wb_G.p, y));                       // y -= G (B^T y)
+      PMG_TRY(pc_notify(pc, it, y));
+    }
+    return 0;
+  }
   if (pc->type == "gamgmc") { // src/pc_gamgmc.c:242-259
     LevelOp *A = pc->lv[pc->nlevels - 1].op;
     if (!b) {
@@ -854,7 +897,7 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
   } else { // mcgibbs: src/pc_mcgibbs.c:167-184; sorgibbs: src/pc_sorgibbs.c:125-129 (running sample_index from 0)
     if (pc->type == "sorgibbs") pc->sample_index = 0;
     LevelOp *op = pc->smp.gibbs.op;
-    if (op->fused_ok() && pc->scratch.p && (pc->noise.mode != PMG_NOISE_INJECTED || op->fused_tape_ok())) { // one fused pass per directional sweep, ping-pong between y and scratch
+    if (op->fused_ok() && pc->scratch.p && (noise_mode(pc) != PMG_NOISE_INJECTED || op->fused_tape_ok())) { // one fused pass per directional sweep, ping-pong between y and scratch
       std::vector<int> dirs;
       LevelSampler     one;
       one.its        = 1;
@@ -885,14 +928,51 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
       }
     }
   }
-  PMG_CUDA(cudaEventRecord(pc->ev1, ctx->stream));
-  PMG_CUDA(cudaStreamSynchronize(ctx->stream));
-  float ms = 0;
-  PMG_CUDA(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
-  pc->last_ms       = ms;
-  pc->last_launches = ctx->launches - l0;
-  pc->last_updates  = ctx->dof_updates - u0;
   return 0;
+}
+
+// PCSetUp_Woodbury + PCWoodburyBuildLRCCorrection (src/woodbury.c:21-86, :141-186): the operator must be a MATLRC; sampler and
+// solver are PCs of this library on its base matrix A.  `-pc_woodbury_solver cholesky` is the exact dense solve (the
+// cholsampler without noise); any sampler type can also serve as solver: its deterministic application from a zero guess
+// (one V-cycle for gamgmc, one sweep for mcgibbs / sorgibbs).
+static int woodbury_setup(pmg_pc pc)
+{
+  pmg_ctx  ctx = pc->ctx;
+  LrcData *lrc = pc->mat->op->lrc_data();
+  if (!lrc || !pc->mat->base) PMG_FAIL(PMG_ERR_SUP, "PCWoodbury only supports matrices of type LRC"); // src/woodbury.c:161
+  if (!pc->has("pc_woodbury_sampler") || !pc->has("pc_woodbury_solver")) PMG_FAIL(PMG_ERR_SUP, "Must provide sampler and solver"); // :149
+  auto make_inner = [&](const std::string &which, pmg_pc *out) -> int {
+    std::string type = pc->get("pc_woodbury_" + which, "");
+    if (type == "cholesky" || type == "lu") type = "cholsampler";
+    PMG_TRY(pmg_pc_create(ctx, type.c_str(), out));
+    (*out)->mat = pc->mat->base;
+    const std::string prefix = "pc_woodbury_" + which + "_";
+    for (const auto &kv : pc->opts)
+      if (kv.first.compare(0, prefix.size(), prefix) == 0) (*out)->opts[kv.first.substr(prefix.size())] = kv.second;
+    return 0;
+  };
+  if (pc->wb_sampler) pmg_pc_destroy(pc->wb_sampler);
+  pc->wb_sampler = nullptr;
+  PMG_TRY(make_inner("sampler", &pc->wb_sampler));
+  pc->wb_sampler->noise.parent = &pc->noise;
+  PMG_TRY(pmg_pc_setup(pc->wb_sampler));
+  pmg_pc solver = nullptr;
+  PMG_TRY(make_inner("solver", &solver));
+  solver->noise.mode = PMG_NOISE_NONE;
+  solver->opts.erase("pc_b200_noise");
+  int err = pmg_pc_setup(solver);
+  // C = solver(B), column by column from a zero guess (PCApply, src/woodbury.c:40-52)
+  const int64_t       n = lrc->n;
+  DevBuf<double>      C;
+  std::vector<double> Ch((size_t)n * lrc->k);
+  if (!err) err = C.alloc((size_t)n * lrc->k);
+  if (!err) err = C.zero(ctx->stream);
+  for (int j = 0; j < lrc->k && !err; ++j) err = richardson_body(solver, lrc->B.p + (size_t)j * n, C.p + (size_t)j * n, 1, 1);
+  if (!err && cudaMemcpyAsync(Ch.data(), C.p, Ch.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) err = PMG_ERR_CUDA;
+  if (!err && cudaStreamSynchronize(ctx->stream) != cudaSuccess) err = PMG_ERR_CUDA;
+  pmg_pc_destroy(solver); // the reference drops the solver after set-up too (src/woodbury.c:184)
+  if (err) return err;
+  return lrc->correction_from(Ch, pc->wb_G);
 }
 
 extern "C" {
@@ -977,7 +1057,7 @@ int pmg_pc_create(pmg_ctx ctx, const char *type, pmg_pc *out)
   pmg_stale("pmg_pc_create");
   if (!ctx || !type) PMG_FAIL(PMG_ERR_ARG, "pmg_pc_create: bad arguments");
   const std::string t = type;
-  if (t != "mcgibbs" && t != "sorgibbs" && t != "gamgmc" && t != "cholsampler") PMG_FAIL(PMG_ERR_SUP, "PC type '%s' is not provided by parmgmc_b200 (mcgibbs | sorgibbs | gamgmc | cholsampler)", type);
+  if (t != "mcgibbs" && t != "sorgibbs" && t != "gamgmc" && t != "cholsampler" && t != "woodbury") PMG_FAIL(PMG_ERR_SUP, "PC type '%s' is not provided by parmgmc_b200 (mcgibbs | sorgibbs | gamgmc | cholsampler | woodbury)", type);
   auto pc  = std::make_unique<pmg_pc_s>(ctx);
   pc->type = t;
   *out     = pc.release();
@@ -1041,7 +1121,8 @@ int pmg_pc_setup(pmg_pc pc)
   else if (nm == "injected") pc->noise.mode = PMG_NOISE_INJECTED;
   else if (nm == "none") pc->noise.mode = PMG_NOISE_NONE;
   else if (!nm.empty()) PMG_FAIL(PMG_ERR_ARG, "-pc_b200_noise %s: expected philox | injected | none", nm.c_str());
-  if (pc->type == "gamgmc") PMG_TRY(gamgmc_setup(pc));
+  if (pc->type == "woodbury") PMG_TRY(woodbury_setup(pc));
+  else if (pc->type == "gamgmc") PMG_TRY(gamgmc_setup(pc));
   else {
     const double omega_keep = pc->smp.gibbs.omega;
     const int    type_keep  = pc->smp.gibbs.type;
@@ -1269,7 +1350,10 @@ int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles)
   pmg_stale("pmg_pc_noise_per_sample");
   if (!pc->is_setup) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_setup has not been called");
   int64_t d = 0;
-  if (pc->type == "gamgmc") {
+  if (pc->type == "woodbury") {
+    PMG_TRY(pmg_pc_noise_per_sample(pc->wb_sampler, &d));
+    d += pc->mat->op->lrc_data()->k;
+  } else if (pc->type == "gamgmc") {
     for (int l = 0; l < pc->nlevels; ++l) d += (l == 0 ? 1 : 2) * sampler_draws(pc->lv[l].smp);
   } else if (pc->type == "cholsampler") d = pc->smp.chol.n;
   else d = pc->smp.gibbs.draws_per_sample();

@@ -859,3 +859,68 @@ def test_device_rng_covariance_and_iact_match_reference_rng_chain(pmg, ctx, orc,
     bound = 6.0 * np.sqrt(max(tau_ref, 1.0) / N) * np.sqrt(n) / 3.0
     assert e_dev < bound and e_ref < bound, (e_dev, e_ref, bound)
     assert e_dev < 3.0 * e_ref + 0.02 and e_ref < 3.0 * e_dev + 0.02, (e_dev, e_ref)
+
+
+# ---- PCWOODBURY (src/woodbury.c): a sampler on A + the Woodbury correction of a MATLRC operator -----------------------------
+@pytest.mark.parametrize("sampler,sopts", [("mcgibbs", {"-pc_woodbury_sampler_pc_mcgibbs_omega": 1.2, "-pc_woodbury_sampler_pc_mcgibbs_symmetric": ""}), ("sorgibbs", {})])
+def test_woodbury_matches_numpy_restatement(pmg, ctx, orc, sampler, sopts):
+    """PCApplyRichardson_Woodbury (src/woodbury.c:259-286) with G = C (S^-1 + B^T C)^-1, C = solver(B) (:21-86), exact solver."""
+    rng = np.random.default_rng(SEED)
+    dims = (21, 17)
+    A = orc.laplace(2, *dims, kappa=1.5)
+    n, k = A.n, 4
+    B, S = _obs_matrix(rng, n, k), rng.uniform(50.0, 200.0, k)
+    col = orc.Coloring.parity(dims)
+    mat = pmg.Mat.lrc(make_mat(pmg, ctx, A, col), B, S)
+    pc = pmg.PC(ctx, "woodbury")
+    pc.set_operator(mat)
+    pc.set_options(dict(sopts, **{"-pc_woodbury_sampler": sampler, "-pc_woodbury_solver": "cholesky"}))
+    pc.setup()
+    its = 3
+    per = pc.noise_per_sample()
+    sym = sampler == "mcgibbs"
+    assert per == k + n * (2 if sym else 1)
+    z = rng.standard_normal(its * per)
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(n), rng.standard_normal(n)
+    Ad = A.to_scipy().toarray()
+    Cm = np.linalg.solve(Ad, B)
+    G = Cm @ np.linalg.inv(np.diag(1.0 / S) + B.T @ Cm)
+    noise = orc.Noise.tape(z)
+    ref = y.copy()
+    for _ in range(its):
+        w = b + B @ (np.sqrt(np.abs(S)) * orc.noise_fill(noise, k))  # the k draws come first (src/woodbury.c:273)
+        ref = orc.gibbs_richardson(A, w, ref, 1, noise, col, 1.2 if sym else 1.0, orc.SOR_SYMMETRIC if sym else orc.SOR_FORWARD)
+        ref = ref - G @ (B.T @ ref)
+    pc.apply_richardson(b, y, its=its)
+    assert relerr(y, ref) < 1e-10
+
+
+def test_woodbury_exact_sampler_gives_the_posterior(pmg, ctx, orc):
+    """examples/ex13.py: -pc_woodbury_sampler cholsampler -pc_woodbury_solver cholesky draws EXACT, independent samples of
+    N((A + B S B^T)^-1 b, (A + B S B^T)^-1): mean and covariance estimators at the Monte Carlo level, IACT = 1."""
+    rng = np.random.default_rng(SEED)
+    dims = (9, 9)
+    A = orc.laplace(2, *dims, kappa=2.0)
+    n, k, N = A.n, 5, 20000
+    B, S = _obs_matrix(rng, n, k), np.full(k, 30.0)
+    b = rng.standard_normal(n)
+    mat = pmg.Mat.lrc(pmg.Mat.from_csr(ctx, A.rowptr, A.col, A.val), B, S)
+    pc = pmg.PC(ctx, "woodbury")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_woodbury_sampler": "cholsampler", "-pc_woodbury_solver": "cholesky", "-pc_b200_noise": "philox"})
+    pc.setup()
+    ctx.set_seed(0xCAFE)
+    out = np.empty((N, n))
+
+    def cb(it, ys):
+        out[it] = ys
+
+    pc.set_sample_callback(cb)
+    pc.apply_richardson(b, np.zeros(n), its=N)
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    mean = np.linalg.solve(P, b)
+    assert np.linalg.norm(out.mean(0) - mean) < 4.0 * np.sqrt(np.trace(np.linalg.inv(P)) / N)
+    assert orc.cov_errors(P, (out - mean)[None])[0] < 6.0 * np.sqrt(n / N) / 3.0
+    tau, ok = orc.iact(out[:, n // 2])
+    assert ok and abs(tau - 1.0) < 0.15
