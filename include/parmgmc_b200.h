@@ -168,6 +168,17 @@ int pmg_pc_set_noise_tape(pmg_pc pc, const double *z_host, int64_t len);
 int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles);
 /* fill z_host[0..n) with the device generator's N(0,1) draw for (seed, call, global rows row0..row0+n):
  * VecSetRandomStandardNormal (src/parmgmc.c:70-116) on the device */
+/* ---- statistics kept on the device -------------------------------------------------------------
+ * pmg_pc_set_qoi: what examples/benchmark/main.cc:151-175 (SaveSample) does in a host callback -- qoi[it] = <y, meas> after
+ * every sample, optionally Welford's running mean / variance of the whole field -- as one kernel per sample, so that no
+ * sample has to travel to the host.  meas_host = NULL switches it off.  pmg_iact / pmg_autocorrelation: IACT / Autocorrelation
+ * of src/iact.c:17-92 (include/parmgmc/iact.h:14-15) with cuFFT in place of FFTW. */
+int pmg_pc_set_qoi(pmg_pc pc, const double *meas_host, int64_t capacity, int est_mean_and_var);
+int pmg_pc_get_qoi(pmg_pc pc, double *qois_host, int64_t *count, int reset);
+int pmg_pc_get_mean_var(pmg_pc pc, double *mean_host, double *var_host, int64_t *nseen);
+int pmg_autocorrelation(pmg_ctx ctx, int64_t n, const double *x_host, double *acf_host);
+int pmg_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, double *acf_host_or_null, int *valid);
+
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z_host);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------- */

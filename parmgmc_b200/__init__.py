@@ -64,6 +64,11 @@ SIGNATURES = {
     "pmg_mat_create_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
+    "pmg_pc_set_qoi": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int]),
+    "pmg_pc_get_qoi": (C.c_int, [_vp, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "pmg_pc_get_mean_var": (C.c_int, [_vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "pmg_autocorrelation": (C.c_int, [_vp, C.c_int64, _f64p, _f64p]),
+    "pmg_iact": (C.c_int, [_vp, C.c_int64, _f64p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int)]),
     "pmg_mat_create_csr_dist": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_destroy": (C.c_int, [_vp]),
     "pmg_mat_get_size": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -228,6 +233,22 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib().pmg_comm_unique_id(buf))
     return buf.raw
+
+
+def autocorrelation(ctx: "Context", x):
+    """Autocorrelation (src/iact.c:17-46) on the device (cuFFT)."""
+    x = _f64(x)
+    acf = np.empty(x.size, np.float64)
+    _check(lib().pmg_autocorrelation(ctx._h, x.size, x, acf))
+    return acf
+
+
+def iact(ctx: "Context", x):
+    """IACT (src/iact.c:48-92): returns (tau, valid)."""
+    x = _f64(x)
+    tau, valid = C.c_double(), C.c_int()
+    _check(lib().pmg_iact(ctx._h, x.size, x, C.byref(tau), None, C.byref(valid)))
+    return tau.value, bool(valid.value)
 
 
 class Mat:
@@ -406,6 +427,28 @@ class PC:
         y = np.empty(self.mat.n, np.float64)
         _check(lib().pmg_pc_apply(self._h, _f64(x), y))
         return y
+
+    # ---- device-side SaveSample of examples/benchmark/main.cc:151-175 ----
+    def set_qoi(self, meas, capacity, est_mean_and_var=False):
+        """qoi[it] = <y, meas> after every sample (and Welford's mean / variance of the field), kept on the device."""
+        if meas is None:
+            _check(lib().pmg_pc_set_qoi(self._h, None, 0, 0))
+            return
+        m = _f64(meas)
+        _check(lib().pmg_pc_set_qoi(self._h, m.ctypes.data, int(capacity), int(bool(est_mean_and_var))))
+
+    def get_qoi(self, reset=False):
+        cnt = C.c_int64()
+        _check(lib().pmg_pc_get_qoi(self._h, None, C.byref(cnt), 0))
+        out = np.empty(cnt.value, np.float64)
+        _check(lib().pmg_pc_get_qoi(self._h, out.ctypes.data, C.byref(cnt), int(bool(reset))))
+        return out
+
+    def get_mean_var(self):
+        n, seen = self.mat.n, C.c_int64()
+        mean, var = np.empty(n, np.float64), np.empty(n, np.float64)
+        _check(lib().pmg_pc_get_mean_var(self._h, mean.ctypes.data, var.ctypes.data, C.byref(seen)))
+        return mean, var, seen.value
 
     def set_sample_callback(self, cb, deleter=None):
         """PCSetSampleCallback(pc, cb, ctx, deleter): cb(it, y) with y a read-only numpy view."""

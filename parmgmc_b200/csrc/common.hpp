@@ -223,6 +223,19 @@ struct LevelOp {
   }
 };
 
+// per-sample statistics kept on the device (estimators.cu; examples/benchmark/main.cc:151-175, src/iact.c)
+struct QoiState {
+  pmg_ctx        ctx = nullptr;
+  bool           on = false, welford = false;
+  int64_t        n = 0, cap = 0, count = 0, nseen = 0;
+  int            nchunks = 0;
+  DevBuf<double> meas, trace, partial, mean, M2;
+  int init(pmg_ctx ctx, int64_t n, const double *meas_host, int64_t capacity, bool with_mean_var);
+  int accumulate(const double *y_dev);
+};
+int device_autocorrelation(pmg_ctx ctx, int64_t n, const double *x_host, double *acf_host);
+int device_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, double *acf_or_null, int *valid);
+
 // grid transfer between level l (fine) and l-1 (coarse): SURVEY Appendix A.3
 struct Transfer {
   virtual ~Transfer() {}

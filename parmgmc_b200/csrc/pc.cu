@@ -359,6 +359,7 @@ struct pmg_pc_s {
   // PCWOODBURY (src/woodbury.c): a sampler on the base matrix A of a MATLRC operator + the correction G
   pmg_pc               wb_sampler = nullptr;
   DevBuf<double>       wb_G;
+  QoiState             qoi; // device-side SaveSample (examples/benchmark/main.cc:151-175)
   DevBuf<double>       scratch;             // out-of-place partner of the iterate for the fused sweeps (pitched)
   DevBuf<double>       pit_y, pit_b;        // pitched copies of the caller's y and b (LevelOp::fused_size)
   // staging
@@ -805,6 +806,7 @@ static int pc_alloc_staging(pmg_pc pc)
 
 static int pc_notify(pmg_pc pc, int64_t it, const double *y_dev)
 {
+  PMG_TRY(pc->qoi.accumulate(y_dev));
   if (!pc->cb) return 0;
   const int64_t n = pc->mat->op->n();
   PMG_CUDA(cudaMemcpyAsync(pc->h_pinned, y_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, pc->ctx->stream));
@@ -864,7 +866,7 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
     for (int64_t it = 0; it < its; ++it) {
       if (top_fused) {
         PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, pc->pit_b.p, pc->pit_y.p, it == 0 && guesszero));
-        if (pc->cb || it + 1 == its) PMG_TRY(A->from_pitched(pc->pit_y.p, y));
+        if (pc->cb || pc->qoi.on || it + 1 == its) PMG_TRY(A->from_pitched(pc->pit_y.p, y));
       } else if (pc->direct_cycle) {
         PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, b, y, it == 0 && guesszero));
       } else if (it == 0 && guesszero) {
@@ -918,7 +920,7 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
           PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, pb, cur, oth, na, nullptr, nullptr, nullptr));
           std::swap(cur, oth);
         }
-        if (pc->cb || it + 1 == its) PMG_TRY(op->from_pitched(cur, y));
+        if (pc->cb || pc->qoi.on || it + 1 == its) PMG_TRY(op->from_pitched(cur, y));
         PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
       }
     } else {
@@ -1359,6 +1361,57 @@ int pmg_pc_noise_per_sample(pmg_pc pc, int64_t *doubles)
   else d = pc->smp.gibbs.draws_per_sample();
   *doubles = d;
   return PMG_OK;
+}
+
+// ---- statistics on the device (examples/benchmark/main.cc:151-175, src/iact.c) ----
+int pmg_pc_set_qoi(pmg_pc pc, const double *meas_host, int64_t capacity, int est_mean_and_var)
+{
+  pmg_stale("pmg_pc_set_qoi");
+  if (!pc->mat) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_set_qoi: no operator set");
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  if (!meas_host) { // switch off
+    pc->qoi.on = false;
+    return PMG_OK;
+  }
+  if (capacity < 1) PMG_FAIL(PMG_ERR_ARG, "pmg_pc_set_qoi: capacity must be positive");
+  return pc->qoi.init(pc->ctx, pc->mat->op->n(), meas_host, capacity, est_mean_and_var != 0);
+}
+int pmg_pc_get_qoi(pmg_pc pc, double *qois_host, int64_t *count, int reset)
+{
+  pmg_stale("pmg_pc_get_qoi");
+  if (!pc->qoi.on) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_get_qoi: no QOI registered");
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  if (qois_host && pc->qoi.count) PMG_CUDA(cudaMemcpyAsync(qois_host, pc->qoi.trace.p, sizeof(double) * (size_t)pc->qoi.count, cudaMemcpyDeviceToHost, pc->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream));
+  if (count) *count = pc->qoi.count;
+  if (reset) pc->qoi.count = 0;
+  return PMG_OK;
+}
+int pmg_pc_get_mean_var(pmg_pc pc, double *mean_host, double *var_host, int64_t *nseen)
+{
+  pmg_stale("pmg_pc_get_mean_var");
+  if (!pc->qoi.on || !pc->qoi.welford) PMG_FAIL(PMG_ERR_ORDER, "pmg_pc_get_mean_var: register the QOI with est_mean_and_var");
+  PMG_CUDA(cudaSetDevice(pc->ctx->device));
+  const size_t n = (size_t)pc->qoi.n;
+  if (mean_host) PMG_CUDA(cudaMemcpyAsync(mean_host, pc->qoi.mean.p, sizeof(double) * n, cudaMemcpyDeviceToHost, pc->ctx->stream));
+  if (var_host) PMG_CUDA(cudaMemcpyAsync(var_host, pc->qoi.M2.p, sizeof(double) * n, cudaMemcpyDeviceToHost, pc->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream));
+  if (var_host && pc->qoi.nseen > 1)
+    for (size_t i = 0; i < n; ++i) var_host[i] /= (double)(pc->qoi.nseen - 1); // sample variance from Welford's M2
+  if (nseen) *nseen = pc->qoi.nseen;
+  return PMG_OK;
+}
+int pmg_autocorrelation(pmg_ctx ctx, int64_t n, const double *x_host, double *acf_host)
+{
+  pmg_stale("pmg_autocorrelation");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  return device_autocorrelation(ctx, n, x_host, acf_host);
+}
+int pmg_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, double *acf_host_or_null, int *valid)
+{
+  pmg_stale("pmg_iact");
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  return device_iact(ctx, n, x_host, tau, acf_host_or_null, valid);
 }
 
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z)

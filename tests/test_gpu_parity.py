@@ -924,3 +924,48 @@ def test_woodbury_exact_sampler_gives_the_posterior(pmg, ctx, orc):
     assert orc.cov_errors(P, (out - mean)[None])[0] < 6.0 * np.sqrt(n / N) / 3.0
     tau, ok = orc.iact(out[:, n // 2])
     assert ok and abs(tau - 1.0) < 0.15
+
+
+# ---- statistics on the device (examples/benchmark/main.cc:151-175, src/iact.c) ---------------------------------------------
+def test_device_qoi_trace_welford_and_iact(pmg, ctx, orc):
+    rng = np.random.default_rng(SEED)
+    dims, N = (33, 21), 300
+    lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=0.5)
+    n = lap.n
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(lap)
+    pc.set_options({"-pc_mcgibbs_symmetric": "", "-pc_b200_noise": "philox"})
+    pc.setup()
+    meas = rng.standard_normal(n)
+    pc.set_qoi(meas, N, True)
+    got = np.empty((N, n))
+
+    def cb(it, ys):
+        got[it] = ys
+
+    pc.set_sample_callback(cb)
+    ctx.set_seed(3)
+    b, y = rng.standard_normal(n), np.zeros(n)
+    pc.apply_richardson(b, y, its=N)
+    q = pc.get_qoi()
+    assert q.size == N and np.abs(q - got @ meas).max() < 1e-11 * np.abs(got @ meas).max()
+    mean, var, seen = pc.get_mean_var()
+    assert seen == N
+    assert np.abs(mean - got.mean(0)).max() < 1e-12 and np.abs(var - got.var(0, ddof=1)).max() < 1e-11
+    with pytest.raises(pmg.PMGError):
+        pc.apply_richardson(b, y, its=1)  # the trace is full
+    assert pc.get_qoi(reset=True).size == N and pc.get_qoi().size == 0
+    # Autocorrelation / IACT of src/iact.c on cuFFT against the oracle's restatement
+    rho, m = 0.9, 60000
+    x = np.empty(m)
+    x[0] = 0.0
+    e = rng.standard_normal(m)
+    for i in range(1, m):
+        x[i] = rho * x[i - 1] + e[i]
+    acf = pmg.autocorrelation(ctx, x[:5000])
+    np.testing.assert_allclose(acf, orc.autocorrelation(x[:5000]), atol=1e-10)
+    tau, valid = pmg.iact(ctx, x)
+    tau_o, valid_o = orc.iact(x)
+    assert valid == valid_o and abs(tau - tau_o) < 1e-8 and abs(tau - (1 + rho) / (1 - rho)) < 2.5
+    with pytest.raises(pmg.PMGError):
+        pmg.iact(ctx, np.zeros(1))
