@@ -849,24 +849,47 @@ struct LapOp final : GridOp {
   // ---- 3D: stream3d.cuh ----
   DevBuf<sweep3d::Item> items3;
   int                   nitems3 = 0, items3_bz = 0, items3_nw = 0;
-  int build_items3(int bz, int NW3) // NW3 warps (grid rows) per CTA tile: NW3 - 2 output rows + 2 halo rows
+  int build_items3(int bz, int NW3) // NW3 warps per CTA tile: NW3 - 2 output rows + 2 halo rows (narrow strips: 2 NW3 - 2 + 2)
   {
     using sweep3d::Item;
-    const int         nstrips = (int)((g.n0 + sweep3d::STRIP_OUT - 1) / sweep3d::STRIP_OUT), ty = NW3 - 2;
-    std::vector<Item> slow, fast;
-    for (int64_t k = g.slo; k < g.shi;) {
-      const int64_t kb_full = std::min<int64_t>(k + bz, g.shi);
-      const bool    kin = k - 1 >= 1 && kb_full <= g.n2 - 2 && k - 2 >= g.slo && kb_full + 1 < g.shi; // sweep3d_kernel's test
-      const int64_t kb = kin ? kb_full : std::min<int64_t>(k + std::max(1, bz * 3 / 4), g.shi); // edge tiles: shorter bands
-      for (int64_t ya = 0; ya < g.n1; ya += ty)
-        for (int s = 0; s < nstrips; ++s) {
+    const int         nstrips = (int)((g.n0 + sweep3d::STRIP_OUT - 1) / sweep3d::STRIP_OUT), ty = NW3 - 2, ty16 = 2 * NW3 - 2;
+    const int64_t     last_w  = g.n0 - (int64_t)(nstrips - 1) * sweep3d::STRIP_OUT; // columns of the last strip
+    static const bool narrow_env = std::getenv("PMG_SW3_NONARROW") == nullptr;
+    static const int  thin_env   = std::getenv("PMG_SW3_THIN") ? std::atoi(std::getenv("PMG_SW3_THIN")) : 4;
+    const bool        narrow = narrow_env && last_w <= 56 && g.n1 >= ty16; // 14 output lanes of 4 columns
+    // bands along z: thin bands where a plane lacks a z neighbour (the table-driven tiles), equal bands of at most bz planes between
+    std::vector<std::pair<int64_t, int64_t>> bands;
+    {
+      const int64_t thin = std::max(2, thin_env);
+      int64_t       lo = g.slo, hi = g.shi;
+      const bool    edge_lo = g.slo < 2, edge_hi = g.shi > g.n2 - 2; // the slab holds the first / last planes of the grid
+      if (g.shi - g.slo <= 2 * thin + 2) {
+        for (int64_t k = lo; k < hi; k += bz) bands.push_back({k, std::min<int64_t>(k + bz, hi)});
+      } else {
+        if (edge_lo) { bands.push_back({lo, lo + thin}); lo += thin; }
+        if (edge_hi) hi -= thin;
+        const int64_t nb = (hi - lo + bz - 1) / bz;
+        for (int64_t i = 0; i < nb; ++i) bands.push_back({lo + (hi - lo) * i / nb, lo + (hi - lo) * (i + 1) / nb});
+        if (edge_hi) bands.push_back({hi, g.shi});
+      }
+    }
+    std::vector<Item> slow, fast, small;
+    for (const auto &bd : bands) {
+      const int64_t k = bd.first, kb = bd.second;
+      const bool    kin = k - 1 >= 1 && kb <= g.n2 - 2; // sweep3d_kernel's zconst test (the slab's tensors always hold planes k-2 and kb+1)
+      const bool    thinband = kb - k < bz / 2;
+      for (int s = 0; s < nstrips; ++s) {
+        const bool nar  = narrow && kin && s == nstrips - 1;
+        const int  step = nar ? ty16 : ty;
+        for (int64_t ya = 0; ya < g.n1; ya += step) {
           const int  c0 = s * sweep3d::STRIP_OUT - 4;
-          const bool interior = kin && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 1 >= 1 && ya + NW3 - 2 <= g.n1 - 2;
-          (interior ? fast : slow).push_back(Item{s, (int)ya, (int)k, (int)kb});
+          const bool interior = kin && !nar && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 1 >= 1 && ya + NW3 - 2 <= g.n1 - 2;
+          (thinband ? small : interior ? fast : slow).push_back(Item{s, (int)ya, (int)k, (int)kb, nar ? 1 : 0});
         }
-      k = kb;
+      }
     }
     slow.insert(slow.end(), fast.begin(), fast.end());
+    slow.insert(slow.end(), small.begin(), small.end());
     nitems3 = (int)slow.size();
     PMG_TRY(items3.upload(slow, ctx->stream));
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -889,13 +912,19 @@ struct LapOp final : GridOp {
     if (swz) {
       const int64_t dims[4] = {4, pitch() / 4, g.n1, g.shi - g.slo + 2 * GH()}, strides[4] = {1, 4, pitch(), pitch() * g.n1};
       const int     boxx[4] = {4, 32, NW + 2, 1}, boxb[4] = {4, 32, NW, 1};
+      const int     boxx16[4] = {4, 16, 2 * NW + 2, 1}, boxb16[4] = {4, 16, 2 * NW, 1};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, true));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, true));
+      PMG_TRY(make_tensor_map(a.tm_x16, xin, 4, dims, strides, boxx16, true));
+      PMG_TRY(make_tensor_map(a.tm_b16, b ? b : xin, 4, dims, strides, boxb16, true));
     } else {
       const int64_t dims[4] = {pitch(), g.n1, g.shi - g.slo + 2 * GH(), 1}, strides[4] = {1, pitch(), pitch() * g.n1, pitch() * g.n1 * (g.shi - g.slo + 2 * GH())};
       const int     boxx[4] = {128, NW + 2, 1, 1}, boxb[4] = {128, NW, 1, 1};
+      const int     boxx16[4] = {64, 2 * NW + 2, 1, 1}, boxb16[4] = {64, 2 * NW, 1, 1};
       PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, false));
       PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, false));
+      PMG_TRY(make_tensor_map(a.tm_x16, xin, 4, dims, strides, boxx16, false));
+      PMG_TRY(make_tensor_map(a.tm_b16, b ? b : xin, 4, dims, strides, boxb16, false));
     }
     static const int bz_env = std::getenv("PMG_SW3_BZ") ? std::atoi(std::getenv("PMG_SW3_BZ")) : 0;
     const int        bz     = bz_env > 0 ? bz_env : 64;
@@ -925,7 +954,7 @@ struct LapOp final : GridOp {
     LapTab t;
     fill_tab(co.omega, t);
     static const int cfg_env = std::getenv("PMG_SW3_CFG") ? std::atoi(std::getenv("PMG_SW3_CFG")) : -1;
-    const int        cfg     = cfg_env >= 0 && cfg_env <= 6 ? cfg_env : (g.n1 >= 48 ? 2 : 1);
+    const int        cfg     = cfg_env >= 0 && cfg_env <= 6 ? cfg_env : (g.n1 >= 48 ? 6 : 1); // 6: warp-specialised for Philox, <16,4,2,1> otherwise
     Args a;
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();

@@ -46,10 +46,12 @@ enum { NOISE_NONE = 0, NOISE_TAPE = 1, NOISE_PHILOX = 2 };
 // one CTA's work: output columns of strip `strip`, output rows [ya, ya + NW - 2), output planes [ka, kb)
 struct Item {
   int strip, ya, ka, kb;
+  int narrow; // 1: the last, short strip of a row (at most 56 columns): 16 lanes per grid row, two grid rows per warp
 };
 
 struct Args {
   CUtensorMap   tm_x, tm_b; // {4, pitch/4, ny, local planes} FP64 tensors (SWIZZLE_32B); boxes 4 x 32 x (NW+2) x 1 and 4 x 32 x NW x 1
+  CUtensorMap   tm_x16, tm_b16; // the same tensors with the boxes of a narrow strip: 4 x 16 x (2NW+2) x 1 and 4 x 16 x 2NW x 1
   int           nx, ny, nz;
   int           slo, shi; // owned planes: the planes that are written, and the planes the injected tape covers
   int           tlo, thi; // planes held by the tensors and by xout: the owned planes plus two ghost planes per side on a slab
@@ -81,7 +83,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("s
 // byte offset of column M of the lane's segment inside a TMA row (SWIZZLE_32B layout, sweep2d.cuh)
 __device__ __forceinline__ uint32_t box_off(int lane, int M, bool swz) { return sweep2d::lane_seg(lane) + (((uint32_t)(M >> 1) * 16u) ^ (swz ? sweep2d::lane_swz(lane) : 0u)) + (uint32_t)(M & 1) * 8u; }
 // the half-updated planes are published component-major ([4][32] doubles per row): conflict-free 8-byte accesses
-__device__ __forceinline__ uint32_t new_off(int lane, int M) { return (uint32_t)(M * 256 + lane * 8); }
+template <int LPR> __device__ __forceinline__ uint32_t new_off(int l, int M) { return (uint32_t)(M * (LPR * 8) + l * 8); }
 
 template <int NW, int SX, int SB, bool WS = false> struct Smem {
   static constexpr int    XSTAGE = (NW + 2) * ROW_BYTES, BSTAGE = NW * ROW_BYTES, NEWBUF = NW * ROW_BYTES;
@@ -114,7 +116,7 @@ __device__ __forceinline__ void update(const Args &a, const Coef *coef, double (
 }
 
 // both colour phases of one plane step for row parity P (first-colour columns M = P, P+2)
-template <int P, bool INTERIOR>
+template <int P, bool INTERIOR, int LPR>
 __device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane, bool swz, bool inner_row, const double (&xm2)[4], double (&xm1)[4], double (&x0)[4], const double (&xp1)[4], uint32_t old_s, uint32_t old_n, uint32_t new_s, uint32_t new_n,
                                        const double (&w)[4], const double (&wk)[2], const int (&ci)[4], const int (&cis)[4])
 {
@@ -126,8 +128,8 @@ __device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane
   { // phase B: second colour of plane kk-1 (the same columns), every neighbour new; halo rows take part in the shuffles only
     const double west = P == 0 ? shfl_up1(xm1[3]) : 0.0, east = P == 1 ? shfl_dn1(xm1[0]) : 0.0;
     if (inner_row) {
-      update<P, INTERIOR>(a, coef, xm1, xm2[P], lds64(new_s + new_off(lane, P)), lds64(new_n + new_off(lane, P)), x0[P], west, east, wk[0], cis[P]);
-      update<P + 2, INTERIOR>(a, coef, xm1, xm2[P + 2], lds64(new_s + new_off(lane, P + 2)), lds64(new_n + new_off(lane, P + 2)), x0[P + 2], west, east, wk[1], cis[P + 2]);
+      update<P, INTERIOR>(a, coef, xm1, xm2[P], lds64(new_s + new_off<LPR>(lane, P)), lds64(new_n + new_off<LPR>(lane, P)), x0[P], west, east, wk[0], cis[P]);
+      update<P + 2, INTERIOR>(a, coef, xm1, xm2[P + 2], lds64(new_s + new_off<LPR>(lane, P + 2)), lds64(new_n + new_off<LPR>(lane, P + 2)), x0[P + 2], west, east, wk[1], cis[P + 2]);
     }
   }
 }
@@ -136,34 +138,45 @@ __device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane
 // plane ahead into a double-buffered shared-memory array, stencil warp i reads it: the long FP64 transcendental chains and
 // the latency-sensitive stencil part run in different warps, and twice as many warps are resident (setmaxnreg gives the
 // producers 40 registers and the stencil warps 88).
-template <int NOISE, bool INTERIOR, int NW, int SX, int SB, bool WS>
+//
+// ZCONST (edge tiles whose planes all have both z neighbours): the node classes do not change from plane to plane and are
+// computed once.  LPR = 16 (narrow strips): a grid row is 16 lanes (14 output lanes = 56 columns) and a warp holds two grid
+// rows of the same parity (tile rows 4(i/2) + (i%2) and + 2 for warp i), so that the colour pattern stays warp-uniform; the
+// shuffles that cross from one row to the other only reach halo lanes.  The shared-memory stages keep their sizes (a box of
+// 2NW+2 rows of 512 B fits a stage of NW+2 rows of 1 KB).
+template <int NOISE, bool INTERIOR, int NW, int SX, int SB, bool WS, bool ZCONST = false, int LPR = 32>
 __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t sm, const Item it)
 {
   using L = Smem<NW, SX, SB, WS>;
-  const int  lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = WS ? warp % NW : warp;
+  static_assert(LPR == 32 || LPR == 16, "lanes per grid row");
+  static_assert(!(INTERIOR && (ZCONST || LPR != 32)), "interior tiles are full-width and need no classes");
+  constexpr int RPW = 32 / LPR, ROWS = NW * RPW, RB = LPR * 32; // grid rows per warp, rows of the tile (2 of them halo), bytes per row
+  const int  wlane = threadIdx.x & 31, lane = wlane % LPR, warp = threadIdx.x >> 5, wi = WS ? warp % NW : warp;
+  const int  w = RPW == 1 ? wi : 4 * (wi >> 1) + (wi & 1) + 2 * (wlane / LPR);
   const bool producer = WS && warp >= NW;
   const int  c0 = it.strip * STRIP_OUT - 4, c = c0 + 4 * lane;
   const int  y = it.ya - 1 + w;
-  const bool inner_row = w >= 1 && w <= NW - 2;
-  const bool out_thread = inner_row && lane >= 1 && lane <= 30 && (INTERIOR || (c < a.nx && y < a.ny));
+  const bool inner_row = w >= 1 && w <= ROWS - 2;
+  const bool out_thread = inner_row && lane >= 1 && lane <= LPR - 2 && (INTERIOR || (c < a.nx && y < a.ny));
   const int  K0 = it.ka - 1, K1 = it.kb;         // plane steps; phase B planes K0 .. K1-1, of which ka .. kb-1 are stored
   const int  nsteps = K1 - K0 + 1;
   const uint32_t bar_x = sm + (uint32_t)L::off_bar, bar_b = bar_x + SX * 8;
-  const uint32_t xbytes = L::XSTAGE, bbytes = L::BSTAGE;
+  const uint32_t xbytes = (ROWS + 2) * RB, bbytes = ROWS * RB;
   const bool     swz = a.swizzle != 0;
+  const CUtensorMap *tmx = LPR == 32 ? &a.tm_x : &a.tm_x16, *tmb = LPR == 32 ? &a.tm_b : &a.tm_b16;
 
   // x sequence q = 0, 1, ...: plane K0 - 1 + q;  b sequence r = 0, 1, ...: plane K0 + r
   auto issue_x = [&](int q) {
     const uint32_t bar = bar_x + (q % SX) * 8;
     mbar_expect_tx(bar, xbytes);
-    if (swz) tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, 0, c0 >> 2, it.ya - 2, K0 - 1 + q - a.tlo, bar);
-    else tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, &a.tm_x, c0, it.ya - 2, K0 - 1 + q - a.tlo, 0, bar);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, tmx, 0, c0 >> 2, it.ya - 2, K0 - 1 + q - a.tlo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_x + (q % SX) * L::XSTAGE, tmx, c0, it.ya - 2, K0 - 1 + q - a.tlo, 0, bar);
   };
   auto issue_b = [&](int r) {
     const uint32_t bar = bar_b + (r % SB) * 8;
     mbar_expect_tx(bar, bbytes);
-    if (swz) tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, 0, c0 >> 2, it.ya - 1, K0 + r - a.tlo, bar);
-    else tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, &a.tm_b, c0, it.ya - 1, K0 + r - a.tlo, 0, bar);
+    if (swz) tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, tmb, 0, c0 >> 2, it.ya - 1, K0 + r - a.tlo, bar);
+    else tma_load_4d(sm + (uint32_t)L::off_b + (r % SB) * L::BSTAGE, tmb, c0, it.ya - 1, K0 + r - a.tlo, 0, bar);
   };
   const int nq = nsteps + 2; // x planes K0-1 .. K1+1
   if (threadIdx.x == 0) {
@@ -184,8 +197,18 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
       colmiss[m] = (c + m == 0 ? 1 : 0) + (c + m == a.nx - 1 ? 1 : 0);
     }
   }
+  int ci0[4] = {0, 0, 0, 0}; // ZCONST: the classes of every plane
+  if (ZCONST) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) ci0[m] = (rowok && colok[m]) ? 6 - colmiss[m] - rowmiss : 7;
+  }
   auto classes = [&](int kk, int (&ci)[4]) {
     if (INTERIOR) return;
+    if (ZCONST) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) ci[m] = ci0[m];
+      return;
+    }
     const bool kok   = kk >= 0 && kk < a.nz;
     const int  kmiss = (kk == 0 ? 1 : 0) + (kk == a.nz - 1 ? 1 : 0);
 #pragma unroll
@@ -210,9 +233,9 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
         double zs[4];
         classes(K0 + s, ci);
         scaled_normals(K0 + s, ci, zs);
-        const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * ROW_BYTES;
+        const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * RB;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) sts64(p + new_off(lane, m), zs[m]);
+        for (int m = 0; m < 4; ++m) sts64(p + new_off<LPR>(lane, m), zs[m]);
       }
       __syncthreads();
     }
@@ -221,12 +244,12 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
   if (WS) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 
   double A[4] = {0, 0, 0, 0}, B[4], C[4], D[4], wk[2] = {0, 0}; // rolling window: planes kk-2, kk-1, kk and the incoming kk+1
-  int    cis[4] = {7, 7, 7, 7};
-  const uint32_t own = (uint32_t)((w + 1) * ROW_BYTES); // this warp's row inside an x box
+  int    cis[4] = {ZCONST ? ci0[0] : 7, ZCONST ? ci0[1] : 7, ZCONST ? ci0[2] : 7, ZCONST ? ci0[3] : 7};
+  const uint32_t own = (uint32_t)((w + 1) * RB); // this warp's row inside an x box
   auto publish = [&](int plane, const double (&v)[4]) {
-    const uint32_t p = sm + (uint32_t)L::off_new + (plane & 1) * L::NEWBUF + w * ROW_BYTES;
+    const uint32_t p = sm + (uint32_t)L::off_new + (plane & 1) * L::NEWBUF + w * RB;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) sts64(p + new_off(lane, m), v[m]);
+    for (int m = 0; m < 4; ++m) sts64(p + new_off<LPR>(lane, m), v[m]);
   };
   mbar_wait(bar_x + 0 * 8, 0);
   lds256(sm + (uint32_t)L::off_x + 0 * L::XSTAGE + own, lane, B, swz);
@@ -247,7 +270,7 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
     lds256(xs1 + own, lane, xp1, swz);
     if (a.has_b) {
       mbar_wait(bar_b + (s % SB) * 8, (uint32_t)(s / SB) & 1u);
-      lds256(sm + (uint32_t)L::off_b + (s % SB) * L::BSTAGE + w * ROW_BYTES, lane, bb, swz);
+      lds256(sm + (uint32_t)L::off_b + (s % SB) * L::BSTAGE + w * RB, lane, bb, swz);
     }
     int ci[4] = {0, 0, 0, 0};
     classes(kk, ci);
@@ -257,9 +280,9 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
 #pragma unroll
       for (int m = 0; m < 4; ++m) wv[m] = bb[m];
     } else if (WS) {
-      const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * ROW_BYTES;
+      const uint32_t p = sm + (uint32_t)L::off_z + (s & 1) * L::NEWBUF + w * RB;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) wv[m] = __dadd_rn(lds64(p + new_off(lane, m)), bb[m]);
+      for (int m = 0; m < 4; ++m) wv[m] = __dadd_rn(lds64(p + new_off<LPR>(lane, m)), bb[m]);
     } else {
       double z[4];
       if (NOISE == NOISE_TAPE) {
@@ -280,10 +303,10 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
         wv[m]           = __dadd_rn(__dmul_rn(z[m], sd), bb[m]);
       }
     }
-    const uint32_t old_s = xs0 + own - ROW_BYTES, old_n = xs0 + own + ROW_BYTES;
+    const uint32_t old_s = xs0 + own - RB, old_n = xs0 + own + RB;
     const uint32_t nb    = sm + (uint32_t)L::off_new + ((kk - 1) & 1) * L::NEWBUF;
-    const uint32_t new_s = nb + (inner_row ? w - 1 : w) * ROW_BYTES, new_n = nb + (inner_row ? w + 1 : w) * ROW_BYTES;
-    phases<P, INTERIOR>(a, coef, lane, swz, inner_row, xm2, xm1, x0, xp1, old_s, old_n, new_s, new_n, wv, wk, ci, cis);
+    const uint32_t new_s = nb + (inner_row ? w - 1 : w) * RB, new_n = nb + (inner_row ? w + 1 : w) * RB;
+    phases<P, INTERIOR, LPR>(a, coef, lane, swz, inner_row, xm2, xm1, x0, xp1, old_s, old_n, new_s, new_n, wv, wk, ci, cis);
     wk[0] = wv[1 - P];
     wk[1] = wv[3 - P];
 #pragma unroll
@@ -338,8 +361,11 @@ template <int NOISE, int NW, int SX, int SB, int MINB, bool WS = false> __global
   const Item it = a.items[blockIdx.x];
   const int  c0 = it.strip * STRIP_OUT - 4;
   // every node the CTA updates exists and has all six neighbours, and every row / plane it reads exists and is owned
-  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2 && it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.tlo && it.kb + 1 < a.thi;
+  const bool zconst = it.ka - 1 >= 1 && it.kb <= a.nz - 2 && it.ka - 2 >= a.tlo && it.kb + 1 < a.thi; // every plane the tile touches has both z neighbours
+  const bool interior = zconst && !it.narrow && c0 >= 1 && c0 + 127 <= a.nx - 2 && it.ya - 1 >= 1 && it.ya + NW - 2 <= a.ny - 2;
   if (interior) run_cta<NOISE, true, NW, SX, SB, WS>(a, ft, coef, sm, it);
+  else if (it.narrow) run_cta<NOISE, false, NW, SX, SB, WS, true, 16>(a, ft, coef, sm, it); // the host makes narrow tiles only where zconst holds
+  else if (zconst) run_cta<NOISE, false, NW, SX, SB, WS, true>(a, ft, coef, sm, it);
   else run_cta<NOISE, false, NW, SX, SB, WS>(a, ft, coef, sm, it);
 }
 

@@ -969,3 +969,32 @@ def test_device_qoi_trace_welford_and_iact(pmg, ctx, orc):
     assert valid == valid_o and abs(tau - tau_o) < 1e-8 and abs(tau - (1 + rho) / (1 - rho)) < 2.5
     with pytest.raises(pmg.PMGError):
         pmg.iact(ctx, np.zeros(1))
+
+
+# ---- the fused 3D sweep on shapes that exercise narrow last strips (16 lanes per grid row), thin z-edge bands, ------------
+# ---- z-constant edge tiles and ragged tile edges: bitwise equal to one launch per colour (itself pinned to the oracle) ------
+@pytest.mark.parametrize("noise", ["philox", "injected", "none"])
+@pytest.mark.parametrize("dims", [(150, 40, 20), (130, 35, 9), (50, 64, 16), (512, 33, 12), (176, 61, 70), (57, 31, 12), (36, 30, 5)])
+def test_fused_3d_sweep_shapes_equal_per_colour(pmg, ctx, dims, noise, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("PMG_NO_FUSED", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_FUSED", "1")
+        mat = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.7)
+        pc = pmg.PC(ctx, "mcgibbs")
+        pc.set_operator(mat)
+        pc.set_options({"-pc_mcgibbs_omega": 1.3, "-pc_mcgibbs_symmetric": "", "-pc_b200_noise": noise})
+        pc.setup()
+        if noise == "injected":
+            pc.set_noise_tape(np.random.default_rng(SEED + 1).standard_normal(2 * pc.noise_per_sample()))
+        ctx.set_seed(11)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] != out[1][1]  # two code paths
