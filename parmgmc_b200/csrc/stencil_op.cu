@@ -936,12 +936,8 @@ struct LapOp final : GridOp {
   template <int NOISE> int launch3_cfg(int cfg, sweep3d::Args &a, const double *b, const double *xin)
   {
     switch (cfg) {
-    case 0: return launch3<NOISE, 16, 3, 2, 1>(a, b, xin); // 512 threads, 128 registers, 1 CTA / SM
     case 1: return launch3<NOISE, 8, 3, 2, 2>(a, b, xin);  // 256 threads, 128 registers, 2 CTAs / SM
-    case 2: return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);
-    case 3: return launch3<NOISE, 16, 5, 3, 1>(a, b, xin);
-    case 4: return launch3<NOISE, 16, 6, 4, 1>(a, b, xin);
-    case 5: return launch3<NOISE, 8, 5, 3, 2>(a, b, xin);
+    case 2: return launch3<NOISE, 16, 4, 2, 1>(a, b, xin); // 512 threads, 128 registers, 1 CTA / SM
     default:
       if (NOISE == sweep3d::NOISE_PHILOX) return launch3<sweep3d::NOISE_PHILOX, 16, 4, 2, 1, true>(a, b, xin); // warp-specialised
       return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);

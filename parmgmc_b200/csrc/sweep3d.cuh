@@ -86,10 +86,11 @@ __device__ __forceinline__ uint32_t box_off(int lane, int M, bool swz) { return 
 template <int LPR> __device__ __forceinline__ uint32_t new_off(int l, int M) { return (uint32_t)(M * (LPR * 8) + l * 8); }
 
 template <int NW, int SX, int SB, bool WS = false> struct Smem {
+  static constexpr int    TREP = NW >= 16 ? 8 : 1; // copies of the Box-Muller tables (fastnormal.cuh): conflict-free gathers where the space is there
   static constexpr int    XSTAGE = (NW + 2) * ROW_BYTES, BSTAGE = NW * ROW_BYTES, NEWBUF = NW * ROW_BYTES;
   static constexpr size_t off_x = 0, off_b = off_x + (size_t)SX * XSTAGE, off_new = off_b + (size_t)SB * BSTAGE, off_z = off_new + 2 * (size_t)NEWBUF; // z: WS only
   static constexpr size_t off_tab = off_z + (WS ? 2 * (size_t)NEWBUF : 0);
-  static constexpr size_t off_coef = off_tab + sizeof(fastnormal::SharedTables), off_bar = off_coef + 8 * sizeof(Coef), total = off_bar + (SX + SB) * 8 + 1024;
+  static constexpr size_t off_coef = off_tab + sizeof(fastnormal::SharedTablesT<TREP>), off_bar = off_coef + 8 * sizeof(Coef), total = off_bar + (SX + SB) * 8 + 1024;
 };
 
 // src/mc_sor.c:260-268 for column M of `row`: accumulation order of the assembled row (down, south, west, east, north, up)
@@ -144,8 +145,8 @@ __device__ __forceinline__ void phases(const Args &a, const Coef *coef, int lane
 // rows of the same parity (tile rows 4(i/2) + (i%2) and + 2 for warp i), so that the colour pattern stays warp-uniform; the
 // shuffles that cross from one row to the other only reach halo lanes.  The shared-memory stages keep their sizes (a box of
 // 2NW+2 rows of 512 B fits a stage of NW+2 rows of 1 KB).
-template <int NOISE, bool INTERIOR, int NW, int SX, int SB, bool WS, bool ZCONST = false, int LPR = 32>
-__device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t sm, const Item it)
+template <int NOISE, bool INTERIOR, int NW, int SX, int SB, bool WS, bool ZCONST = false, int LPR = 32, typename FT>
+__device__ __forceinline__ void run_cta(const Args &a, const FT &ft, const Coef *coef, uint32_t sm, const Item it)
 {
   using L = Smem<NW, SX, SB, WS>;
   static_assert(LPR == 32 || LPR == 16, "lanes per grid row");
@@ -320,23 +321,27 @@ __device__ __forceinline__ void run_cta(const Args &a, const fastnormal::Tables 
       if (a.has_b && s + SB < nsteps) issue_b(s + SB);
     }
   };
-  // the row parity alternates from plane to plane: steps are unrolled in pairs so that the colour pattern is a compile-time
-  // constant; every warp of the CTA runs the same number of steps (one barrier each)
+  // the row parity alternates from plane to plane and the rolling window has four slots: steps are unrolled in fours so that
+  // the colour pattern is a compile-time constant and the window never moves between registers; every warp of the CTA runs
+  // the same number of steps (one barrier each)
   auto pairs = [&](auto qtag) {
     constexpr int Q = decltype(qtag)::value;
-    int           s = 0;
-    for (; s + 1 < nsteps; s += 2) {
-      step(std::integral_constant<int, Q>{}, s, A, B, C, D);
-      step(std::integral_constant<int, 1 - Q>{}, s + 1, B, C, D, A);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) { // window (C, D, A) -> (A, B, C)
-        const double t = A[m];
-        A[m] = C[m];
-        B[m] = D[m];
-        C[m] = t;
+    using T0 = std::integral_constant<int, Q>;
+    using T1 = std::integral_constant<int, 1 - Q>;
+    int s = 0;
+    for (; s + 3 < nsteps; s += 4) {
+      step(T0{}, s, A, B, C, D);
+      step(T1{}, s + 1, B, C, D, A);
+      step(T0{}, s + 2, C, D, A, B);
+      step(T1{}, s + 3, D, A, B, C);
+    }
+    if (s < nsteps) {
+      step(T0{}, s, A, B, C, D);
+      if (s + 1 < nsteps) {
+        step(T1{}, s + 1, B, C, D, A);
+        if (s + 2 < nsteps) step(T0{}, s + 2, C, D, A, B);
       }
     }
-    if (s < nsteps) step(std::integral_constant<int, Q>{}, s, A, B, C, D);
   };
   if (((y + K0 + a.flip) & 1) == 0) pairs(std::integral_constant<int, 0>{});
   else pairs(std::integral_constant<int, 1>{});
@@ -347,9 +352,9 @@ template <int NOISE, int NW, int SX, int SB, int MINB, bool WS = false> __global
   using L = Smem<NW, SX, SB, WS>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  fastnormal::SharedTables *fts  = reinterpret_cast<fastnormal::SharedTables *>(base + L::off_tab);
+  auto *fts = reinterpret_cast<fastnormal::SharedTablesT<L::TREP> *>(base + L::off_tab);
   Coef                     *coef = reinterpret_cast<Coef *>(base + L::off_coef);
-  const fastnormal::Tables  ft   = fastnormal::load_tables(*fts);
+  const auto ft = fastnormal::load_tables(*fts);
   if (threadIdx.x < 8) coef[threadIdx.x] = a.coef[threadIdx.x];
   const uint32_t sm = smem_u32(base);
   if (threadIdx.x == 0) {
