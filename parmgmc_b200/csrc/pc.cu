@@ -576,7 +576,12 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   for (size_t s = 0; s < dirs.size(); ++s) { // pre-smoothing; the last sweep also forms the coarse right-hand side
     const bool last = s + 1 == dirs.size();
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
-    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, (zero_guess && s == 0) ? nullptr : cur, oth, na, c.op, nullptr, last ? c.b.p : nullptr));
+    const double *xin = (zero_guess && s == 0) ? nullptr : cur;
+    if (!xin && !v.op->fused_null_xin_ok()) { // the 3D sweep reads its iterate through the TMA: hand it zeros
+      PMG_CUDA(cudaMemsetAsync(cur, 0, (size_t)v.op->fused_size() * sizeof(double), ctx->stream));
+      xin = cur;
+    }
+    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, xin, oth, na, c.op, nullptr, last ? c.b.p : nullptr));
     std::swap(cur, oth);
   }
   PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));

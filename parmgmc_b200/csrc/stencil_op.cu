@@ -40,6 +40,7 @@ struct Geom {
   int64_t slo, shi;   // owned units of the slowest dimension
   int64_t unit;       // nodes per unit
   int64_t nl;         // owned nodes
+  int64_t ld;         // row stride of the vectors the kernel indexes: n0 (natural layout) or the pitch of the fused sweeps (pitched())
   __host__ __device__ int64_t nslow() const { return dim == 2 ? n1 : n2; }
   __host__ __device__ int64_t row0() const { return unit * slo; }
 };
@@ -55,6 +56,15 @@ Geom make_geom(int dim, const int64_t n[3], int64_t slo, int64_t shi)
   g.shi  = shi;
   g.unit = dim == 2 ? g.n0 : g.n0 * g.n1;
   g.nl   = g.unit * (shi - slo);
+  g.ld   = g.n0;
+  return g;
+}
+// the same grid over PITCHED vectors (row stride `pitch`, no ghost units): for the kernels that index through ld / unit / nl
+Geom pitched(Geom g, int64_t pitch)
+{
+  g.ld   = pitch;
+  g.unit = g.dim == 2 ? pitch : pitch * g.n1;
+  g.nl   = g.unit * (g.shi - g.slo);
   return g;
 }
 
@@ -101,12 +111,12 @@ template <int DIM> __device__ __forceinline__ bool node_of_thread(const Geom &g,
     if (rj >= g.shi - g.slo) return false;
     j   = g.slo + rj;
     k   = 0;
-    idx = i + g.n0 * rj;
+    idx = i + g.ld * rj;
   } else {
     if (rj >= g.n1) return false;
     j   = rj;
     k   = g.slo + blockIdx.z;
-    idx = i + g.n0 * (rj + g.n1 * (int64_t)blockIdx.z);
+    idx = i + g.ld * (rj + g.n1 * (int64_t)blockIdx.z);
   }
   return true;
 }
@@ -214,18 +224,18 @@ template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_app
   double       ax  = 0.0;
   if (DIM == 3) {
     if (D) ax = fma(mh, ldg(x, glo, ghi, idx - g.unit, g), ax);
-    if (S) ax = fma(mh, x[idx - g.n0], ax);
+    if (S) ax = fma(mh, x[idx - g.ld], ax);
   } else {
-    if (S) ax = fma(mh, ldg(x, glo, ghi, idx - g.n0, g), ax);
+    if (S) ax = fma(mh, ldg(x, glo, ghi, idx - g.ld, g), ax);
   }
   if (W) ax = fma(mh, x[idx - 1], ax);
   ax = fma(tab.diag[deg], x[idx], ax);
   if (E) ax = fma(mh, x[idx + 1], ax);
   if (DIM == 3) {
-    if (N) ax = fma(mh, x[idx + g.n0], ax);
+    if (N) ax = fma(mh, x[idx + g.ld], ax);
     if (U) ax = fma(mh, ldg(x, glo, ghi, idx + g.unit, g), ax);
   } else {
-    if (N) ax = fma(mh, ldg(x, glo, ghi, idx + g.n0, g), ax);
+    if (N) ax = fma(mh, ldg(x, glo, ghi, idx + g.ld, g), ax);
   }
   out[idx] = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
 }
@@ -366,7 +376,7 @@ template <int DIM> __global__ void __launch_bounds__(256) restrict_kernel(Geom g
         const int64_t i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
         if (i < 0 || i >= gf.n0 || j < 0 || j >= gf.n1 || k < 0 || k >= gf.n2) continue;
         const double  w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
-        const int64_t q = DIM == 2 ? i + gf.n0 * (j - gf.slo) : i + gf.n0 * (j + gf.n1 * (k - gf.slo));
+        const int64_t q = DIM == 2 ? i + gf.ld * (j - gf.slo) : i + gf.ld * (j + gf.n1 * (k - gf.slo));
         acc             = fma(w, ldg(r, rlo, rhi, q, gf), acc);
       }
   bc[idx] = acc;
@@ -390,7 +400,7 @@ template <int DIM> __global__ void __launch_bounds__(256) prolong_kernel(Geom gf
         const int64_t I = I0 + a;
         if (I >= gc.n0) continue;
         const double  w = (ci == 2 ? 0.5 : 1.0) * (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0);
-        const int64_t q = DIM == 2 ? I + gc.n0 * (J - gc.slo) : I + gc.n0 * (J + gc.n1 * (K - gc.slo));
+        const int64_t q = DIM == 2 ? I + gc.ld * (J - gc.slo) : I + gc.ld * (J + gc.n1 * (K - gc.slo));
         s               = fma(w, ldg(xc, clo, chi, q, gc), s);
       }
     }
@@ -771,7 +781,8 @@ struct LapOp final : GridOp {
     if (g.dim == 2) return g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
     return g.n0 >= 8 && g.n1 >= 2 && g.n2 >= 2 && g.n0 < (1 << 20) && g.n1 < (1 << 20) && g.n2 < (1 << 20);
   }
-  bool fused_mg_ok() const override { return fused_ok() && g.dim == 2 && !parallel; }
+  bool fused_mg_ok() const override { return fused_ok() && !parallel && (g.dim == 2 || !std::getenv("PMG_NO_FUSED_MG3")); }
+  bool fused_null_xin_ok() const override { return g.dim == 2; }
   bool fused_tape_ok() const override { return !parallel; } // the ghost units' noise is recomputed, which a tape of owned rows cannot supply
   // On a slab the pitched vectors carry GH ghost units (grid rows in 2D, planes in 3D) on either side: one fused sweep
   // updates both colours, so the boundary unit's second-colour update needs the neighbour's boundary unit AFTER its
@@ -848,6 +859,7 @@ struct LapOp final : GridOp {
   // b, xin, xout are pitched (fused_size() elements); xc / bc are the coarse level's natural-layout vectors
   // ---- 3D: stream3d.cuh ----
   DevBuf<sweep3d::Item> items3;
+  DevBuf<double>        r_pitched; // residual of the fused 3D top level (fused_sweep with bc)
   int                   nitems3 = 0, items3_bz = 0, items3_nw = 0;
   int build_items3(int bz, int NW3) // NW3 warps per CTA tile: NW3 - 2 output rows + 2 halo rows (narrow strips: 2 NW3 - 2 + 2)
   {
@@ -1101,9 +1113,30 @@ struct LapOp final : GridOp {
 
   int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
   {
-    if (g.dim == 3) {
-      if (xc || bc) PMG_FAIL(PMG_ERR_SUP, "the 3D fused sweep does not include the grid transfers");
-      return fused_sweep3(dir, co, b, xin, xout, na);
+    if (g.dim == 3) { // the transfers run as separate kernels on the pitched vectors (same arithmetic as the unfused V-cycle)
+      if ((xc || bc) && (parallel || !coarse)) PMG_FAIL(PMG_ERR_SUP, "the 3D fused sweep with grid transfers needs an undistributed level pair");
+      const Geom gp = pitched(g, pitch());
+      if (xc) { // x_old = xin + P xc, in place (the caller's iterate buffer: it is dead after this sweep)
+        const Geom &gc = static_cast<GridOp *>(coarse)->g;
+        const Plan  pl = plan_nodes<3>(gp);
+        PMG_PLAN_CHECK(pl);
+        prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, gc, xc, nullptr, nullptr, const_cast<double *>(xin));
+        PMG_CUDA(cudaGetLastError());
+        ctx->launches++;
+      }
+      PMG_TRY(fused_sweep3(dir, co, b, xin, xout, na));
+      if (bc) { // b_c = P^T (b - A xout)
+        const Geom &gc = static_cast<GridOp *>(coarse)->g;
+        if (!r_pitched.p) PMG_TRY(r_pitched.alloc((size_t)fused_size()));
+        const Plan pf = plan_nodes<3>(gp), pc = plan_nodes<3>(gc);
+        PMG_PLAN_CHECK(pf);
+        PMG_PLAN_CHECK(pc);
+        lap_apply_kernel<3, true><<<pf.grid, pf.block, 0, ctx->stream>>>(gp, tab, b, xout, nullptr, nullptr, r_pitched.p);
+        restrict_kernel<3><<<pc.grid, pc.block, 0, ctx->stream>>>(gp, gc, r_pitched.p, nullptr, nullptr, bc);
+        PMG_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+      }
+      return 0;
     }
     static const bool no_tma = std::getenv("PMG_NO_TMA") != nullptr;
     static const bool no_tma_prolong = std::getenv("PMG_NO_TMA_PROLONG") != nullptr;

@@ -444,6 +444,50 @@ def test_gamgmc_3d(pmg, ctx, orc):
     assert relerr(y, ref) < RTOL
 
 
+@pytest.mark.parametrize("dims,levels,its", [((17, 17, 17), 3, 1), ((33, 17, 9), 2, 2), ((21, 13, 17), 2, 1)])
+def test_gamgmc_3d_fused_top_level_matches_oracle(pmg, ctx, orc, dims, levels, its):
+    """3D V-cycle whose finest level runs the TMA-fed fused sweep on pitched vectors (odd nx: pitch != nx), with the
+    prolongation / residual / restriction kernels indexing the pitched layout: against the oracle's cycle (tape order F7)."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=1.0)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(lap)
+    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity", "-gamgmc_mg_levels_ksp_max_it": its})
+    pc.setup()
+    omg = oracle_mg(orc, 3, dims, 1.0, levels, its=its)
+    z = rng.standard_normal(2 * pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y = rng.standard_normal(n), np.zeros(n)
+    pc.apply_richardson(b, y, its=2)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.zeros(n), 2)
+    assert relerr(y, ref) < RTOL
+
+
+@pytest.mark.parametrize("dims,levels", [((65, 65, 65), 4), ((129, 33, 65), 4)])
+def test_gamgmc_3d_fused_top_level_equals_unfused(pmg, ctx, dims, levels, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("PMG_NO_FUSED_MG3", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_FUSED_MG3", "1")
+        lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.5)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_noise": "philox"})
+        pc.setup()
+        ctx.set_seed(21)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=3)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] != out[1][1]
+
+
 # ---- statistics with the device RNG (examples/ex1.c) -------------------------------------------------------
 @pytest.mark.parametrize("pctype,opts,nsamp", [
     ("mcgibbs", {}, 400000),
