@@ -314,6 +314,33 @@ def run_b200(args):
         gibbs3d = {"workload": f"3D 7-point {n3}^3 per GPU, fused red-black sweep (sweep3d_kernel)", "sweep_ms": ms3, "dof_updates_per_s": world * mat3.n / (ms3 * 1e-3),
                    "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak, "frac_of_nominal_8TBs": ach3 / 8000.0, "algorithmic_bytes_per_dof_update": bytes_per_update}}
 
+        del g3, mat3, y3, b3
+
+    # ---- config 4's building block at N = 1: one MGMC V-cycle sample on a 3D grid (fused fine level, Galerkin 27-point levels) ----
+    mgmc3d = None
+    if world == 1 and not args.no_mgmc3d:
+        nm = args.n3 + 1 if args.n3 % 2 == 0 else args.n3  # 2^k + 1 nodes per direction for the Q1 hierarchy
+        lv3 = 1
+        while ((nm - 1) >> (lv3 - 1)) % 2 == 0 and (((nm - 1) >> (lv3 - 1)) + 1) ** 3 > 4096:
+            lv3 += 1
+        matm = pmg.Mat.laplace(ctx, 3, nm, nm, nm, args.kappa)
+        m3 = pmg.PC(ctx, "gamgmc")
+        m3.set_operator(matm)
+        m3.set_options({"-gamgmc_pc_mg_levels": lv3, "-pc_b200_noise": "philox"})
+        m3.setup()
+        ym = torch.zeros(matm.n, dtype=torch.float64, device="cuda")
+        bm = torch.zeros(matm.n, dtype=torch.float64, device="cuda")
+        m3.apply_richardson_dev(bm, ym, its=2)
+        barrier()
+        e0.record(stream)
+        m3.apply_richardson_dev(bm, ym, its=8)
+        e1.record(stream)
+        barrier()
+        msm = e0.elapsed_time(e1) / 8
+        mgmc3d = {"workload": f"3D 7-point {nm}^3, PCGAMGMC V(1,1), {lv3} levels, SOR-Gibbs smoother, dense Cholesky coarsest", "ms_per_sample": msm, "samples_per_s": 1e3 / msm,
+                  "launches_per_sample": m3.last_stats()["launches"] / 8}
+        del m3, matm, ym, bm
+
     if rank == 0:
         cpu = cpu_baseline_leg(args, args.cpu_samples) if (world == 1 and not args.no_cpu_baseline) else None
         out = {"metric": "mgmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -330,6 +357,8 @@ def run_b200(args):
                "mgmc_ms_per_sample": ms / (args.steps * S), "view": view}
         if gibbs3d is not None:
             out["gibbs3d"] = gibbs3d
+        if mgmc3d is not None:
+            out["mgmc3d"] = mgmc3d
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
@@ -351,6 +380,7 @@ def main():
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU chains of the reference arm (0: min(cores, 16, memory / 3 GB))")
     ap.add_argument("--no-gibbs3d", action="store_true", help="skip the 3D 7-point sweep measurement")
+    ap.add_argument("--no-mgmc3d", action="store_true", help="skip the 3D V-cycle measurement (N = 1 only)")
     ap.add_argument("--cpu-samples", type=int, default=4)
     ap.add_argument("--bytes-per-update", type=float, default=32.0, help="algorithmic bytes per DOF update of the fine sweep (DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

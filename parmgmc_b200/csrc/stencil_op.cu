@@ -240,6 +240,89 @@ template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) lap_app
   out[idx] = RESIDUAL ? __dsub_rn(b[idx], ax) : ax;
 }
 
+// ---- finest 3D level of the fused V-cycle: the same residual and prolongation on PITCHED vectors, four columns per thread
+// (one 32-byte segment: 256-bit loads and stores, a quarter of the load instructions of the per-node kernels; the
+// arithmetic per node is lap_apply_kernel<3, true>'s and prolong_kernel<3>'s, fma for fma).  Undistributed levels only.
+__device__ __forceinline__ void ldg256(const double *p, double (&v)[4]) { asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p)); }
+__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) { asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory"); }
+__device__ __forceinline__ void stg256(double *p, const double (&v)[4]) { asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory"); }
+// thread -> (quad t of the row, row j, plane k)
+__device__ __forceinline__ bool quad_of_thread(const Geom &g, int nq, int &t, int &j, int &k)
+{
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (unsigned)nq * (unsigned)g.n1) return false;
+  j = (int)(q / (unsigned)nq);
+  t = (int)(q - (unsigned)j * (unsigned)nq);
+  k = (int)blockIdx.y;
+  return true;
+}
+__global__ void __launch_bounds__(256) lap_residual3_pitched_kernel(Geom g, LapTab tab, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ out)
+{
+  const int nq = (int)(g.ld >> 2);
+  int       t, j, k;
+  if (!quad_of_thread(g, nq, t, j, k)) return;
+  const int64_t idx = 4 * (int64_t)t + g.ld * ((int64_t)j + g.n1 * (int64_t)k);
+  const bool    S = j > 0, N = j < g.n1 - 1, D = k > 0, U = k < g.n2 - 1;
+  double        xc[4], xs[4] = {0, 0, 0, 0}, xn[4] = {0, 0, 0, 0}, xd[4] = {0, 0, 0, 0}, xu[4] = {0, 0, 0, 0}, bb[4], r[4];
+  ldg256(x + idx, xc);
+  ldg256(b + idx, bb);
+  if (S) ldg256(x + idx - g.ld, xs);
+  if (N) ldg256(x + idx + g.ld, xn);
+  if (D) ldg256(x + idx - g.unit, xd);
+  if (U) ldg256(x + idx + g.unit, xu);
+  const int    i0 = 4 * t;
+  const double xw = i0 > 0 ? __ldg(x + idx - 1) : 0.0, xe = i0 + 4 < g.n0 ? __ldg(x + idx + 4) : 0.0;
+  const double mh = -tab.h;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int  i = i0 + m;
+    const bool W = i > 0, E = i < g.n0 - 1;
+    const int  deg = (int)W + (int)E + (int)S + (int)N + (int)D + (int)U;
+    double     ax  = 0.0;
+    if (D) ax = fma(mh, xd[m], ax);
+    if (S) ax = fma(mh, xs[m], ax);
+    if (W) ax = fma(mh, m == 0 ? xw : xc[m == 0 ? 0 : m - 1], ax);
+    ax = fma(tab.diag[deg], xc[m], ax);
+    if (E) ax = fma(mh, m == 3 ? xe : xc[m == 3 ? 3 : m + 1], ax);
+    if (N) ax = fma(mh, xn[m], ax);
+    if (U) ax = fma(mh, xu[m], ax);
+    r[m] = i < g.n0 ? __dsub_rn(bb[m], ax) : 0.0;
+  }
+  stg256(out + idx, r);
+}
+__global__ void __launch_bounds__(256) prolong3_pitched_kernel(Geom gf, Geom gc, const double *__restrict__ xc, double *__restrict__ xf)
+{
+  const int nq = (int)(gf.ld >> 2);
+  int       t, j, k;
+  if (!quad_of_thread(gf, nq, t, j, k)) return;
+  const int64_t idx = 4 * (int64_t)t + gf.ld * ((int64_t)j + gf.n1 * (int64_t)k);
+  double        s[4];
+  ld256(xf + idx, s);
+  const int cj = (j & 1) ? 2 : 1, ck = (k & 1) ? 2 : 1;
+  const int J0 = j >> 1, K0 = k >> 1, I0 = 2 * t; // coarse columns I0, I0 + 1, I0 + 2 serve the four fine columns
+  for (int c = 0; c < ck; ++c) { // prolong_kernel's order: K, then J, then I ascending
+    const int K = K0 + c;
+    if (K >= gc.n2) continue;
+    for (int bq = 0; bq < cj; ++bq) {
+      const int J = J0 + bq;
+      if (J >= gc.n1) continue;
+      const double *row = xc + gc.ld * ((int64_t)J + gc.n1 * (int64_t)K);
+      const double  v0 = I0 < gc.n0 ? __ldg(row + I0) : 0.0, v1 = I0 + 1 < gc.n0 ? __ldg(row + I0 + 1) : 0.0, v2 = I0 + 2 < gc.n0 ? __ldg(row + I0 + 2) : 0.0;
+      const double  we = (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0), wo = 0.5 * (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0); // even / odd fine column
+      if (I0 < gc.n0) s[0] = fma(we, v0, s[0]);
+      if (I0 < gc.n0) s[1] = fma(wo, v0, s[1]);
+      if (I0 + 1 < gc.n0) s[1] = fma(wo, v1, s[1]);
+      if (I0 + 1 < gc.n0) s[2] = fma(we, v1, s[2]);
+      if (I0 + 1 < gc.n0) s[3] = fma(wo, v1, s[3]);
+      if (I0 + 2 < gc.n0) s[3] = fma(wo, v2, s[3]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    if (4 * t + m >= gf.n0) s[m] = 0.0; // pad columns stay zero
+  stg256(xf + idx, s);
+}
+
 // natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
 template <bool TO_PITCHED> __global__ void __launch_bounds__(256) repitch_kernel(int64_t n0, int64_t rows, int64_t pitch, const double *__restrict__ src, double *__restrict__ dst)
 {
@@ -1118,9 +1201,7 @@ struct LapOp final : GridOp {
       const Geom gp = pitched(g, pitch());
       if (xc) { // x_old = xin + P xc, in place (the caller's iterate buffer: it is dead after this sweep)
         const Geom &gc = static_cast<GridOp *>(coarse)->g;
-        const Plan  pl = plan_nodes<3>(gp);
-        PMG_PLAN_CHECK(pl);
-        prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, gc, xc, nullptr, nullptr, const_cast<double *>(xin));
+        prolong3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)g.n2), 256, 0, ctx->stream>>>(gp, gc, xc, const_cast<double *>(xin));
         PMG_CUDA(cudaGetLastError());
         ctx->launches++;
       }
@@ -1128,10 +1209,9 @@ struct LapOp final : GridOp {
       if (bc) { // b_c = P^T (b - A xout)
         const Geom &gc = static_cast<GridOp *>(coarse)->g;
         if (!r_pitched.p) PMG_TRY(r_pitched.alloc((size_t)fused_size()));
-        const Plan pf = plan_nodes<3>(gp), pc = plan_nodes<3>(gc);
-        PMG_PLAN_CHECK(pf);
+        const Plan pc = plan_nodes<3>(gc);
         PMG_PLAN_CHECK(pc);
-        lap_apply_kernel<3, true><<<pf.grid, pf.block, 0, ctx->stream>>>(gp, tab, b, xout, nullptr, nullptr, r_pitched.p);
+        lap_residual3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)g.n2), 256, 0, ctx->stream>>>(gp, tab, b, xout, r_pitched.p);
         restrict_kernel<3><<<pc.grid, pc.block, 0, ctx->stream>>>(gp, gc, r_pitched.p, nullptr, nullptr, bc);
         PMG_CUDA(cudaGetLastError());
         ctx->launches += 2;
