@@ -89,8 +89,14 @@ struct Plan {
 };
 static Plan plan3(int64_t ni, int64_t nrows, int64_t nplanes)
 {
+  // the block width (a multiple of 32, at most 256) that wastes the fewest threads on this row length: the grids of the
+  // Q1 hierarchy have 2^k + 1 nodes per direction, which a power-of-two width covers at 50 % in the worst case
   unsigned bx = 32;
-  while (bx < ni && bx < 256) bx *= 2;
+  int64_t  best = -1;
+  for (unsigned c = 32; c <= 256; c += 32) {
+    const int64_t slots = (ni + c - 1) / c * c;
+    if (best < 0 || slots <= best) { best = slots; bx = c; }
+  }
   const unsigned by = 256 / bx;
   Plan           p;
   p.block = dim3(bx, by, 1);
@@ -321,6 +327,52 @@ __global__ void __launch_bounds__(256) prolong3_pitched_kernel(Geom gf, Geom gc,
   for (int m = 0; m < 4; ++m)
     if (4 * t + m >= gf.n0) s[m] = 0.0; // pad columns stay zero
   stg256(xf + idx, s);
+}
+
+// b_c = P^T r for a pitched fine residual: four coarse nodes per thread (fine columns 8t-1 .. 8t+7 of each of the 9 fine rows:
+// two 256-bit loads and one scalar), restrict_kernel<3>'s accumulation order (k, j, i ascending) per coarse node
+__global__ void __launch_bounds__(256) restrict3_pitched_kernel(Geom gf, Geom gc, const double *__restrict__ r, double *__restrict__ bc)
+{
+  const int      nqc = (int)((gc.n0 + 3) >> 2);
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (unsigned)nqc * (unsigned)gc.n1) return;
+  const int J = (int)(q / (unsigned)nqc), t = (int)(q - (unsigned)J * (unsigned)nqc), K = (int)blockIdx.y;
+  double    acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int dk = -1; dk <= 1; ++dk) {
+    const int k = 2 * K + dk;
+    if (k < 0 || k >= gf.n2) continue;
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+      const int j = 2 * J + dj;
+      if (j < 0 || j >= gf.n1) continue;
+      const double *row = r + gf.ld * ((int64_t)j + gf.n1 * (int64_t)k);
+      const int     i0 = 8 * t; // fine column of the thread's first coarse node
+      double        v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // fine columns i0-1 .. i0+7; columns >= ld are not loaded
+      if (i0 > 0) v[0] = __ldg(row + i0 - 1);
+      {
+        double a[4];
+        ldg256(row + i0, a);
+        v[1] = a[0]; v[2] = a[1]; v[3] = a[2]; v[4] = a[3];
+      }
+      if (i0 + 4 < gf.ld) {
+        double a[4];
+        ldg256(row + i0 + 4, a);
+        v[5] = a[0]; v[6] = a[1]; v[7] = a[2]; v[8] = a[3];
+      }
+      const double wjk = (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int ic = i0 + 2 * m; // fine column of coarse node 4t + m
+        if (ic - 1 >= 0 && ic - 1 < gf.n0) acc[m] = fma(0.5 * wjk, v[2 * m], acc[m]);
+        if (ic < gf.n0) acc[m] = fma(wjk, v[2 * m + 1], acc[m]);
+        if (ic + 1 < gf.n0) acc[m] = fma(0.5 * wjk, v[2 * m + 2], acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    if (4 * t + m < gc.n0) bc[4 * t + m + gc.ld * ((int64_t)J + gc.n1 * (int64_t)K)] = acc[m];
 }
 
 // natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
@@ -1209,10 +1261,8 @@ struct LapOp final : GridOp {
       if (bc) { // b_c = P^T (b - A xout)
         const Geom &gc = static_cast<GridOp *>(coarse)->g;
         if (!r_pitched.p) PMG_TRY(r_pitched.alloc((size_t)fused_size()));
-        const Plan pc = plan_nodes<3>(gc);
-        PMG_PLAN_CHECK(pc);
         lap_residual3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)g.n2), 256, 0, ctx->stream>>>(gp, tab, b, xout, r_pitched.p);
-        restrict_kernel<3><<<pc.grid, pc.block, 0, ctx->stream>>>(gp, gc, r_pitched.p, nullptr, nullptr, bc);
+        restrict3_pitched_kernel<<<dim3((unsigned)((((gc.n0 + 3) >> 2) * gc.n1 + 255) / 256), (unsigned)gc.n2), 256, 0, ctx->stream>>>(gp, gc, r_pitched.p, bc);
         PMG_CUDA(cudaGetLastError());
         ctx->launches += 2;
       }
