@@ -16,6 +16,7 @@ CASES = {
     # name: (pc type, dim, dims, options, its, ragged cut?)
     "sorgibbs2d": ("sorgibbs", 2, (65, 67, 1), {}, 3, True),
     "mcgibbs3d_sym": ("mcgibbs", 3, (17, 12, 20), {"-pc_mcgibbs_symmetric": "", "-pc_mcgibbs_omega": 1.3}, 2, True),
+    "mcgibbs3d_narrow_strip": ("mcgibbs", 3, (150, 40, 48), {"-pc_mcgibbs_symmetric": "", "-pc_mcgibbs_omega": 1.2}, 2, False),  # 16-lane last strip, thin z-edge bands on slabs
     "gamgmc2d_deep": ("gamgmc", 2, (129, 257, 1), {"-gamgmc_pc_mg_levels": 5, "-pc_b200_replicate_below": 500}, 3, True),
     "gamgmc2d_default": ("gamgmc", 2, (129, 257, 1), {"-gamgmc_pc_mg_levels": 4}, 2, False),
     "gamgmc3d": ("gamgmc", 3, (33, 33, 65), {"-gamgmc_pc_mg_levels": 3, "-pc_b200_replicate_below": 3000}, 2, False),
