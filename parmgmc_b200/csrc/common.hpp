@@ -203,6 +203,7 @@ struct LevelOp {
   virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
   virtual bool fused_tape_ok() const { return true; } // fused_sweep can take an injected noise tape
   virtual bool fused_null_xin_ok() const { return true; } // fused_sweep accepts xin = NULL for a zero iterate
+  virtual bool pitched_is_natural() const { return false; } // the pitched layout of the fused sweeps equals the natural one
   // One directional sweep in a single out-of-place pass on the level's natural-layout vectors (box_stream.cuh)
   virtual bool stream_ok() const { return false; }
   virtual int  stream_sweep(int dir, const SweepCoeffs &c, const double *b, const double *xin, double *xout, const NoiseArgs &na)

@@ -911,13 +911,19 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
       one.gibbs.type = pc->smp.gibbs.type;
       sweep_dirs(one, dirs);
       PMG_TRY(pc->smp.gibbs.ensure());
+      // when the pitched layout IS the natural one (row length a multiple of 4, no ghost units) the sweeps run on the
+      // caller's vectors directly: no layout copies, y and the scratch vector ping-pong
+      const bool    direct = op->pitched_is_natural() && ((((uintptr_t)y) | ((uintptr_t)b)) & 31u) == 0;
       const double *pb = nullptr;
       if (b) {
-        PMG_TRY(op->to_pitched(b, pc->pit_b.p));
-        pb = pc->pit_b.p;
+        if (direct) pb = b;
+        else {
+          PMG_TRY(op->to_pitched(b, pc->pit_b.p));
+          pb = pc->pit_b.p;
+        }
       }
-      PMG_TRY(op->to_pitched(y, pc->pit_y.p));
-      double   *cur = pc->pit_y.p, *oth = pc->scratch.p;
+      if (!direct) PMG_TRY(op->to_pitched(y, pc->pit_y.p));
+      double   *cur = direct ? y : pc->pit_y.p, *oth = pc->scratch.p;
       NoiseArgs na;
       for (int64_t it = 0; it < its; ++it) {
         for (int d : dirs) {
@@ -925,7 +931,10 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
           PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, pb, cur, oth, na, nullptr, nullptr, nullptr));
           std::swap(cur, oth);
         }
-        if (pc->cb || pc->qoi.on || it + 1 == its) PMG_TRY(op->from_pitched(cur, y));
+        if (pc->cb || pc->qoi.on || it + 1 == its) {
+          if (!direct) PMG_TRY(op->from_pitched(cur, y));
+          else if (cur != y) PMG_CUDA(cudaMemcpyAsync(y, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         PMG_TRY(pc_notify(pc, pc->type == "sorgibbs" ? pc->sample_index++ : it, y));
       }
     } else {

@@ -918,6 +918,7 @@ struct LapOp final : GridOp {
   }
   bool fused_mg_ok() const override { return fused_ok() && !parallel && (g.dim == 2 || !std::getenv("PMG_NO_FUSED_MG3")); }
   bool fused_null_xin_ok() const override { return g.dim == 2; }
+  bool pitched_is_natural() const override { return !parallel && pitch() == g.n0; }
   bool fused_tape_ok() const override { return !parallel; } // the ghost units' noise is recomputed, which a tape of owned rows cannot supply
   // On a slab the pitched vectors carry GH ghost units (grid rows in 2D, planes in 3D) on either side: one fused sweep
   // updates both colours, so the boundary unit's second-colour update needs the neighbour's boundary unit AFTER its
