@@ -204,6 +204,15 @@ struct LevelOp {
   virtual bool fused_tape_ok() const { return true; } // fused_sweep can take an injected noise tape
   virtual bool fused_null_xin_ok() const { return true; } // fused_sweep accepts xin = NULL for a zero iterate
   virtual bool pitched_is_natural() const { return false; } // the pitched layout of the fused sweeps equals the natural one
+  // slab-distributed finest level of the V-cycle: fused sweeps for the smoothing (one exchange of two ghost units per sweep
+  // instead of one per colour), residual and transfers as separate kernels on the pitched vectors
+  virtual bool fused_smooth_ok() const { return false; }
+  virtual int  residual_pitched(const double *b, const double *x, double *r)
+  {
+    (void)b; (void)x; (void)r;
+    pmg_set_error("pitched residual not available for this operator");
+    return PMG_ERR_SUP;
+  }
   // One directional sweep in a single out-of-place pass on the level's natural-layout vectors (box_stream.cuh)
   virtual bool stream_ok() const { return false; }
   virtual int  stream_sweep(int dir, const SweepCoeffs &c, const double *b, const double *xin, double *xout, const NoiseArgs &na)
@@ -248,6 +257,19 @@ struct Transfer {
   {
     (void)b_fine; (void)x_fine; (void)b_coarse;
     pmg_set_error("fused residual + restriction not available for this transfer");
+    return PMG_ERR_SUP;
+  }
+  // the same transfers with the FINE vector in the pitched layout of the fused sweeps (ghost units in place)
+  virtual int restrict_pitched(double *r_fine_pitched, double *b_coarse)
+  {
+    (void)r_fine_pitched; (void)b_coarse;
+    pmg_set_error("pitched restriction not available for this transfer");
+    return PMG_ERR_SUP;
+  }
+  virtual int prolong_pitched(const double *x_coarse, double *x_fine_pitched)
+  {
+    (void)x_coarse; (void)x_fine_pitched;
+    pmg_set_error("pitched prolongation not available for this transfer");
     return PMG_ERR_SUP;
   }
   virtual int restrict_to(const double *r_fine, double *b_coarse) = 0; // b_c = P^T r

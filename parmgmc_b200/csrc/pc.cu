@@ -553,6 +553,32 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(v.P->prolong_add(pc->lv[l - 1].x.p, v.x.p));
     return smooth();
   }
+  // slab-distributed finest level: fused sweeps on the pitched vectors (one ghost exchange per sweep), pitched residual / transfers
+  if (!fused && l > 0 && l == pc->nlevels - 1 && v.smp.kind != KIND_CHOL && v.op->fused_smooth_ok() && v.x2.p && x == pc->pit_y.p) {
+    MgLevel         &c = pc->lv[l - 1];
+    std::vector<int> dirs;
+    sweep_dirs(v.smp, dirs);
+    PMG_TRY(v.smp.gibbs.ensure());
+    double   *cur = x, *oth = v.x2.p;
+    NoiseArgs na;
+    auto      smooth = [&]() -> int {
+      for (int d : dirs) {
+        PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+        PMG_TRY(v.op->fused_sweep(d, v.smp.gibbs.coeffs, b, cur, oth, na, nullptr, nullptr, nullptr));
+        std::swap(cur, oth);
+      }
+      return 0;
+    };
+    if (zero_guess) PMG_CUDA(cudaMemsetAsync(cur, 0, (size_t)v.op->fused_size() * sizeof(double), ctx->stream));
+    PMG_TRY(smooth());
+    PMG_TRY(v.op->residual_pitched(b, cur, v.r.p));
+    PMG_TRY(v.P->restrict_pitched(v.r.p, c.b.p));
+    PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
+    PMG_TRY(v.P->prolong_pitched(c.x.p, cur));
+    PMG_TRY(smooth());
+    if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->fused_size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+  }
   if (!fused) {
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
     PMG_TRY(run_level_sampler(pc, v.smp, b, x));
@@ -758,7 +784,11 @@ static int gamgmc_setup(pmg_pc pc)
     }
     if (l > 0) PMG_TRY(v.r.alloc(n));
     if (l > 0 && l < L - 1 && v.smp.kind != KIND_CHOL && v.op->stream_ok()) PMG_TRY(v.x2.alloc(n));
-    if (l > 0 && l == L - 1 && v.op->fused_mg_ok() && v.smp.kind != KIND_CHOL) {
+    if (l > 0 && l == L - 1 && (v.op->fused_mg_ok() || v.op->fused_smooth_ok()) && v.smp.kind != KIND_CHOL) {
+      if (v.op->fused_smooth_ok()) { // the residual lives in the pitched layout too
+        PMG_TRY(v.r.alloc((size_t)v.op->fused_size()));
+        PMG_TRY(v.r.zero(ctx->stream));
+      }
       PMG_TRY(v.x2.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_y.alloc((size_t)v.op->fused_size()));
       PMG_TRY(pc->pit_b.alloc((size_t)v.op->fused_size()));

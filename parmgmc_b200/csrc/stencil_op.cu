@@ -830,6 +830,9 @@ struct GridOp : LevelOp {
     if (!parallel) return 0;
     return comm_halo_exchange(ctx, x, ghost_lo.p, x + g.nl - g.unit, ghost_hi.p, (size_t)g.unit, (size_t)g.unit, ctx->stream);
   }
+  // pitched layout of the fused sweeps (LapOp): geometry, offset of the owned part, ghost exchange in place
+  virtual bool pitched_view(Geom &gp, int64_t &own_offset) const { (void)gp; (void)own_offset; return false; }
+  virtual int  pitched_halo(double *pitched) { (void)pitched; return PMG_ERR_SUP; }
   virtual bool star() const = 0;
   int          ncolors() const override { return star() ? 2 : (g.dim == 3 ? 8 : 4); }
   int32_t      colour_of(int64_t i, int64_t j, int64_t k) const { return star() ? (int32_t)((i + j + k) & 1) : (int32_t)((i & 1) + 2 * (j & 1) + (g.dim == 3 ? 4 * (k & 1) : 0)); }
@@ -919,6 +922,29 @@ struct LapOp final : GridOp {
   bool fused_mg_ok() const override { return fused_ok() && !parallel && (g.dim == 2 || !std::getenv("PMG_NO_FUSED_MG3")); }
   bool fused_null_xin_ok() const override { return g.dim == 2; }
   bool pitched_is_natural() const override { return !parallel && pitch() == g.n0; }
+  bool fused_smooth_ok() const override { return parallel && fused_ok() && !std::getenv("PMG_NO_FUSED_SMOOTH"); }
+  bool pitched_view(Geom &gp, int64_t &own_offset) const override
+  {
+    gp         = pitched(g, pitch());
+    own_offset = GH() * unit_rows() * pitch();
+    return true;
+  }
+  int pitched_halo(double *p) override { return fused_halo(p); }
+  int residual_pitched(const double *b, const double *x, double *r) override
+  {
+    PMG_TRY(fused_halo(const_cast<double *>(x)));
+    Geom    gp;
+    int64_t off;
+    pitched_view(gp, off);
+    const Plan pl = g.dim == 2 ? plan_nodes<2>(gp) : plan_nodes<3>(gp);
+    PMG_PLAN_CHECK(pl);
+    const double *xo = x + off;
+    if (g.dim == 2) lap_apply_kernel<2, true><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, tab, b + off, xo, xo - gp.unit, xo + gp.nl, r + off);
+    else lap_apply_kernel<3, true><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, tab, b + off, xo, xo - gp.unit, xo + gp.nl, r + off);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
   bool fused_tape_ok() const override { return !parallel; } // the ghost units' noise is recomputed, which a tape of owned rows cannot supply
   // On a slab the pitched vectors carry GH ghost units (grid rows in 2D, planes in 3D) on either side: one fused sweep
   // updates both colours, so the boundary unit's second-colour update needs the neighbour's boundary unit AFTER its
@@ -1603,6 +1629,37 @@ struct GridTransfer final : Transfer {
     ctx->launches++;
     return 0;
   }
+  int restrict_pitched(double *r, double *bcoarse) override
+  {
+    Geom    gf;
+    int64_t off;
+    if (!fine->pitched_view(gf, off)) PMG_FAIL(PMG_ERR_SUP, "the fine operator has no pitched layout");
+    PMG_TRY(fine->pitched_halo(r));
+    const Geom &gc = coarse->g;
+    const Plan  pl = gf.dim == 2 ? plan_nodes<2>(gc) : plan_nodes<3>(gc);
+    PMG_PLAN_CHECK(pl);
+    const double *ro = r + off;
+    if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, bcoarse);
+    else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, bcoarse);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int prolong_pitched(const double *xc, double *xf) override
+  {
+    Geom    gf;
+    int64_t off;
+    if (!fine->pitched_view(gf, off)) PMG_FAIL(PMG_ERR_SUP, "the fine operator has no pitched layout");
+    PMG_TRY(coarse->halo(xc));
+    const Geom &gc = coarse->g;
+    const Plan  pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf + off);
+    else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf + off);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
   int prolong_add(const double *xc, double *xf) override
   {
     PMG_TRY(coarse->halo(xc));
@@ -1639,6 +1696,37 @@ struct ReplicatingTransfer final : Transfer {
       ctx->launches++;
     }
     return comm_allgatherv(ctx, slab.p, bcoarse_full, counts.data(), displs.data(), ctx->stream);
+  }
+  int restrict_pitched(double *r, double *bcoarse_full) override
+  {
+    Geom    gf;
+    int64_t off;
+    if (!fine->pitched_view(gf, off)) PMG_FAIL(PMG_ERR_SUP, "the fine operator has no pitched layout");
+    PMG_TRY(fine->pitched_halo(r));
+    if (gc.nl > 0) {
+      const Plan pl = gf.dim == 2 ? plan_nodes<2>(gc) : plan_nodes<3>(gc);
+      PMG_PLAN_CHECK(pl);
+      const double *ro = r + off;
+      if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, slab.p);
+      else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, slab.p);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return comm_allgatherv(ctx, slab.p, bcoarse_full, counts.data(), displs.data(), ctx->stream);
+  }
+  int prolong_pitched(const double *xc_full, double *xf) override
+  {
+    Geom    gf;
+    int64_t off;
+    if (!fine->pitched_view(gf, off)) PMG_FAIL(PMG_ERR_SUP, "the fine operator has no pitched layout");
+    const double *xc = xc_full + gc.row0(); // the neighbouring units are simply adjacent in the replica
+    const Plan    pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
+    PMG_PLAN_CHECK(pl);
+    if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf + off);
+    else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf + off);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
   }
   int prolong_add(const double *xc_full, double *xf) override
   {
