@@ -1447,9 +1447,18 @@ struct BoxOp final : GridOp {
     const int  nc = ncolors();
     const Plan pl = g.dim == 2 ? box_colour_plan<2>(g) : box_colour_plan<3>(g);
     PMG_PLAN_CHECK(pl);
+    // A colour lives on the units (grid rows / planes) of ONE parity of the slowest dimension, and everything it reads from a
+    // ghost unit has the other parity: the ghosts need refreshing only when units of that other parity have been swept
+    // since the last exchange -- twice per sweep instead of once per colour (src/mc_sor.c:318-319 scatters before every colour).
+    bool dirty[2] = {true, true};
     for (int s = 0; s < nc; ++s) {
       const int c = dir == PMG_SOR_FORWARD_SWEEP ? s : nc - 1 - s;
-      PMG_TRY(halo(y));
+      const int sp = g.dim == 2 ? (c >> 1) & 1 : (c >> 2) & 1;
+      if (dirty[1 - sp]) {
+        PMG_TRY(halo(y));
+        dirty[0] = dirty[1] = false;
+      }
+      dirty[sp] = true;
       if (g.dim == 2) box_sweep_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
       else box_sweep_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(g, c, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, ghost_lo.p, ghost_hi.p, na);
       PMG_CUDA(cudaGetLastError());
