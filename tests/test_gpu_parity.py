@@ -2,6 +2,8 @@
 seeded inputs.  Integer/index work (colourings) and injected-noise sweeps must be bit-exact; paths
 whose operation order legitimately differs are held to a relative error of 1e-12 (the tolerance
 BASELINE.json's north_star states for FP64)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -1042,3 +1044,76 @@ def test_fused_3d_sweep_shapes_equal_per_colour(pmg, ctx, dims, noise, monkeypat
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0])
     assert out[0][1] != out[1][1]  # two code paths
+
+
+# ---- BASELINE config 5: P1 finite elements on data/lshape.msh, 17 ball observations with sigma^2 = 1e-5 as a MATLRC term ------
+# ---- (fixture: tests/golden/make_lshape.py; the oracle on the same arrays is pinned by tests/test_oracle.py) ------------------
+def _lshape(orc, nref):
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"lshape_config5_r{nref}.npz"))
+    return orc.CSR(int(d["rowptr"].size - 1), d["rowptr"], d["col"], d["val"]), d
+
+
+@pytest.mark.parametrize("nref", [0, 1])
+@pytest.mark.parametrize("pctype,sweep", [("mcgibbs", 1), ("mcgibbs", 3), ("sorgibbs", 1)])
+def test_config5_lrc_gibbs_matches_oracle(pmg, ctx, orc, nref, pctype, sweep):
+    """Unstructured operator, greedy colouring injected on both sides, LRC right-hand side and Woodbury post-correction
+    (src/pc_mcgibbs.c:130-140, src/mc_sor.c:101-112, :480-544) with an injected tape.  S = 1e5 makes the k x k system of the
+    correction ill-conditioned (cond ~ 1e6), so the sample agrees to 1e-9 rather than to the 1e-12 of a plain sweep."""
+    rng = np.random.default_rng(SEED)
+    A, d = _lshape(orc, nref)
+    n, k = A.n, 17
+    B, S, f = d["B"], d["S"], d["f"]
+    col = orc.Coloring.greedy(A)
+    mat = pmg.Mat.lrc(make_mat(pmg, ctx, A, col), B, S)
+    x = rng.standard_normal(n)
+    assert relerr(mat.mult(x), A.to_scipy() @ x + B @ (S * (B.T @ x))) < 1e-12
+    pc = pmg.PC(ctx, pctype)
+    pc.set_operator(mat)
+    if pctype == "mcgibbs":
+        pc.mcgibbs_set_sweep_type(sweep)
+    pc.setup()
+    its = 3
+    per = pc.noise_per_sample()
+    assert per == (n + k) * (2 if sweep == 3 else 1)
+    z = rng.standard_normal(its * per)
+    pc.set_noise_tape(z)
+    y = rng.standard_normal(n)
+    ref = orc.lrc_gibbs_richardson(A, B, S, f, y.copy(), its, orc.Noise.tape(z), col, 1.0, sweep)
+    pc.apply_richardson(f, y, its=its)
+    assert relerr(y, ref) < 1e-9
+    # the sweep itself (MCSORApply on the base matrix, no low-rank term) is bit-exact on this operator
+    mc = pmg.MCSOR(make_mat(pmg, ctx, A, col))
+    mc.set_sweep_type(sweep)
+    y2 = rng.standard_normal(n)
+    ref2 = orc.MCSOR(A, col, 1.0, sweep).apply(f, y2.copy())
+    mc.apply(f, y2)
+    assert np.array_equal(y2, ref2)
+
+
+def test_config5_posterior_mean_and_qoi_device_rng(pmg, ctx, orc):
+    """The reference's acceptance for this configuration (examples/benchmark: posterior sampling with -with_lr): the chain
+    mean converges to (A + B S B^T)^-1 f; PCWOODBURY with the exact sampler / solver draws independent posterior samples, so
+    the QOI of examples/benchmark/lshape.opts:11-13 has IACT 1 and the mean / variance the posterior prescribes."""
+    A, d = _lshape(orc, 0)
+    n, N = A.n, 20000
+    B, S, f, meas = d["B"], d["S"], d["f"], d["meas"]
+    mat = pmg.Mat.lrc(pmg.Mat.from_csr(ctx, A.rowptr, A.col, A.val), B, S)
+    pc = pmg.PC(ctx, "woodbury")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_woodbury_sampler": "cholsampler", "-pc_woodbury_solver": "cholesky", "-pc_b200_noise": "philox"})
+    pc.setup()
+    pc.set_qoi(meas, N, True)
+    ctx.set_seed(0xCAFE)
+    pc.apply_richardson(f, np.zeros(n), its=N)
+    q = pc.get_qoi()
+    mean_dev, var_dev, seen = pc.get_mean_var()
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    Sigma = np.linalg.inv(P)
+    mean = Sigma @ f
+    assert seen == N
+    assert np.linalg.norm(mean_dev - mean) < 4.0 * np.sqrt(np.trace(Sigma) / N)
+    assert np.abs(var_dev / np.diag(Sigma) - 1.0).max() < 6.0 * np.sqrt(2.0 / N)
+    qm, qv = meas @ mean, meas @ Sigma @ meas
+    assert abs(q.mean() - qm) < 4.0 * np.sqrt(qv / N) and abs(q.var(ddof=1) / qv - 1.0) < 5.0 * np.sqrt(2.0 / N)
+    tau, ok = pmg.iact(ctx, q)
+    assert ok and abs(tau - 1.0) < 0.15

@@ -447,3 +447,56 @@ def test_philox_grid_blocks_use_padded_index(orc):
     assert np.array_equal(orc.noise_fill(ns, 21), orc.normal_philox(0xCAFE, 0, 0, 21))
     # nx a multiple of 4: nothing changes
     assert np.array_equal(orc.noise_fill(orc.Noise.philox(7, grid=(8, 3, 1)), 24), orc.normal_philox(7, 0, 0, 24))
+
+
+# ---- BASELINE config 5: P1 finite elements on data/lshape.msh + 17 low-rank ball observations (tests/golden/make_lshape.py) ----
+def _lshape(orc, nref=0):
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"lshape_config5_r{nref}.npz"))
+    A = orc.CSR(int(d["rowptr"].size - 1), d["rowptr"], d["col"], d["val"])
+    return A, d
+
+
+def test_config5_fixture_is_the_fe_operator_of_the_reference(orc):
+    """kappa^2 M + K with natural boundary conditions (src/ms.c:86-164): symmetric positive definite, K 1 = 0 so that
+    A 1 = kappa^2 M 1 and 1^T A 1 = kappa^2 |Omega| = 25 * 3; B = M u_i and f = B (S * values) as MakeObservationMats builds them."""
+    for nref, n in ((0, 408), (1, 1549)):
+        A, d = _lshape(orc, nref)
+        assert A.n == n
+        As = A.to_scipy()
+        assert abs(As - As.T).max() < 1e-14
+        one = np.ones(n)
+        assert abs(one @ (As @ one) - 25.0 * 3.0) < 1e-10
+        assert np.linalg.eigvalsh(As.toarray()).min() > 0
+        B, S, f = d["B"], d["S"], d["f"]
+        assert B.shape == (n, 17) and np.allclose(S, 1.0 / 1e-5, rtol=1e-15) and np.allclose(f, B @ (S * d["obs_values"]), rtol=1e-14)
+        assert np.all(B >= 0) and (np.abs(B).sum(0) > 0).sum() == (13 if nref == 0 else 17)
+        # an observation functional integrates the indicator / volume: close to 1 where the ball is resolved by the mesh
+        if nref == 1:
+            assert np.all(np.abs(B.sum(0)[8:] - 1.0) < 0.35)
+        col = orc.Coloring.greedy(A)
+        assert col.violations(A) == 0 and col.ncolors <= 12
+
+
+@pytest.mark.parametrize("sweep", [1, 3])
+def test_config5_lrc_gibbs_leaves_the_posterior_invariant(orc, sweep):
+    """The LRC Gibbs sampler on the FE operator with the 17 observations: G Sigma G^T + N N^T = Sigma for
+    Sigma = (A + B S B^T)^-1, and the deterministic part converges to the posterior mean (A + B S B^T)^-1 f."""
+    A, d = _lshape(orc, 0)
+    n, k = A.n, 17
+    B, S, f = d["B"], d["S"], d["f"]
+    col = orc.Coloring.greedy(A)
+    per = (n + k) * (2 if sweep == orc.SOR_SYMMETRIC else 1)
+
+    def sample(y0, z, b=None):
+        return orc.lrc_gibbs_richardson(A, B, S, b, y0.copy(), 1, orc.Noise.tape(z), col, 1.0, sweep)
+
+    G = np.column_stack([sample(np.eye(n)[:, i], np.zeros(per)) for i in range(n)])
+    N = np.column_stack([sample(np.zeros(n), np.eye(per)[:, i]) for i in range(per)])
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    Sigma = np.linalg.inv(P)
+    assert np.abs(G @ Sigma @ G.T + N @ N.T - Sigma).max() / np.abs(Sigma).max() < 1e-9  # cond(P) ~ 1e6: sigma^2 = 1e-5
+    mean = np.linalg.solve(P, f)
+    c = sample(np.zeros(n), np.zeros(per), f)  # affine part: y' = G y + c, fixed point (I - G)^-1 c
+    fix = np.linalg.solve(np.eye(n) - G, c)
+    assert np.abs(fix - mean).max() / np.abs(mean).max() < 1e-7
