@@ -47,12 +47,12 @@ struct Args {
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-template <bool INTERIOR> struct Warp {
+template <bool INTERIOR, int TREP = 1> struct Warp {
   const Args              &a;
-  const fastnormal::Tables ft;
+  const fastnormal::TablesT<TREP> ft;
   int                      lane, c;
 
-  __device__ __forceinline__ Warp(const Args &a_, const fastnormal::Tables &ft_, int lane_, int c_) : a(a_), ft(ft_), lane(lane_), c(c_) {}
+  __device__ __forceinline__ Warp(const Args &a_, const fastnormal::TablesT<TREP> &ft_, int lane_, int c_) : a(a_), ft(ft_), lane(lane_), c(c_) {}
 
   __device__ __forceinline__ void load_row(const double *__restrict__ v, int j, double (&out)[4]) const
   {
@@ -212,10 +212,11 @@ template <bool INTERIOR> struct Warp {
   }
 };
 
-template <int WARPS, int MINB> __global__ void __launch_bounds__(WARPS * 32, MINB) box_stream_kernel(const Args a)
+// TREP: interleaved copies of the Box-Muller tables (fastnormal.cuh): fewer bank conflicts in the gathers, more to load per CTA
+template <int WARPS, int MINB, int TREP = 1> __global__ void __launch_bounds__(WARPS * 32, MINB) box_stream_kernel(const Args a)
 {
-  __shared__ fastnormal::SharedTables fts;
-  const fastnormal::Tables            ft = fastnormal::load_tables(fts);
+  __shared__ fastnormal::SharedTablesT<TREP> fts;
+  const fastnormal::TablesT<TREP>            ft = fastnormal::load_tables(fts);
   __syncthreads();
   const int lane = threadIdx.x & 31, w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= a.nitems) return;
@@ -225,11 +226,11 @@ template <int WARPS, int MINB> __global__ void __launch_bounds__(WARPS * 32, MIN
   const int  r = a.ring;
   const bool interior = a.has_const && c0 >= r && c0 + 127 <= a.nx - 1 - r && it.ja - 1 >= r && it.jb <= a.ny - 1 - r && it.ja - 2 >= 0 && it.jb + 2 <= a.ny - 1;
   if (interior) {
-    Warp<true> W(a, ft, lane, c);
+    Warp<true, TREP> W(a, ft, lane, c);
     if (a.flip) W.template run<1>(it);
     else W.template run<0>(it);
   } else {
-    Warp<false> W(a, ft, lane, c);
+    Warp<false, TREP> W(a, ft, lane, c);
     if (a.flip) W.template run<1>(it);
     else W.template run<0>(it);
   }
