@@ -1483,7 +1483,7 @@ struct BoxOp final : GridOp {
     using namespace boxstream;
     constexpr int WARPS = 4;
     static const int mb_env = std::getenv("PMG_BOX_STREAM_MINB") ? std::atoi(std::getenv("PMG_BOX_STREAM_MINB")) : 4;
-auto          kern  = mb_env == 6 ? box_stream_kernel<WARPS, 6> : mb_env == 5 ? box_stream_kernel<WARPS, 5> : box_stream_kernel<WARPS, 4>; // replicated Box-Muller tables (TREP 2 / 4 / 8) measured: no gain here, the CTAs are short-lived
+    auto          kern  = mb_env == 6 ? box_stream_kernel<WARPS, 6> : mb_env == 5 ? box_stream_kernel<WARPS, 5> : box_stream_kernel<WARPS, 4>; // replicated Box-Muller tables (TREP 2 / 4 / 8) measured: no gain here, the CTAs are short-lived
     if (!nsitems) { // one resident wave: bands sized from the kernel's occupancy
       int occ = 0;
       PMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, 0));
