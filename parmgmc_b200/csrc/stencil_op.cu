@@ -462,6 +462,97 @@ template <int DIM> __global__ void __launch_bounds__(256) box_sweep_kernel(Geom 
   x[idx]           = fma(id, sum, t0);
 }
 
+// Two colours of the 27-point sweep that differ only in the x parity (c = ci + 2 cj + 4 ck and c + 1) live on the SAME grid rows,
+// and no other row of their nine-row neighbourhood changes while they are swept.  One block per grid row stages the nine rows
+// in shared memory (coalesced, each value fetched once for both colours), updates the nodes of the first colour, publishes them
+// in the staged centre row, and updates the second colour from it: 4 launches per sweep instead of 8, unit-stride global loads
+// instead of stride-2 gathers, and one Philox / Box-Muller call per node PAIR (columns 2t, 2t+1 are the cos / sin halves of one
+// generator call, philox.cuh).  Arithmetic per node is box_sweep_kernel<3>'s, fma for fma.  Undistributed levels with rows of at
+// most 512 nodes.
+__global__ void __launch_bounds__(256) box_pair_sweep3_kernel(Geom g, int cjk, int backward, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ idiag, const double *__restrict__ sqrtdiag, double omo,
+                                                              const double *__restrict__ b, double *__restrict__ x, NoiseArgs na)
+{
+  extern __shared__ double prow[]; // [9][n0 + 2]: row (dj + 1) + 3 (dk + 1), column i at index i + 1
+  const int j = 2 * (int)blockIdx.x + (cjk & 1), k = 2 * (int)blockIdx.y + (cjk >> 1);
+  if (j >= g.n1 || k >= g.n2) return;
+  const int n0 = (int)g.n0, ldr = n0 + 2;
+  { // all 18 loads of a thread are issued before the first store (2 blockDim.x >= n0: two elements per thread and row)
+    const int i0 = threadIdx.x, i1 = threadIdx.x + blockDim.x;
+    double    v[18];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int     jj = j + r % 3 - 1, kk = k + r / 3 - 1;
+      const bool    ok = jj >= 0 && jj < g.n1 && kk >= 0 && kk < g.n2; // absent rows are never read
+      const double *src = x + g.n0 * ((int64_t)(ok ? jj : j) + g.n1 * (int64_t)(ok ? kk : k));
+      v[2 * r]     = i0 < n0 ? src[i0] : 0.0;
+      v[2 * r + 1] = i1 < n0 ? src[i1] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      if (i0 < n0) prow[r * ldr + 1 + i0] = v[2 * r];
+      if (i1 < n0) prow[r * ldr + 1 + i1] = v[2 * r + 1];
+    }
+  }
+  __syncthreads();
+  const int     t = threadIdx.x;
+  const int64_t row0 = g.n0 * ((int64_t)j + g.n1 * (int64_t)k);
+  // the pair's two normals: one generator call (rows 4q, 4q+1 -> (w0, w1), rows 4q+2, 4q+3 -> (w2, w3); cos for the even row)
+  double z0 = 0.0, z1 = 0.0;
+  if (2 * t < n0) {
+    if (na.mode == PMG_NOISE_INJECTED) {
+      z0 = na.tape[row0 + 2 * t];
+      if (2 * t + 1 < n0) z1 = na.tape[row0 + 2 * t + 1];
+    } else if (na.mode == PMG_NOISE_PHILOX) {
+      const uint64_t nid = (uint64_t)(((int64_t)k * g.n1 + j) * ((g.n0 + 3) & ~(int64_t)3) + 2 * t);
+      uint32_t       w0, w1, w2, w3;
+      philox4x32_10((uint32_t)(nid >> 2), (uint32_t)(nid >> 34), (uint32_t)na.call, (uint32_t)(na.call >> 32), (uint32_t)na.seed, (uint32_t)(na.seed >> 32), w0, w1, w2, w3);
+      if (nid & 2) box_muller_32(w2, w3, z0, z1);
+      else box_muller_32(w0, w1, z0, z1);
+    }
+  }
+  auto node = [&](int p) {
+    const int i = 2 * t + p;
+    if (i >= n0) return;
+    const int64_t idx = row0 + i;
+    const bool    interior = box_interior<3>(g, bc, i, j, k);
+    const double  sq = interior ? bc.sqrtdiag : sqrtdiag[idx], id = interior ? bc.idiag : idiag[idx];
+    const double  bv = b ? b[idx] : 0.0;
+    double        sum = na.mode == PMG_NOISE_NONE ? bv : __dadd_rn(__dmul_rn(p ? z1 : z0, sq), bv); // noisy_rhs_id
+    if (interior) {
+#pragma unroll
+      for (int s = 0; s < 27; ++s) {
+        if (s == 13) continue;
+        const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+        sum          = fma(-bc.c[s], prow[((dj + 1) + 3 * (dk + 1)) * ldr + 1 + i + di], sum);
+      }
+    } else {
+      // the one or two boundary nodes of an interior row sit in a warp whose other lanes wait for them: all coefficient loads
+      // are issued before the first use (one memory latency instead of 26 dependent ones)
+      double cf[27];
+#pragma unroll
+      for (int s = 0; s < 27; ++s) {
+        const int  di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+        const bool ex = s != 13 && i + di >= 0 && i + di < n0 && j + dj >= 0 && j + dj < g.n1 && k + dk >= 0 && k + dk < g.n2;
+        cf[s]         = ex ? coef[(int64_t)s * stride + idx] : 0.0;
+      }
+#pragma unroll
+      for (int s = 0; s < 27; ++s) {
+        if (s == 13) continue;
+        const int  di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+        const bool ex = i + di >= 0 && i + di < n0 && j + dj >= 0 && j + dj < g.n1 && k + dk >= 0 && k + dk < g.n2;
+        if (ex) sum = fma(-cf[s], prow[((dj + 1) + 3 * (dk + 1)) * ldr + 1 + i + di], sum); // structurally absent entries are skipped
+      }
+    }
+    const double t0 = __dmul_rn(omo, prow[4 * ldr + 1 + i]);
+    const double xn = fma(id, sum, t0);
+    x[idx]                = xn;
+    prow[4 * ldr + 1 + i] = xn;
+  };
+  node(backward ? 1 : 0);
+  __syncthreads();
+  node(backward ? 0 : 1);
+}
+
 template <int DIM, bool RESIDUAL> __global__ void __launch_bounds__(256) box_apply_kernel(Geom g, const double *__restrict__ coef, int64_t stride, BoxConst bc, const double *__restrict__ b, const double *__restrict__ x, const double *__restrict__ glo, const double *__restrict__ ghi, double *__restrict__ out)
 {
   int64_t i, j, k, idx;
@@ -1445,6 +1536,19 @@ struct BoxOp final : GridOp {
       k.sqrtdiag     = std::sqrt(std::fabs(d)) * std::sqrt((2 - co.omega) / co.omega);
     }
     const int  nc = ncolors();
+    if (g.dim == 3 && !parallel && g.n0 <= 512 && (g.n2 + 1) / 2 <= 65535 && !std::getenv("PMG_NO_BOX_PAIR")) { // colour pairs (ci = 0, 1) in one launch
+      const unsigned bx = (unsigned)((((g.n0 + 1) / 2) + 31) / 32 * 32);
+      const dim3     grid((unsigned)((g.n1 + 1) / 2), (unsigned)((g.n2 + 1) / 2));
+      const size_t   sm = (size_t)9 * (size_t)(g.n0 + 2) * sizeof(double);
+      for (int s = 0; s < 4; ++s) {
+        const int p = dir == PMG_SOR_FORWARD_SWEEP ? s : 3 - s;
+        box_pair_sweep3_kernel<<<grid, bx, sm, ctx->stream>>>(g, p, dir == PMG_SOR_FORWARD_SWEEP ? 0 : 1, coef.p, g.nl, k, co.idiag.p, co.sqrtdiag.p, 1.0 - co.omega, b, y, na);
+        PMG_CUDA(cudaGetLastError());
+        ctx->launches++;
+      }
+      ctx->dof_updates += g.nl;
+      return 0;
+    }
     const Plan pl = g.dim == 2 ? box_colour_plan<2>(g) : box_colour_plan<3>(g);
     PMG_PLAN_CHECK(pl);
     // A colour lives on the units (grid rows / planes) of ONE parity of the slowest dimension, and everything it reads from a

@@ -1117,3 +1117,37 @@ def test_config5_posterior_mean_and_qoi_device_rng(pmg, ctx, orc):
     assert abs(q.mean() - qm) < 4.0 * np.sqrt(qv / N) and abs(q.var(ddof=1) / qv - 1.0) < 5.0 * np.sqrt(2.0 / N)
     tau, ok = pmg.iact(ctx, q)
     assert ok and abs(tau - 1.0) < 0.15
+
+
+# ---- 27-point Galerkin levels: two colours per launch (box_pair_sweep3_kernel) against one launch per colour ----------------
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((65, 65, 65), 4, {}),
+    ((33, 41, 25), 3, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.3}),
+    ((129, 17, 33), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+])
+def test_box_colour_pair_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, noise, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for pair in (True, False):
+        if pair:
+            monkeypatch.delenv("PMG_NO_BOX_PAIR", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_BOX_PAIR", "1")
+        lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.8)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(7).standard_normal(2 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(31)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
