@@ -180,6 +180,10 @@ int pmg_autocorrelation(pmg_ctx ctx, int64_t n, const double *x_host, double *ac
 int pmg_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, double *acf_host_or_null, int *valid);
 
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z_host);
+/* host-side work list of the fused 3D sweep (csrc/sweep3d.cuh; the tiling that replaces the colour loops of src/mc_sor.c:257-285
+ * on a 7-point grid operator): `count` items of five ints (strip of 120 columns, first row, first plane, end plane, narrow-strip flag).
+ * Needs no device; the CPU tests check that the tiles cover the owned planes exactly once.  items = NULL only counts. */
+int pmg_plan_sweep3d(int64_t nx, int64_t ny, int64_t nz, int64_t slo, int64_t shi, int bz, int nw, int32_t *items, int64_t capacity, int64_t *count);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------- */
 /* average device time [ms] and launch count of the kernels the last apply_richardson* call issued */

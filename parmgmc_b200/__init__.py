@@ -64,6 +64,7 @@ SIGNATURES = {
     "pmg_mat_create_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
+    "pmg_plan_sweep3d": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "pmg_pc_set_qoi": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int]),
     "pmg_pc_get_qoi": (C.c_int, [_vp, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "pmg_pc_get_mean_var": (C.c_int, [_vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
@@ -233,6 +234,16 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib().pmg_comm_unique_id(buf))
     return buf.raw
+
+
+def plan_sweep3d(nx, ny, nz, slab=None, bz=64, nw=16):
+    """Work list of the fused 3D sweep as an (items, 5) int32 array: strip, first row, first plane, end plane, narrow flag."""
+    slo, shi = slab if slab is not None else (0, nz)
+    cnt = C.c_int64()
+    _check(lib().pmg_plan_sweep3d(nx, ny, nz, slo, shi, bz, nw, None, 0, C.byref(cnt)))
+    out = np.empty((cnt.value, 5), np.int32)
+    _check(lib().pmg_plan_sweep3d(nx, ny, nz, slo, shi, bz, nw, out.ctypes.data, cnt.value, C.byref(cnt)))
+    return out
 
 
 def autocorrelation(ctx: "Context", x):

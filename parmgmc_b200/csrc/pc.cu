@@ -1458,6 +1458,20 @@ int pmg_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, double *
   return device_iact(ctx, n, x_host, tau, acf_host_or_null, valid);
 }
 
+// host-side work list of the fused 3D sweep: no device needed (tests/test_abi_cpu.py checks the tiling)
+int pmg_plan_sweep3d(int64_t nx, int64_t ny, int64_t nz, int64_t slo, int64_t shi, int bz, int nw, int32_t *items, int64_t capacity, int64_t *count)
+{
+  if (nx < 1 || ny < 1 || nz < 1 || slo < 0 || shi > nz || slo >= shi || bz < 1 || nw < 3 || !count) PMG_FAIL(PMG_ERR_ARG, "pmg_plan_sweep3d: bad geometry");
+  std::vector<int32_t> flat;
+  sweep3d_plan(nx, ny, nz, slo, shi, bz, nw, true, 4, flat);
+  *count = (int64_t)(flat.size() / 5);
+  if (items) {
+    if (capacity < *count) PMG_FAIL(PMG_ERR_ARG, "pmg_plan_sweep3d: %lld items, capacity %lld", (long long)*count, (long long)capacity);
+    std::memcpy(items, flat.data(), flat.size() * sizeof(int32_t));
+  }
+  return PMG_OK;
+}
+
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z)
 {
   pmg_stale("pmg_normal_fill");

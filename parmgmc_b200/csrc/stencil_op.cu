@@ -32,6 +32,53 @@ int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, cons
 int comm_allgather_i64(pmg_ctx ctx, const int64_t *local_host, int count, int64_t *all_host);
 int comm_allgatherv(pmg_ctx ctx, const double *send, double *recv, const int64_t *counts, const int64_t *displs, cudaStream_t stream);
 
+// Work list of the fused 3D sweep (sweep3d.cuh), host only (also exported as pmg_plan_sweep3d for the CPU tests): items of
+// five ints (strip, ya, ka, kb, narrow).  Strips of 120 output columns; tiles of nw - 2 output rows (narrow last strip of at
+// most 56 columns: 2 nw - 2 rows, 16 lanes per grid row); bands along z: `thin` planes where a plane lacks a z neighbour (the
+// table-driven tiles), equal bands of at most bz planes between.  Order: edge tiles, interior tiles, thin-band tiles.
+void sweep3d_plan(int64_t n0, int64_t n1, int64_t n2, int64_t slo, int64_t shi, int bz, int nw, bool allow_narrow, int thin_planes, std::vector<int32_t> &out)
+{
+  constexpr int STRIP = sweep3d::STRIP_OUT;
+  const int     nstrips = (int)((n0 + STRIP - 1) / STRIP), ty = nw - 2, ty16 = 2 * nw - 2;
+  const int64_t last_w = n0 - (int64_t)(nstrips - 1) * STRIP; // columns of the last strip
+  const bool    narrow = allow_narrow && last_w <= 56 && n1 >= ty16; // 14 output lanes of 4 columns
+  std::vector<std::pair<int64_t, int64_t>> bands;
+  {
+    const int64_t thin = std::max(2, thin_planes);
+    int64_t       lo = slo, hi = shi;
+    const bool    edge_lo = slo < 2, edge_hi = shi > n2 - 2; // the slab holds the first / last planes of the grid
+    if (shi - slo <= 2 * thin + 2) {
+      for (int64_t k = lo; k < hi; k += bz) bands.push_back({k, std::min<int64_t>(k + bz, hi)});
+    } else {
+      if (edge_lo) { bands.push_back({lo, lo + thin}); lo += thin; }
+      if (edge_hi) hi -= thin;
+      const int64_t nb = (hi - lo + bz - 1) / bz;
+      for (int64_t i = 0; i < nb; ++i) bands.push_back({lo + (hi - lo) * i / nb, lo + (hi - lo) * (i + 1) / nb});
+      if (edge_hi) bands.push_back({hi, shi});
+    }
+  }
+  std::vector<int32_t> slow, fast, small;
+  for (const auto &bd : bands) {
+    const int64_t k = bd.first, kb = bd.second;
+    const bool    kin = k - 1 >= 1 && kb <= n2 - 2; // sweep3d_kernel's zconst test (the slab's tensors always hold planes k-2 and kb+1)
+    const bool    thinband = kb - k < bz / 2;
+    for (int s = 0; s < nstrips; ++s) {
+      const bool nar  = narrow && kin && s == nstrips - 1;
+      const int  step = nar ? ty16 : ty;
+      for (int64_t ya = 0; ya < n1; ya += step) {
+        const int  c0 = s * STRIP - 4;
+        const bool interior = kin && !nar && c0 >= 1 && c0 + 127 <= n0 - 2 && ya - 1 >= 1 && ya + nw - 2 <= n1 - 2;
+        std::vector<int32_t> &dst = thinband ? small : interior ? fast : slow;
+        const int32_t         it[5] = {s, (int32_t)ya, (int32_t)k, (int32_t)kb, nar ? 1 : 0};
+        dst.insert(dst.end(), it, it + 5);
+      }
+    }
+  }
+  out = slow;
+  out.insert(out.end(), fast.begin(), fast.end());
+  out.insert(out.end(), small.begin(), small.end());
+}
+
 namespace {
 
 struct Geom {
@@ -1143,47 +1190,14 @@ struct LapOp final : GridOp {
   int                   nitems3 = 0, items3_bz = 0, items3_nw = 0;
   int build_items3(int bz, int NW3) // NW3 warps per CTA tile: NW3 - 2 output rows + 2 halo rows (narrow strips: 2 NW3 - 2 + 2)
   {
-    using sweep3d::Item;
-    const int         nstrips = (int)((g.n0 + sweep3d::STRIP_OUT - 1) / sweep3d::STRIP_OUT), ty = NW3 - 2, ty16 = 2 * NW3 - 2;
-    const int64_t     last_w  = g.n0 - (int64_t)(nstrips - 1) * sweep3d::STRIP_OUT; // columns of the last strip
     static const bool narrow_env = std::getenv("PMG_SW3_NONARROW") == nullptr;
     static const int  thin_env   = std::getenv("PMG_SW3_THIN") ? std::atoi(std::getenv("PMG_SW3_THIN")) : 4;
-    const bool        narrow = narrow_env && last_w <= 56 && g.n1 >= ty16; // 14 output lanes of 4 columns
-    // bands along z: thin bands where a plane lacks a z neighbour (the table-driven tiles), equal bands of at most bz planes between
-    std::vector<std::pair<int64_t, int64_t>> bands;
-    {
-      const int64_t thin = std::max(2, thin_env);
-      int64_t       lo = g.slo, hi = g.shi;
-      const bool    edge_lo = g.slo < 2, edge_hi = g.shi > g.n2 - 2; // the slab holds the first / last planes of the grid
-      if (g.shi - g.slo <= 2 * thin + 2) {
-        for (int64_t k = lo; k < hi; k += bz) bands.push_back({k, std::min<int64_t>(k + bz, hi)});
-      } else {
-        if (edge_lo) { bands.push_back({lo, lo + thin}); lo += thin; }
-        if (edge_hi) hi -= thin;
-        const int64_t nb = (hi - lo + bz - 1) / bz;
-        for (int64_t i = 0; i < nb; ++i) bands.push_back({lo + (hi - lo) * i / nb, lo + (hi - lo) * (i + 1) / nb});
-        if (edge_hi) bands.push_back({hi, g.shi});
-      }
-    }
-    std::vector<Item> slow, fast, small;
-    for (const auto &bd : bands) {
-      const int64_t k = bd.first, kb = bd.second;
-      const bool    kin = k - 1 >= 1 && kb <= g.n2 - 2; // sweep3d_kernel's zconst test (the slab's tensors always hold planes k-2 and kb+1)
-      const bool    thinband = kb - k < bz / 2;
-      for (int s = 0; s < nstrips; ++s) {
-        const bool nar  = narrow && kin && s == nstrips - 1;
-        const int  step = nar ? ty16 : ty;
-        for (int64_t ya = 0; ya < g.n1; ya += step) {
-          const int  c0 = s * sweep3d::STRIP_OUT - 4;
-          const bool interior = kin && !nar && c0 >= 1 && c0 + 127 <= g.n0 - 2 && ya - 1 >= 1 && ya + NW3 - 2 <= g.n1 - 2;
-          (thinband ? small : interior ? fast : slow).push_back(Item{s, (int)ya, (int)k, (int)kb, nar ? 1 : 0});
-        }
-      }
-    }
-    slow.insert(slow.end(), fast.begin(), fast.end());
-    slow.insert(slow.end(), small.begin(), small.end());
-    nitems3 = (int)slow.size();
-    PMG_TRY(items3.upload(slow, ctx->stream));
+    std::vector<int32_t> flat;
+    sweep3d_plan(g.n0, g.n1, g.n2, g.slo, g.shi, bz, NW3, narrow_env, thin_env, flat);
+    std::vector<sweep3d::Item> all(flat.size() / 5);
+    for (size_t q = 0; q < all.size(); ++q) all[q] = sweep3d::Item{flat[5 * q], flat[5 * q + 1], flat[5 * q + 2], flat[5 * q + 3], flat[5 * q + 4]};
+    nitems3 = (int)all.size();
+    PMG_TRY(items3.upload(all, ctx->stream));
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
     items3_bz = bz;
     items3_nw = NW3;

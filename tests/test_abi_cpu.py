@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import parmgmc_b200 as pmg
@@ -67,3 +68,45 @@ def test_petsc_shim_builds_and_fails_loudly_without_device():
         pytest.skip("GPU present: the run itself is tests/test_shim_host.py")
     r = subprocess.run([exe, "mcgibbs", "10", "0.02"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+# ---- host logic of the fused 3D sweep: the work list (pmg_plan_sweep3d; csrc/stencil_op.cu sweep3d_plan) -----------------------
+@pytest.mark.parametrize("dims,slab,bz,nw", [
+    ((512, 512, 512), None, 64, 16),      # config 3: 4 full strips + a 32-column narrow strip, thin z-edge bands
+    ((513, 513, 513), None, 64, 16),      # config 4's per-GPU grid
+    ((150, 40, 48), (24, 48), 64, 16),    # upper slab of a 2-rank split: thin band only at the grid's last planes
+    ((150, 40, 48), (0, 24), 64, 16),
+    ((57, 31, 12), None, 64, 16),         # last strip wider than 56 columns: no narrow tiles
+    ((36, 30, 5), None, 64, 16),          # short in z: plain bands
+    ((50, 64, 16), None, 64, 8),
+])
+def test_sweep3d_work_list_tiles_the_slab_exactly_once(dims, slab, bz, nw):
+    import parmgmc_b200 as pmg
+    nx, ny, nz = dims
+    slo, shi = slab if slab else (0, nz)
+    items = pmg.plan_sweep3d(nx, ny, nz, slab, bz, nw)
+    assert items.shape[1] == 5 and len(items) > 0
+    cover = np.zeros((shi - slo, ny, (nx + 119) // 120), np.int32)
+    nstrips = (nx + 119) // 120
+    for s, ya, ka, kb, narrow in items:
+        rows = (2 * nw - 2) if narrow else (nw - 2)
+        assert 0 <= s < nstrips and 0 <= ya < ny and slo <= ka < kb <= shi
+        if narrow:  # only the last, short strip, and only where every plane touched has both z neighbours
+            assert s == nstrips - 1 and nx - 120 * s <= 56 and ka - 1 >= 1 and kb <= nz - 2
+        cover[ka - slo:kb - slo, ya:min(ya + rows, ny), s] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    # planes without a z neighbour sit in bands of at most 4 planes when the slab is long enough
+    if shi - slo > 10:
+        for s, ya, ka, kb, narrow in items:
+            if ka < 2 or kb > nz - 2:
+                assert kb - ka <= 4
+    if (nx % 120) and nx - 120 * (nstrips - 1) <= 56 and ny >= 2 * nw - 2 and shi - slo > 10:
+        assert items[:, 4].sum() > 0
+
+
+def test_sweep3d_work_list_rejects_bad_geometry():
+    import parmgmc_b200 as pmg
+    with pytest.raises(pmg.PMGError):
+        pmg.plan_sweep3d(64, 64, 64, (10, 5))
+    with pytest.raises(pmg.PMGError):
+        pmg.plan_sweep3d(64, 64, 64, None, 64, 2)
