@@ -500,3 +500,21 @@ def test_config5_lrc_gibbs_leaves_the_posterior_invariant(orc, sweep):
     c = sample(np.zeros(n), np.zeros(per), f)  # affine part: y' = G y + c, fixed point (I - G)^-1 c
     fix = np.linalg.solve(np.eye(n) - G, c)
     assert np.abs(fix - mean).max() / np.abs(mean).max() < 1e-7
+
+
+def test_config5_woodbury_exact_sampler_identity(orc):
+    """PCWOODBURY (src/woodbury.c:21-86, :259-286) with an exact sampler on A: y_s ~ N(A^-1 w, A^-1), w = f + B sqrt(S) eta, then
+    y = y_s - G B^T y_s with G = C (S^-1 + B^T C)^-1, C = A^-1 B.  Mean and covariance of y must be those of the posterior
+    N((A + B S B^T)^-1 f, (A + B S B^T)^-1): the identity the construction rests on, checked on the config-5 operator."""
+    A, d = _lshape(orc, 0)
+    n = A.n
+    Ad, B, S, f = A.to_scipy().toarray(), d["B"], d["S"], d["f"]
+    Ainv = np.linalg.inv(Ad)
+    Cm = Ainv @ B
+    G = Cm @ np.linalg.inv(np.diag(1.0 / S) + B.T @ Cm)
+    T = np.eye(n) - G @ B.T
+    cov_s = Ainv + Cm @ np.diag(S) @ Cm.T  # A^-1 (noise of the sampler) + A^-1 B S B^T A^-1 (the k extra draws)
+    P = Ad + B @ np.diag(S) @ B.T
+    Sigma = np.linalg.inv(P)
+    assert np.abs(T @ cov_s @ T.T - Sigma).max() / np.abs(Sigma).max() < 1e-8
+    assert np.abs(T @ (Ainv @ f) - Sigma @ f).max() / np.abs(Sigma @ f).max() < 1e-8
