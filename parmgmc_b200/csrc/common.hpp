@@ -177,6 +177,10 @@ struct LrcData {
 // An operator on one level on one device.
 struct LevelOp {
   pmg_ctx ctx = nullptr;
+  // Row stride of this level's V-cycle vectors (b, x) when the cycle keeps them PITCHED (box2d.cuh: a Galerkin level between
+  // two one-pass levels); 0: natural layout.  Set by the V-cycle set-up, read by the kernels that write / read the level's
+  // vectors from the level above (fused restriction / prolongation).
+  int64_t level_pitch = 0;
   virtual ~LevelOp() {}
   virtual int64_t n() const    = 0; // local rows
   virtual int64_t nglobal() const { return n(); }
@@ -200,6 +204,8 @@ struct LevelOp {
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
+  virtual bool    box2_capable() const { return false; } // a Galerkin level that can run on the one-pass kernels once its vectors are pitched
+  virtual int64_t box2_pitch() const { return 0; }
   virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
   virtual bool fused_tape_ok() const { return true; } // fused_sweep can take an injected noise tape
   virtual bool fused_null_xin_ok() const { return true; } // fused_sweep accepts xin = NULL for a zero iterate

@@ -528,6 +528,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   // ping-pongs between v.x and v.x2, so the current one is always v.x.p
   const bool bstream = !fused && l > 0 && v.smp.kind != KIND_CHOL && v.x2.p && x == v.x.p && v.op->stream_ok() &&
                        (noise_mode(pc) != PMG_NOISE_INJECTED || v.op->fused_tape_ok());
+  if (!fused && l > 0 && pc->lv[l - 1].op->level_pitch) PMG_FAIL(PMG_ERR_ORDER, "gamgmc: level %d keeps pitched vectors but level %d does not run the fused kernels (path switches must be set before pmg_pc_setup)", l - 1, l);
   if (bstream) {
     MgLevel         &c = pc->lv[l - 1];
     std::vector<int> dirs;
@@ -765,6 +766,22 @@ static int gamgmc_setup(pmg_pc pc)
       Bl.swap(Bc);
     }
   }
+  const std::string cyc = pc->get("pc_b200_cycle", "direct");
+  if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
+  pc->direct_cycle = cyc == "direct";
+  const char   *tm_env   = std::getenv("PMG_TAIL_MAX");
+  const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "20000").c_str());
+  // Galerkin levels that run on the one-pass kernels (box2d.cuh) keep their vectors PITCHED: a chain of levels below a fused
+  // finest level, down to the first level that is small enough for the one-launch tail (or cannot run the kernels)
+  for (int l = 0; l < L - 1; ++l) pc->lv[l].op->level_pitch = 0;
+  if (pc->direct_cycle && L > 2 && !top->lrc_data() && pc->get("gamgmc_mg_levels_pc_type", "sorgibbs") != "cholsampler") {
+    bool chain = pc->lv[L - 1].op->fused_mg_ok();
+    for (int l = L - 2; l >= 1 && chain; --l) {
+      LevelOp *o = pc->lv[l].op;
+      chain      = o->box2_capable() && o->n() > tail_max;
+      if (chain) o->level_pitch = o->box2_pitch();
+    }
+  }
   // samplers: defaults of src/pc_gamgmc.c:305-349 (levels: richardson + sorgibbs, 1 it; coarse: cholsampler)
   for (int l = 0; l < L; ++l) {
     MgLevel          &v      = pc->lv[l];
@@ -778,12 +795,21 @@ static int gamgmc_setup(pmg_pc pc)
     if (l < L - 1) PMG_TRY(apply_coloring_policy(pc, v.op, false));
     PMG_TRY(setup_level_sampler(ctx, v.smp, v.op));
     const size_t n = (size_t)v.op->n();
-    if (l < L - 1) {
+    const bool   pitched_level = l < L - 1 && v.op->level_pitch != 0;
+    if (pitched_level) { // pad columns are read as ordinary elements by the TMA and must stay zero
+      const size_t fs = (size_t)v.op->fused_size();
+      PMG_TRY(v.b.alloc(fs));
+      PMG_TRY(v.x.alloc(fs));
+      PMG_TRY(v.x2.alloc(fs));
+      PMG_TRY(v.b.zero(ctx->stream));
+      PMG_TRY(v.x.zero(ctx->stream));
+      PMG_TRY(v.x2.zero(ctx->stream));
+    } else if (l < L - 1) {
       PMG_TRY(v.b.alloc(n));
       PMG_TRY(v.x.alloc(n));
     }
-    if (l > 0) PMG_TRY(v.r.alloc(n));
-    if (l > 0 && l < L - 1 && v.smp.kind != KIND_CHOL && v.op->stream_ok()) PMG_TRY(v.x2.alloc(n));
+    if (l > 0 && !pitched_level) PMG_TRY(v.r.alloc(n));
+    if (l > 0 && l < L - 1 && !pitched_level && v.smp.kind != KIND_CHOL && v.op->stream_ok()) PMG_TRY(v.x2.alloc(n));
     if (l > 0 && l == L - 1 && (v.op->fused_mg_ok() || v.op->fused_smooth_ok()) && v.smp.kind != KIND_CHOL) {
       if (v.op->fused_smooth_ok()) { // the residual lives in the pitched layout too
         PMG_TRY(v.r.alloc((size_t)v.op->fused_size()));
@@ -798,15 +824,10 @@ static int gamgmc_setup(pmg_pc pc)
       PMG_TRY(pc->pit_b.zero(ctx->stream));
     }
   }
-  const std::string cyc = pc->get("pc_b200_cycle", "direct");
-  if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
-  pc->direct_cycle = cyc == "direct";
   // the coarse tail: the largest lt < L-1 such that levels 0..lt are whole-grid stencil-array levels on this device, level 0
   // is the dense gemv sampler with one iteration, and level lt has at most -pc_b200_tail_max_n nodes
   pc->tail_top = -1;
   {
-    const char   *tm_env   = std::getenv("PMG_TAIL_MAX");
-    const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "20000").c_str());
     MgLevel      &c0       = pc->lv[0];
     if (pc->direct_cycle && L >= 3 && tail_max > 0 && c0.smp.kind == KIND_CHOL && c0.smp.its == 1 && c0.smp.chol.use_gemv && grid_tail_level_ok(c0.op)) {
       int lt = 0;

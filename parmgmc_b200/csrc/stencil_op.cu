@@ -26,6 +26,7 @@
 #include "sweep2d.cuh"
 #include "sweep3d.cuh"
 #include "box_stream.cuh"
+#include "box2d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -657,6 +658,22 @@ template <int DIM> __global__ void box_uniform_kernel(Geom g, const double *__re
   constexpr int NST = DIM == 2 ? 9 : 27;
   bool          same = true;
   for (int s = 0; s < NST; ++s) same = same && (__double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(coef[(int64_t)s * stride + ref_idx]));
+  if (!same) atomicAdd(mismatches, 1ull);
+}
+
+// boundary classes of a 2D stencil-array level (box2d.cuh): class of a node = (row class, column class), each first /
+// interior / last; counts the nodes whose nine coefficients differ bitwise from their class representative's
+struct BoxClassTab {
+  double c[9][9]; // [3 row class + column class][stencil entry]
+};
+__global__ void box_class_kernel(Geom g, const double *__restrict__ coef, int64_t stride, BoxClassTab t, unsigned long long *__restrict__ mismatches)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  const int64_t i = idx % g.n0, j = idx / g.n0;
+  const int     cc = i == 0 ? 0 : (i == g.n0 - 1 ? 2 : 1), rc = j == 0 ? 0 : (j == g.n1 - 1 ? 2 : 1);
+  bool          same = true;
+  for (int s = 0; s < 9; ++s) same = same && (__double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(t.c[3 * rc + cc][s]));
   if (!same) atomicAdd(mismatches, 1ull);
 }
 
@@ -1369,12 +1386,13 @@ struct LapOp final : GridOp {
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;
     a.xout  = xout;
-    a.xc = nullptr; a.cnx = a.cny = 0;
+    a.xc = nullptr; a.cnx = a.cny = a.cpitch = 0;
     if (xc) { // prolongation fused into the sweep: the coarse level is a whole grid on this device
       int     cd;
       int64_t cn[3];
       if (!coarse || !coarse->structured(cd, cn) || parallel) PMG_FAIL(PMG_ERR_SUP, "fused prolongation needs a structured coarse level on one device");
       a.xc = xc; a.cnx = (int)cn[0]; a.cny = (int)cn[1];
+      a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
     }
     a.tape  = na.tape;
     a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega;
@@ -1436,12 +1454,14 @@ struct LapOp final : GridOp {
     Args a;
     a.g = Geom2{(int)g.n0, (int)g.n1, (int)g.slo, (int)g.shi};
     a.gc = a.g;
+    a.cpitch = a.g.nx;
     if (coarse) {
       int     cd;
       int64_t cn[3];
       coarse->structured(cd, cn);
       auto *cg = static_cast<GridOp *>(coarse);
       a.gc     = Geom2{(int)cn[0], (int)cn[1], (int)cg->g.slo, (int)cg->g.shi};
+      a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
     }
     static const int by_env = std::getenv("PMG_STREAM_BY") ? std::atoi(std::getenv("PMG_STREAM_BY")) : 0;
     int by = by_env > 0 ? by_env : 64;
@@ -1621,7 +1641,7 @@ struct BoxOp final : GridOp {
     if (std::getenv("PMG_NO_BOX_STREAM")) return false;
     const char   *mn    = std::getenv("PMG_BOX_STREAM_MIN"); // smaller levels are launch-latency bound either way
     const int64_t min_n = mn ? std::atoll(mn) : 20000;
-    return g.dim == 2 && !parallel && g.slo == 0 && g.shi == g.n1 && g.n0 >= 16 && g.n1 >= 8 && g.nl >= min_n && g.nl < ((int64_t)1 << 31);
+    return !level_pitch && g.dim == 2 && !parallel && g.slo == 0 && g.shi == g.n1 && g.n0 >= 16 && g.n1 >= 8 && g.nl >= min_n && g.nl < ((int64_t)1 << 31);
   }
   int stream_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na) override
   {
@@ -1675,6 +1695,146 @@ struct BoxOp final : GridOp {
     return 0;
   }
 
+  // ---- one-pass TMA kernels (box2d.cuh): 2D, one device, PITCHED level vectors (LevelOp::level_pitch) ----
+  bool        classes_ok = false;
+  BoxClassTab cls_tab;
+  int         detect_classes()
+  {
+    classes_ok = false;
+    if (g.dim != 2 || parallel || g.slo != 0 || g.shi != g.n1 || g.n0 < 3 || g.n1 < 3 || g.nl >= ((int64_t)1 << 31)) return 0;
+    const int64_t ri[3] = {0, 1, g.n0 - 1}, rj[3] = {0, 1, g.n1 - 1};
+    for (int rc = 0; rc < 3; ++rc)
+      for (int cc = 0; cc < 3; ++cc)
+        for (int s = 0; s < 9; ++s) PMG_CUDA(cudaMemcpyAsync(&cls_tab.c[3 * rc + cc][s], coef.p + (size_t)s * g.nl + (size_t)(ri[cc] + g.n0 * rj[rc]), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevBuf<unsigned long long> cnt;
+    PMG_TRY(cnt.alloc(1));
+    PMG_TRY(cnt.zero(ctx->stream));
+    box_class_kernel<<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, cls_tab, cnt.p);
+    PMG_CUDA(cudaGetLastError());
+    unsigned long long bad = 1;
+    PMG_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    classes_ok = bad == 0;
+    return 0;
+  }
+  int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
+  // the level can run on the one-pass kernels; whether it does is the V-cycle's decision (it must keep the vectors pitched)
+  bool box2_capable() const override { return classes_ok && g.n0 >= 16 && g.n1 >= 8 && !std::getenv("PMG_NO_BOX2"); }
+  int64_t box2_pitch() const override { return pitch(); }
+  bool    fused_ok() const override { return level_pitch != 0; }
+  bool    fused_mg_ok() const override { return level_pitch != 0; }
+  int64_t fused_size() const override { return level_pitch ? level_pitch * g.n1 : n(); }
+  int     to_pitched(const double *natural, double *pitched) override
+  {
+    const Plan pl = plan3(g.n0, g.n1, 1);
+    PMG_PLAN_CHECK(pl);
+    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.n1, pitch(), natural, pitched);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  int from_pitched(const double *pitched, double *natural) override
+  {
+    const Plan pl = plan3(g.n0, g.n1, 1);
+    PMG_PLAN_CHECK(pl);
+    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.n1, pitch(), pitched, natural);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+  DevBuf<box2d::Item> b2items[2]; // [MODE_RESTRICT ? 1 : 0]: the fused residual + restriction runs narrower strips
+  int                 b2n[2] = {0, 0};
+  template <int NOISE, int MODE, int PC> int launch_box2(box2d::Args &a)
+  {
+    using namespace box2d;
+    constexpr int WARPS = 8, STAGES = 2, MINB = MODE == MODE_RESTRICT ? 1 : 2;
+    auto          kern = box2d_kernel<NOISE, MODE, PC, WARPS, STAGES, MINB>;
+    const size_t  sm   = smem_bytes<WARPS, STAGES>();
+    static int    occ_dev[16] = {0}; // per device: function attributes belong to the device's context
+    const int     dv = ctx->device & 15;
+    if (!occ_dev[dv]) {
+      PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int occ = 0;
+      PMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, sm));
+      occ_dev[dv] = std::max(1, occ);
+    }
+    const int r = MODE == MODE_RESTRICT ? 1 : 0;
+    if (!b2n[r]) { // about one resident wave of warps; bands start on even rows (the band that owns fine row 2J emits coarse row J)
+      static const int by_env = std::getenv("PMG_BOX2_BY") ? std::atoi(std::getenv("PMG_BOX2_BY")) : 0;
+      static const int by_min = std::getenv("PMG_BOX2_BY_MIN") ? std::atoi(std::getenv("PMG_BOX2_BY_MIN")) : 4;
+      const int        slots   = occ_dev[dv] * WARPS * ctx->sm_count;
+      const int        nstrips = (int)((g.n0 + Strip<MODE>::OUT - 1) / Strip<MODE>::OUT);
+      int              by      = by_env > 0 ? by_env : std::max<int>(by_min, (int)((g.n1 * nstrips + slots - 1) / slots));
+      by += by & 1;
+      std::vector<Item> list;
+      for (int64_t j = 0; j < g.n1; j += by)
+        for (int st = 0; st < nstrips; ++st) list.push_back(Item{st, (int)j, (int)std::min<int64_t>(j + by, g.n1)});
+      b2n[r] = (int)list.size();
+      PMG_TRY(b2items[r].upload(list, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    a.items  = b2items[r].p;
+    a.nitems = b2n[r];
+    kern<<<(unsigned)((a.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a);
+    return 0;
+  }
+  template <int NOISE, int MODE> int launch_box2_dir(int dir, box2d::Args &a) { return dir == PMG_SOR_BACKWARD_SWEEP ? launch_box2<NOISE, MODE, 1>(a) : launch_box2<NOISE, MODE, 0>(a); }
+  template <int MODE> int launch_box2_noise(int dir, int noise, box2d::Args &a) { return noise == PMG_NOISE_PHILOX ? launch_box2_dir<box2d::NOISE_PHILOX, MODE>(dir, a) : launch_box2_dir<box2d::NOISE_RT, MODE>(dir, a); }
+  static void fill_class(box2d::Cls &k, const double (&c)[9], double omega)
+  {
+    const double d = c[4], f = std::sqrt((2 - omega) / omega);
+    for (int s = 0, q = 0; s < 9; ++s)
+      if (s != 4) k.nc[q++] = -c[s];
+    double inv = 1.0 / d;
+    k.idiag    = inv * omega;               // box_coeffs_kernel
+    k.sd       = std::sqrt(std::fabs(d)) * f;
+    k.omo      = 1.0 - omega;
+    k.ndiag    = -d;
+  }
+  // b, xin, xout: this level's pitched vectors; xc / bc: the coarse level's vectors (row stride coarse->level_pitch or natural)
+  int fused_sweep(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse, const double *xc, double *bc) override
+  {
+    using namespace box2d;
+    if (!level_pitch) PMG_FAIL(PMG_ERR_ORDER, "one-pass sweep on a level whose vectors are not pitched");
+    if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
+    if (xc && !xin) PMG_FAIL(PMG_ERR_ARG, "fused prolongation needs a fine iterate");
+    Args a;
+    std::memset(&a, 0, sizeof a);
+    const int64_t P = level_pitch;
+    const int64_t dims[3] = {P, g.n1, 1}, strides[3] = {1, P, P * g.n1};
+    const int     box[3]  = {128, 2, 1};
+    const double *any = xin ? xin : (b ? b : xout);
+    PMG_TRY(make_tensor_map(a.tm_x, xin ? xin : any, 3, dims, strides, box, false));
+    PMG_TRY(make_tensor_map(a.tm_b, b ? b : any, 3, dims, strides, box, false));
+    a.nx = (int)g.n0; a.ny = (int)g.n1; a.pitch = (int)P;
+    a.has_x = xin ? 1 : 0; a.has_b = b ? 1 : 0;
+    a.xout = xout; a.xc = xc; a.bc = bc;
+    if (xc || bc) {
+      int     cd;
+      int64_t cn[3];
+      if (!coarse || !coarse->structured(cd, cn)) PMG_FAIL(PMG_ERR_SUP, "fused grid transfer needs a structured coarse level");
+      a.cnx = (int)cn[0]; a.cny = (int)cn[1];
+      a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
+      a.ccols  = a.cpitch;
+    }
+    a.mode = na.mode; a.tape = na.tape;
+    for (int q = 0; q < 16; ++q) {
+      const int rc = q >> 2, cc = q & 3;
+      if (rc < 3 && cc < 3) fill_class(a.cls[q], cls_tab.c[3 * rc + cc], co.omega);
+    }
+    a.in = a.cls[5];
+    philox_expand_keys(na.seed, a.pk);
+    a.call_lo = (uint32_t)na.call; a.call_hi = (uint32_t)(na.call >> 32);
+    if (bc) PMG_TRY(launch_box2_noise<MODE_RESTRICT>(dir, na.mode, a));
+    else if (xc) PMG_TRY(launch_box2_noise<MODE_PROLONG>(dir, na.mode, a));
+    else PMG_TRY(launch_box2_noise<MODE_PLAIN>(dir, na.mode, a));
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+
   template <bool RES> int apply(const double *b, const double *x, double *out)
   {
     PMG_TRY(halo(x));
@@ -1721,6 +1881,7 @@ struct BoxOp final : GridOp {
     char buf[256];
     snprintf(buf, sizeof buf, "%d-point stencil arrays %lldx%lldx%lld (units %lld..%lld), %d colours, interior stencil %s", nst(), (long long)g.n0, (long long)g.n1, (long long)g.n2, (long long)g.slo, (long long)g.shi, ncolors(), bc.on ? "shared (read from kernel parameters)" : "per node");
     out = buf;
+    if (level_pitch) out += ", one-pass TMA kernels on pitched vectors";
   }
 };
 
@@ -2061,6 +2222,7 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64
     if (!replicate) {
       PMG_TRY(c->exchange_coef_ghosts());
       PMG_TRY(c->detect_interior());
+      PMG_TRY(c->detect_classes());
       auto t    = std::make_unique<GridTransfer>();
       t->ctx    = ctx;
       t->fine   = cur;
@@ -2089,6 +2251,7 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64
       for (int s = 0; s < full->nst(); ++s) PMG_TRY(comm_allgatherv(ctx, c->coef.p + (size_t)s * gc.nl, full->coef.p + (size_t)s * full->g.nl, t->counts.data(), t->displs.data(), ctx->stream));
       PMG_CUDA(cudaStreamSynchronize(ctx->stream));
       PMG_TRY(full->detect_interior());
+      PMG_TRY(full->detect_classes());
       transfers[(size_t)l] = std::move(t);
       cur                  = full.get();
       ops[(size_t)l - 1]   = std::move(full);

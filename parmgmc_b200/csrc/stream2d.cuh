@@ -49,6 +49,7 @@ struct Args {
   int           pitch; // row stride of xin / xout / b: nx rounded up to 4, so that a lane's four columns are one aligned
                        // 32-byte access (LDG.256 / STG.256) and a warp row is one contiguous kilobyte
   int           by, nstrips, nbands;
+  int           cpitch; // row stride of xc / bc: the coarse row length, or the coarse level's pitch when its vectors are pitched
   int           flip; // 0: forward sweep (colour (i+j) even first); 1: backward sweep (colour (i+j) odd first)
   const double *xin, *b, *xc;
   double       *xout, *bc;
@@ -198,8 +199,8 @@ __device__ __forceinline__ void guess_row(const Args &a, int j, int c, double (&
   if (GUESS == GUESS_PROLONG && INTERIOR) { // all parents exist
     const int    J0 = j >> 1, nJ = (j & 1) ? 2 : 1;
     const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
-    const double *p = a.xc + (size_t)(J0 - a.gc.slo) * a.gc.nx + (c >> 1);
-    for (int q = 0; q < nJ; ++q, p += a.gc.nx) {
+    const double *p = a.xc + (size_t)(J0 - a.gc.slo) * a.cpitch + (c >> 1);
+    for (int q = 0; q < nJ; ++q, p += a.cpitch) {
       const double c0 = p[0], c1 = p[1], c2 = p[2];
       out[0] = fma(wj, c0, out[0]);
       out[1] = fma(wh, c1, fma(wh, c0, out[1]));
@@ -217,7 +218,7 @@ __device__ __forceinline__ void guess_row(const Args &a, int j, int c, double (&
       const int J = J0 + q;
       if (J >= a.gc.ny) continue;
       double       cv[3];
-      const double *p = a.xc + (size_t)(J - a.gc.slo) * a.gc.nx + I0;
+      const double *p = a.xc + (size_t)(J - a.gc.slo) * a.cpitch + I0;
 #pragma unroll
       for (int m = 0; m < 3; ++m) cv[m] = (I0 + m >= 0 && I0 + m < a.gc.nx) ? p[m] : 0.0;
       // column c (even): parent I0; c+1 (odd): I0, I0+1; c+2 (even): I0+1; c+3 (odd): I0+1, I0+2
@@ -341,7 +342,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
             acc = fma(0.5, nC, acc);
             if (hasE) acc = fma(0.25, nE, acc);
           }
-          a.bc[(size_t)(J - a.gc.slo) * a.gc.nx + I] = acc;
+          a.bc[(size_t)(J - a.gc.slo) * a.cpitch + I] = acc;
         }
       }
       copy4(r2, r1); r2w = r1w;

@@ -58,7 +58,7 @@ struct Args {
   int           swizzle; // 1: tensors are {4, pitch/4, rows} with SWIZZLE_32B; 0: {pitch, rows, 1}, plain rows
   double       *xout;
   const double *xc;   // non-null: the sweep starts from xin + P xc (MatInterpolateAdd fused into the post-smoother); xc is the
-  int           cnx, cny; // coarse level's natural-layout iterate on its cnx x cny grid (Q1)
+  int           cnx, cny, cpitch; // coarse level's iterate on its cnx x cny grid, row stride cpitch (Q1)
   const double *tape; // injected noise of this block: natural layout (row stride nx), local rows
   double        h, idiag, sd, omo; // interior coefficients
   Coef          coef[6];
@@ -257,8 +257,8 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
     const int    I0 = c >> 1; // c = 0 mod 4: fine columns c .. c+3 see coarse columns I0, I0+1, I0+2
     if (INTERIOR) {
-      const double *p = a.xc + (long long)Jlo * a.cnx + I0;
-      for (int q = 0; q < nJ; ++q, p += a.cnx) {
+      const double *p = a.xc + (long long)Jlo * a.cpitch + I0;
+      for (int q = 0; q < nJ; ++q, p += a.cpitch) {
         const double c0v = p[0], c1v = p[1], c2v = p[2];
         out[0] = fma(wj, c0v, out[0]);
         out[1] = fma(wh, c1v, fma(wh, c0v, out[1]));
@@ -272,7 +272,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       const int J = Jlo + q;
       if (J >= a.cny) continue;
       double        cv[3];
-      const double *p = a.xc + (long long)J * a.cnx + I0;
+      const double *p = a.xc + (long long)J * a.cpitch + I0;
 #pragma unroll
       for (int m = 0; m < 3; ++m) cv[m] = (I0 + m >= 0 && I0 + m < a.cnx) ? p[m] : 0.0;
       if (c >= 0 && c < a.nx) out[0] = fma(wj, cv[0], out[0]);
@@ -289,11 +289,11 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   };
   auto prefetch_coarse = [&](int j) { // the coarse rows that fine rows j, j+1 will read
     if (!INTERIOR || a.xc == nullptr) return;
-    const double *p = a.xc + (long long)(j >> 1) * a.cnx + (c >> 1);
+    const double *p = a.xc + (long long)(j >> 1) * a.cpitch + (c >> 1);
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cnx));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cnx + 2));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cpitch));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cpitch + 2));
   };
   prolong(J0 - 1, xs);
   prolong(J0, x0);

@@ -795,6 +795,7 @@ def test_box_stream_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, noise,
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
     out = []
     for stream in (True, False):
+        monkeypatch.setenv("PMG_NO_BOX2", "1")  # the natural-layout one-pass sweep, not its pitched TMA successor (box2d.cuh)
         if stream:
             monkeypatch.setenv("PMG_BOX_STREAM_MIN", "0")
             monkeypatch.delenv("PMG_NO_BOX_STREAM", raising=False)
@@ -815,6 +816,64 @@ def test_box_stream_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, noise,
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1]
+
+
+# ---- the TMA-fed one-pass kernels of the 9-point levels (box2d.cuh): sweep + residual + restriction / prolongation + sweep ----
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((257, 257, 1), 4, {}),
+    ((301, 173, 1), 4, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    ((129, 513, 1), 4, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.4}),
+    ((260, 140, 1), 3, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_backward": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 0.8}),
+    ((1025, 769, 1), 6, {}),
+])
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+def test_box2d_one_pass_levels_are_bit_identical(pmg, ctx, dims, levels, extra, noise, monkeypatch):
+    """Pre-sample + residual + restriction in one pass and prolongation + post-sample in another, on pitched level vectors,
+    must reproduce the launch-per-colour V-cycle (separate residual / restriction / prolongation kernels) exactly."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for box2 in (True, False):
+        monkeypatch.setenv("PMG_NO_BOX_STREAM", "1")
+        if box2:
+            monkeypatch.delenv("PMG_NO_BOX2", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_BOX2", "1")
+        lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=1.0)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(5).standard_normal(2 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(99)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
+
+
+@pytest.mark.parametrize("dims,levels", [((257, 131), 4), ((300, 202), 4), ((513, 129), 5)])
+def test_box2d_one_pass_levels_match_oracle(pmg, ctx, orc, dims, levels):
+    """The same path against the CPU oracle's V-cycle (injected tape, 1e-12)."""
+    rng = np.random.default_rng(SEED)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(pmg.Mat.laplace(ctx, 2, dims[0], dims[1], kappa=1.0))
+    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0})
+    pc.setup()
+    assert "one-pass" in pc.view()
+    omg = oracle_mg(orc, 2, dims + (1,), 1.0, levels)
+    its, per, n = 2, pc.noise_per_sample(), dims[0] * dims[1]
+    z, b = rng.standard_normal(its * per), rng.standard_normal(n)
+    pc.set_noise_tape(z)
+    y = np.full(n, 0.5)
+    pc.apply_richardson(b, y, its=its)
+    ref = omg.richardson(orc.Noise.tape(z), b, np.full(n, 0.5), its)
+    assert relerr(y, ref) < RTOL, relerr(y, ref)
 
 
 @pytest.mark.parametrize("dim,dims,levels", [(2, (129, 97, 1), 4), (3, (33, 25, 17), 3)])
