@@ -1302,7 +1302,7 @@ struct LapOp final : GridOp {
   // ---- 2D plain sweep: sweep2d.cuh (TMA-fed) ----
   DevBuf<sweep2d::Item> items2;
   int                   nitems2 = 0, items2_cfg = -1;
-  int build_items2(int by, std::vector<sweep2d::Item> &out) const
+  int build_items2(int by, std::vector<sweep2d::Item> &out, bool restrict_mode = false) const
   {
     using sweep2d::Item;
     const int         nstrips = (int)((g.n0 + sweep2d::STRIP_OUT - 1) / sweep2d::STRIP_OUT);
@@ -1313,7 +1313,8 @@ struct LapOp final : GridOp {
       int64_t    j = g.slo;
       while (j < g.shi) {
         const int64_t jb_full = std::min<int64_t>(j + by, g.shi);
-        const bool    interior = !edge_strip && j - 2 >= 1 && jb_full <= g.n1 - 2 && j - 3 >= g.slo && jb_full + 2 < g.shi; // sweep2d_kernel's test
+        const int     lo = restrict_mode ? 4 : 2, hi = restrict_mode ? 2 : 0;
+        const bool    interior = !edge_strip && j - lo >= 1 && jb_full + hi <= g.n1 - 2 && j - lo - 1 >= g.slo && jb_full + hi + 2 < g.shi; // sweep2d_kernel's test
         const int64_t h  = interior ? by : std::max(2, (by * 3 / 4) & ~1); // edge warps run the table-driven loop: shorter bands
         const int64_t jb = std::min<int64_t>(j + h, g.shi);
         (interior ? fast : slow).push_back(Item{s, (int)j, (int)jb});
@@ -1324,22 +1325,40 @@ struct LapOp final : GridOp {
     out.insert(out.end(), fast.begin(), fast.end());
     return (int)out.size();
   }
-  template <int NOISE, int WARPS, int STAGES, int MINB> int launch2(const sweep2d::Args &a, int &slots)
+  template <int NOISE, int WARPS, int STAGES, int MINB, bool RESTRICT = false> int launch2(const sweep2d::Args &a, int &slots)
   {
     using namespace sweep2d;
-    auto          kern = sweep2d_kernel<NOISE, WARPS, STAGES, MINB>;
+    auto          kern = sweep2d_kernel<NOISE, WARPS, STAGES, MINB, RESTRICT>;
     const size_t  sm   = smem_bytes<WARPS, STAGES>();
-    static bool   attr_set = false;
-    static int    occ      = 0;
-    if (!attr_set) {
+    static int    occ_dev[16] = {0}; // per device: function attributes belong to the device's context
+    const int     dv = ctx->device & 15;
+    if (!occ_dev[dv]) {
+      int occ = 0;
       PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       PMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, sm));
-      attr_set = true;
+      occ_dev[dv] = std::max(1, occ);
     }
-    slots = occ * WARPS * ctx->sm_count;
+    slots = occ_dev[dv] * WARPS * ctx->sm_count;
     if (a.nitems > 0) kern<<<(unsigned)((a.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a);
     return 0;
   }
+  // the pre-smoother with the fused residual + restriction (sweep2d.cuh RESTRICT)
+  template <int NOISE> int launch2r_cfg(int cfg, const sweep2d::Args &a, int &slots)
+  {
+    switch (cfg) {
+    case 0: return launch2<NOISE, 8, 3, 2, true>(a, slots); // 128 registers, 16 warps / SM
+    case 1: return launch2<NOISE, 4, 3, 3, true>(a, slots); // 168 registers, 12 warps / SM
+    default: return launch2<NOISE, 8, 3, 1, true>(a, slots);
+    }
+  }
+  int sweep2dr_launch(int cfg, const sweep2d::Args &a, int mode, int &slots)
+  {
+    if (mode == PMG_NOISE_NONE) return launch2r_cfg<sweep2d::NOISE_NONE>(cfg, a, slots);
+    if (mode == PMG_NOISE_INJECTED) return launch2r_cfg<sweep2d::NOISE_TAPE>(cfg, a, slots);
+    return launch2r_cfg<sweep2d::NOISE_PHILOX>(cfg, a, slots);
+  }
+  DevBuf<sweep2d::Item> items2r;
+  int                   nitems2r = 0, items2r_cfg = -1;
   template <int NOISE> int launch2_cfg(int cfg, const sweep2d::Args &a, int &slots)
   {
     switch (cfg) {
@@ -1356,7 +1375,7 @@ struct LapOp final : GridOp {
     if (mode == PMG_NOISE_INJECTED) return launch2_cfg<sweep2d::NOISE_TAPE>(cfg, a, slots);
     return launch2_cfg<sweep2d::NOISE_PHILOX>(cfg, a, slots);
   }
-  int fused_sweep2_tma(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse = nullptr, const double *xc = nullptr)
+  int fused_sweep2_tma(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na, LevelOp *coarse = nullptr, const double *xc = nullptr, double *bc = nullptr)
   {
     using namespace sweep2d;
     LapTab t;
@@ -1386,20 +1405,46 @@ struct LapOp final : GridOp {
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;
     a.xout  = xout;
-    a.xc = nullptr; a.cnx = a.cny = a.cpitch = 0;
-    if (xc) { // prolongation fused into the sweep: the coarse level is a whole grid on this device
+    a.xc = nullptr; a.bc = nullptr; a.cnx = a.cny = a.cpitch = 0;
+    if (xc || bc) { // prolongation / residual + restriction fused into the sweep: the coarse level is a whole grid on this device
       int     cd;
       int64_t cn[3];
-      if (!coarse || !coarse->structured(cd, cn) || parallel) PMG_FAIL(PMG_ERR_SUP, "fused prolongation needs a structured coarse level on one device");
-      a.xc = xc; a.cnx = (int)cn[0]; a.cny = (int)cn[1];
+      if (!coarse || !coarse->structured(cd, cn) || parallel) PMG_FAIL(PMG_ERR_SUP, "fused grid transfers need a structured coarse level on one device");
+      a.xc = xc; a.bc = bc; a.cnx = (int)cn[0]; a.cny = (int)cn[1];
       a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
     }
     a.tape  = na.tape;
-    a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega;
-    for (int d = 0; d < 5; ++d) a.coef[d] = Coef{t.idiag[d], t.sqrtdiag[d], 1.0 - co.omega, 0.0};
+    a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega; a.diag = t.diag[4];
+    for (int d = 0; d < 5; ++d) a.coef[d] = Coef{t.idiag[d], t.sqrtdiag[d], 1.0 - co.omega, t.diag[d]};
     a.coef[5] = Coef{0.0, 0.0, 0.0, 0.0};
     philox_expand_keys(na.seed, a.pk);
     a.call_lo = (uint32_t)na.call; a.call_hi = (uint32_t)(na.call >> 32);
+    if (bc) { // pre-smoother + residual + restriction
+      const int rcfg_env = std::getenv("PMG_SW2R_CFG") ? std::atoi(std::getenv("PMG_SW2R_CFG")) : 1; // 168 registers, 12 warps / SM measured fastest (profiles/r2_summary.md)
+      static const int rby_env  = std::getenv("PMG_SW2R_BY") ? std::atoi(std::getenv("PMG_SW2R_BY")) : 0;
+      if ((g.slo & 1) != 0) PMG_FAIL(PMG_ERR_SUP, "fused restriction needs an even first row");
+      if (items2r_cfg != rcfg_env) {
+        a.items = nullptr; a.nitems = 0;
+        int slots = 0;
+        PMG_TRY(sweep2dr_launch(rcfg_env, a, na.mode, slots));
+        std::vector<Item> list;
+        const int         nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
+        int by = rby_env > 0 ? rby_env : std::max<int>(4, (int)(((g.shi - g.slo) * nstrips + slots - 1) / std::max(1, slots)));
+        by += by & 1;
+        while (build_items2(by, list, true) > slots && rby_env <= 0 && by < g.shi - g.slo) by += 2;
+        nitems2r = (int)list.size();
+        PMG_TRY(items2r.upload(list, ctx->stream));
+        PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+        items2r_cfg = rcfg_env;
+      }
+      a.items = items2r.p; a.nitems = nitems2r;
+      int slots = 0;
+      PMG_TRY(sweep2dr_launch(rcfg_env, a, na.mode, slots));
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+      ctx->dof_updates += g.nl;
+      return 0;
+    }
     if (items2_cfg != cfg) { // size the bands so that the work list is one resident wave
       a.items = nullptr; a.nitems = 0;
       int slots = 0;
@@ -1447,7 +1492,9 @@ struct LapOp final : GridOp {
     }
     static const bool no_tma = std::getenv("PMG_NO_TMA") != nullptr;
     static const bool no_tma_prolong = std::getenv("PMG_NO_TMA_PROLONG") != nullptr;
-    if (!bc && xin && !no_tma && (!xc || !no_tma_prolong)) return fused_sweep2_tma(dir, co, b, xin, xout, na, coarse, xc);
+    static const bool no_tma_restrict = std::getenv("PMG_NO_TMA_RESTRICT") != nullptr;
+    if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
+    if (xin && !no_tma && (!xc || !no_tma_prolong) && (!bc || !no_tma_restrict)) return fused_sweep2_tma(dir, co, b, xin, xout, na, coarse, xc, bc);
     using namespace stream2d;
     LapTab t;
     fill_tab(co.omega, t);

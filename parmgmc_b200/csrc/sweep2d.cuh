@@ -42,7 +42,7 @@ struct Item {
 };
 
 struct Coef { // per-node coefficients of the edge warps, indexed by the number of existing neighbours; 5 = no such node
-  double idiag, sd, omo, pad;
+  double idiag, sd, omo, diag;
 };
 
 struct Args {
@@ -59,8 +59,9 @@ struct Args {
   double       *xout;
   const double *xc;   // non-null: the sweep starts from xin + P xc (MatInterpolateAdd fused into the post-smoother); xc is the
   int           cnx, cny, cpitch; // coarse level's iterate on its cnx x cny grid, row stride cpitch (Q1)
+  double       *bc;   // non-null (RESTRICT kernels): b_c = P^T (b - A xout), MatResidual + MatRestrict fused into the pre-smoother
   const double *tape; // injected noise of this block: natural layout (row stride nx), local rows
-  double        h, idiag, sd, omo; // interior coefficients
+  double        h, idiag, sd, omo, diag; // interior coefficients
   Coef          coef[6];
   PhiloxKeys    pk;
   uint32_t      call_lo, call_hi;
@@ -202,19 +203,77 @@ template <int NOISE, bool INTERIOR> struct Warp {
     const int jo = jj - 1; // row jj-1 is final
     if (out_lane && jo >= ja && jo < jb) st256(a.xout + (long long)(jo - a.tlo) * a.pitch + c, xs);
   }
+
+  // r = b - A x of the lane's four columns of row jr (stream2d::resid: the assembled row's order S, W, C, E, N); nodes that
+  // do not exist give 0
+  __device__ __forceinline__ void resid_row(int jr, const double (&row)[4], const double (&south)[4], const double (&north)[4], const double (&bv)[4], double (&r)[4]) const
+  {
+    const double west = shfl_up1(row[3]), east = shfl_dn1(row[0]), mh = -a.h;
+    int          ci[4] = {0, 0, 0, 0};
+    if (!INTERIOR) {
+      const bool rowok   = jr >= 0 && jr < a.ny;
+      const int  rowmiss = (jr == 0 ? 1 : 0) + (jr == a.ny - 1 ? 1 : 0);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) ci[m] = (rowok && colok[m]) ? 4 - colmiss[m] - rowmiss : 5;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double xw = m == 0 ? west : row[m == 0 ? 0 : m - 1];
+      const double xe = m == 3 ? east : row[m == 3 ? 3 : m + 1];
+      double       ax = 0.0;
+      ax = fma(mh, south[m], ax);
+      ax = fma(mh, xw, ax);
+      ax = fma(INTERIOR ? a.diag : coef[ci[m]].diag, row[m], ax);
+      ax = fma(mh, xe, ax);
+      ax = fma(mh, north[m], ax);
+      r[m] = __dsub_rn(bv[m], ax);
+      if (!INTERIOR && ci[m] == 5) r[m] = 0.0;
+    }
+  }
+  // b_c row J (fine centre row 2J) from the residual rows 2J-1, 2J, 2J+1 (restrict_kernel: ascending fine index)
+  __device__ __forceinline__ void emit_coarse(int J, const double (&rs)[4], const double (&rm)[4], const double (&rn)[4]) const
+  {
+    const double rsw = shfl_up1(rs[3]), rmw = shfl_up1(rm[3]), rnw = shfl_up1(rn[3]);
+    if (!out_lane) return;
+    const int I0 = c >> 1;
+    double   *p  = a.bc + (long long)J * a.cpitch + I0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { // coarse columns c/2 (fine c) and c/2 + 1 (fine c + 2)
+      const double sW = q == 0 ? rsw : rs[1], sC = q == 0 ? rs[0] : rs[2], sE = q == 0 ? rs[1] : rs[3];
+      const double cW = q == 0 ? rmw : rm[1], cC = q == 0 ? rm[0] : rm[2], cE = q == 0 ? rm[1] : rm[3];
+      const double nW = q == 0 ? rnw : rn[1], nC = q == 0 ? rn[0] : rn[2], nE = q == 0 ? rn[1] : rn[3];
+      double       s  = 0.0;
+      s = fma(0.25, sW, s);
+      s = fma(0.5, sC, s);
+      s = fma(0.25, sE, s);
+      s = fma(0.5, cW, s);
+      s = fma(1.0, cC, s);
+      s = fma(0.5, cE, s);
+      s = fma(0.25, nW, s);
+      s = fma(0.5, nC, s);
+      s = fma(0.25, nE, s);
+      if (INTERIOR || I0 + q < a.cnx) p[q] = s;
+    }
+  }
 };
 
 // smem layout per CTA: [WARPS][STAGES] stages of STAGE_BYTES | tables | coef | mbarriers
 template <int WARPS, int STAGES> constexpr size_t smem_bytes() { return (size_t)WARPS * STAGES * STAGE_BYTES + sizeof(fastnormal::SharedTables) + 6 * sizeof(Coef) + (size_t)WARPS * (STAGES + 1) * 8 + 1024; }
 
-template <int NOISE, bool INTERIOR, int STAGES>
+// RESTRICT: the pass also forms b_c = P^T (b - A xout) (stream2d.cuh's fused residual + restriction on the TMA structure):
+// after row step jj rows <= jj-1 are final, so the residual of row jj-2 follows, and a coarse row is emitted when the three
+// residual rows around its centre row 2J are there.  The band runs three rows ahead of and two rows past its outputs.  The
+// right-hand side rows of the residual are re-read from the PREVIOUS ring stage, which is therefore refilled one iteration
+// later than in the plain sweep (prefetch distance STAGES-1).
+template <int NOISE, bool INTERIOR, int STAGES, bool RESTRICT = false>
 __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables &ft, const Coef *coef, uint32_t ring, uint32_t bars, int lane, const Item it)
 {
   const int c0 = it.strip * STRIP_OUT - 4, c = c0 + 4 * lane;
   Warp<NOISE, INTERIOR> W(a, ft, coef, lane, c, it.ja, it.jb);
-  // first step row: ja-1 or ja-2, whichever makes (J0 + flip) even, so that the unrolled pair is always (P=0, P=1)
-  const int J0 = (((it.ja - 1 + a.flip) & 1) == 0) ? it.ja - 1 : it.ja - 2;
-  const int N  = it.jb - J0 + 1;  // row steps J0 .. jb
+  // first step row: ja-lead or ja-lead-1, whichever makes (J0 + flip) even, so that the unrolled pair is always (P=0, P=1)
+  constexpr int lead = RESTRICT ? 3 : 1;
+  const int J0 = (((it.ja - lead + a.flip) & 1) == 0) ? it.ja - lead : it.ja - lead - 1;
+  const int N  = it.jb + (RESTRICT ? 2 : 0) - J0 + 1; // row steps J0 .. jb (+2)
   const int T  = (N + 1) >> 1;    // stages: stage t feeds steps J0+2t, J0+2t+1 with x rows J0+2t+1, J0+2t+2 and b rows J0+2t, J0+2t+1
   const uint32_t bytes = a.has_b ? STAGE_BYTES : STAGE_BYTES / 2;
   const uint32_t bar_pro = bars + STAGES * 8;
@@ -307,10 +366,28 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     for (int m = 0; m < 4; ++m) ci[m] = (rowok && W.colok[m]) ? 4 - W.colmiss[m] - rowmiss : 5;
   };
 
+  double xsss[4] = {0, 0, 0, 0};                         // RESTRICT: row jj-3
+  double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};      // RESTRICT: residual rows jr-1, jr-2 of the residual row jr being formed
+  // residual of row jr (rows jr-1 .. jr+1 final) with the right-hand side row at shared-memory address bsrc, then the coarse row
+  // whose centre is row jr-1
+  auto residual_step = [&](int jr, const double (&south)[4], const double (&row)[4], const double (&north)[4], uint32_t bsrc, bool have_b) {
+    double bv[4] = {0, 0, 0, 0}, r0[4];
+    if (have_b) lds256(bsrc, lane, bv, swz);
+    W.resid_row(jr, row, south, north, bv, r0);
+    const int jc = jr - 1;
+    if ((jc & 1) == 0 && jc >= it.ja && jc < it.jb) W.emit_coarse(jc >> 1, r2, r1, r0);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      r2[m] = r1[m];
+      r1[m] = r0[m];
+    }
+  };
+
   int jj = J0;
   for (int t = 0; t < T; ++t, jj += 2) {
     const int      s   = t % STAGES;
     const uint32_t src = ring + s * STAGE_BYTES;
+    const uint32_t prv = ring + ((t + STAGES - 1) % STAGES) * STAGE_BYTES + 2 * ROW_BYTES; // b rows jj-2, jj-1 (stage t-1)
     mbar_wait(bars + s * 8, (uint32_t)(t / STAGES) & 1u);
     double xa[4], ba[4] = {0, 0, 0, 0};
     lds256(src, lane, xa, swz);
@@ -319,26 +396,35 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     if (jj + 4 <= it.jb) prefetch_coarse(jj + 3);
     W.template step<0>(jj, xss, xs, x0, xa, ba, wk, cis);
     row_classes(jj, cis);
+    if (RESTRICT) residual_step(jj - 2, xsss, xss, xs, prv, a.has_b && t > 0);
     if (2 * t + 1 < N) {
       double xb[4], bb[4] = {0, 0, 0, 0};
       lds256(src + ROW_BYTES, lane, xb, swz);
       if (a.has_b) lds256(src + 3 * ROW_BYTES, lane, bb, swz);
       prolong(jj + 2, xb);
-      __syncwarp();
-      if (lane == 0 && t + STAGES < T) issue(t + STAGES);
+      if (!RESTRICT) {
+        __syncwarp();
+        if (lane == 0 && t + STAGES < T) issue(t + STAGES);
+      }
       W.template step<1>(jj + 1, xs, x0, xa, xb, bb, wk, cis);
       row_classes(jj + 1, cis);
+      if (RESTRICT) residual_step(jj - 1, xss, xs, x0, prv + ROW_BYTES, a.has_b && t > 0);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
+        if (RESTRICT) xsss[m] = xs[m];
         xss[m] = x0[m];
         xs[m]  = xa[m];
         x0[m]  = xb[m];
       }
     }
+    if (RESTRICT) { // stage t-1 has now been read for the last time: refill its slot
+      __syncwarp();
+      if (lane == 0 && t >= 1 && t - 1 + STAGES < T) issue(t - 1 + STAGES);
+    }
   }
 }
 
-template <int NOISE, int WARPS, int STAGES, int MINB> __global__ void __launch_bounds__(WARPS * 32, MINB) sweep2d_kernel(const __grid_constant__ Args a)
+template <int NOISE, int WARPS, int STAGES, int MINB, bool RESTRICT = false> __global__ void __launch_bounds__(WARPS * 32, MINB) sweep2d_kernel(const __grid_constant__ Args a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -358,12 +444,12 @@ template <int NOISE, int WARPS, int STAGES, int MINB> __global__ void __launch_b
   if (w >= a.nitems) return;
   const Item it = a.items[w];
   const int  c0 = it.strip * STRIP_OUT - 4;
-  const int  J0 = it.ja - 2; // lowest possible first step row
+  const int  J0 = it.ja - (RESTRICT ? 4 : 2), jl = it.jb + (RESTRICT ? 2 : 0); // lowest possible first step row, last step row
   // every node the warp updates exists and has all four neighbours, and every row it reads is owned
-  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && J0 >= 1 && it.jb <= a.ny - 2 && J0 - 1 >= a.tlo && it.jb + 2 < a.thi;
+  const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && J0 >= 1 && jl <= a.ny - 2 && J0 - 1 >= a.tlo && jl + 2 < a.thi;
   const uint32_t ring = smem_u32(base) + wl * STAGES * STAGE_BYTES, bars = smem_u32(bar + wl * (STAGES + 1));
-  if (interior) run_warp<NOISE, true, STAGES>(a, ft, coef, ring, bars, lane, it);
-  else run_warp<NOISE, false, STAGES>(a, ft, coef, ring, bars, lane, it);
+  if (interior) run_warp<NOISE, true, STAGES, RESTRICT>(a, ft, coef, ring, bars, lane, it);
+  else run_warp<NOISE, false, STAGES, RESTRICT>(a, ft, coef, ring, bars, lane, it);
 }
 
 } // namespace sweep2d

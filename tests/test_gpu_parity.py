@@ -876,6 +876,41 @@ def test_box2d_one_pass_levels_match_oracle(pmg, ctx, orc, dims, levels):
     assert relerr(y, ref) < RTOL, relerr(y, ref)
 
 
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((257, 257, 1), 4, {}),
+    ((300, 202, 1), 4, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_backward": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.3}),
+    ((1030, 517, 1), 6, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+])
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2"])
+def test_fine_level_tma_residual_restriction_is_bit_identical(pmg, ctx, dims, levels, extra, noise, cfg, monkeypatch):
+    """Fine-level pre-sample + residual + restriction on the TMA structure (sweep2d.cuh RESTRICT) vs the plain-load
+    streaming kernel (stream2d.cuh): same arithmetic, bit for bit, for every register / occupancy configuration."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    monkeypatch.setenv("PMG_SW2R_CFG", cfg)
+    for tma in (True, False):
+        if tma:
+            monkeypatch.delenv("PMG_NO_TMA_RESTRICT", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_TMA_RESTRICT", "1")
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(pmg.Mat.laplace(ctx, 2, *dims, kappa=1.0))
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(5).standard_normal(2 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(99)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append(y)
+    assert np.array_equal(out[0], out[1]), relerr(out[0], out[1])
+
+
 @pytest.mark.parametrize("dim,dims,levels", [(2, (129, 97, 1), 4), (3, (33, 25, 17), 3)])
 def test_fused_residual_restriction_is_bit_identical(pmg, ctx, dim, dims, levels, monkeypatch):
     """b_c = P^T (b - A x) in one kernel (box_restrict_residual_kernel) vs residual + restriction."""
