@@ -407,6 +407,7 @@ template <int NOISE, int MODE, int PC, int WARPS, int STAGES, int MINB> __global
   Cls                      *cls = reinterpret_cast<Cls *>(fts + 1);
   unsigned long long       *bar = reinterpret_cast<unsigned long long *>(cls + 16);
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  pdl_launch_dependents();
   const fastnormal::Tables ft = fastnormal::load_tables(*fts);
   for (int q = threadIdx.x; q < 16 * (int)(sizeof(Cls) / sizeof(double)); q += blockDim.x) reinterpret_cast<double *>(cls)[q] = reinterpret_cast<const double *>(a.cls)[q];
   if (lane == 0) {
@@ -425,6 +426,7 @@ template <int NOISE, int MODE, int PC, int WARPS, int STAGES, int MINB> __global
   // every node the warp touches (rows e0-2 .. elast+2, columns c0 .. c0+127) is an interior-class node
   const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && e0 - 2 >= 1 && elast + 2 <= a.ny - 2;
   const uint32_t ring = smem_u32(base) + wl * STAGES * STAGE_BYTES, bars = smem_u32(bar + wl * (STAGES + 1));
+  pdl_wait(); // everything above reads launch constants only; the level's vectors belong to the preceding kernels
   if (interior) run_warp<NOISE, MODE, PC, false, STAGES>(a, ft, cls, ring, bars, lane, it);
   else run_warp<NOISE, MODE, PC, true, STAGES>(a, ft, cls, ring, bars, lane, it);
 }

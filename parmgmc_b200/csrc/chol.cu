@@ -114,9 +114,13 @@ template <bool LOWER> __global__ void __launch_bounds__(256) tri_gemv_kernel(int
 {
   const int i    = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (i >= n) return;
   const int     k0 = LOWER ? 0 : i, k1 = LOWER ? i + 1 : n;
   const double *row = M + (size_t)i * n;
+  // the factor is a launch constant: pull this warp's row towards L2 while the preceding kernel is still running
+  for (int k = k0 + lane * 16; k < k1; k += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + k));
+  pdl_wait();
   double        acc = 0.0;
   for (int k = k0 + lane; k < k1; k += 32) acc = fma(row[k], in[k], acc);
 #pragma unroll
@@ -193,7 +197,7 @@ static int launch_chol(pmg_ctx ctx, int64_t n, const double *L, const double *LT
 
 template <bool LOWER> static int launch_gemv(pmg_ctx ctx, int64_t n, const double *M, const double *in, double *out, const NoiseArgs &na)
 {
-  tri_gemv_kernel<LOWER><<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>((int)n, M, in, out, na);
+  PMG_CUDA(launch_pdl(ctx->stream, tri_gemv_kernel<LOWER>, dim3((unsigned)((n * 32 + 255) / 256)), dim3(256), 0, (int)n, M, in, out, na));
   PMG_CUDA(cudaGetLastError());
   ctx->launches++;
   return 0;

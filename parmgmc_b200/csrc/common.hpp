@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <memory>
 #include <string>
 #include <vector>
@@ -34,6 +36,33 @@ void pmg_set_error(const char *fmt, ...);
     pmg_set_error(__VA_ARGS__); \
     return (code);             \
   } while (0)
+
+// ---- programmatic dependent launch --------------------------------------------------------------------------------
+// The kernels of a V-cycle are short and strictly ordered, so launch latency and each kernel's prologue (noise tables,
+// mbarriers, work item) sit on the critical path.  A kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor is still running; it does its prologue, then blocks in pdl_wait() until the predecessor
+// has completed and its writes are visible.  Everything a kernel reads or writes that another kernel of the stream
+// touches must come after pdl_wait(); pdl_launch_dependents() at the top lets the successor be scheduled early in turn.
+// Without the attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KA, class... A> inline cudaError_t launch_pdl(cudaStream_t stream, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, A &&...args)
+{
+  static const bool off = std::getenv("PMG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim          = grid;
+  cfg.blockDim         = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs    = at;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+#endif
 
 // device buffer
 template <class T> struct DevBuf {

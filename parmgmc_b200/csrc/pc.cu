@@ -770,7 +770,7 @@ static int gamgmc_setup(pmg_pc pc)
   if (cyc != "direct" && cyc != "literal") PMG_FAIL(PMG_ERR_ARG, "-pc_b200_cycle %s: expected direct | literal", cyc.c_str());
   pc->direct_cycle = cyc == "direct";
   const char   *tm_env   = std::getenv("PMG_TAIL_MAX");
-  const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "20000").c_str());
+  const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "1500").c_str());
   // Galerkin levels that run on the one-pass kernels (box2d.cuh) keep their vectors PITCHED: a chain of levels below a fused
   // finest level, down to the first level that is small enough for the one-launch tail (or cannot run the kernels)
   for (int l = 0; l < L - 1; ++l) pc->lv[l].op->level_pitch = 0;

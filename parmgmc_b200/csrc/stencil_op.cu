@@ -1339,7 +1339,7 @@ struct LapOp final : GridOp {
       occ_dev[dv] = std::max(1, occ);
     }
     slots = occ_dev[dv] * WARPS * ctx->sm_count;
-    if (a.nitems > 0) kern<<<(unsigned)((a.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a);
+    if (a.nitems > 0) PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a));
     return 0;
   }
   // the pre-smoother with the fused residual + restriction (sweep2d.cuh RESTRICT)
@@ -1823,7 +1823,7 @@ struct BoxOp final : GridOp {
     }
     a.items  = b2items[r].p;
     a.nitems = b2n[r];
-    kern<<<(unsigned)((a.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a);
+    PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a));
     return 0;
   }
   template <int NOISE, int MODE> int launch_box2_dir(int dir, box2d::Args &a) { return dir == PMG_SOR_BACKWARD_SWEEP ? launch_box2<NOISE, MODE, 1>(a) : launch_box2<NOISE, MODE, 0>(a); }

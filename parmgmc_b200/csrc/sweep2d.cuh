@@ -432,6 +432,7 @@ template <int NOISE, int WARPS, int STAGES, int MINB, bool RESTRICT = false> __g
   Coef                     *coef = reinterpret_cast<Coef *>(fts + 1);
   unsigned long long       *bar  = reinterpret_cast<unsigned long long *>(coef + 6);
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  pdl_launch_dependents();
   const fastnormal::Tables ft = fastnormal::load_tables(*fts);
   if (threadIdx.x < 6) coef[threadIdx.x] = a.coef[threadIdx.x];
   if (lane == 0) {
@@ -448,6 +449,7 @@ template <int NOISE, int WARPS, int STAGES, int MINB, bool RESTRICT = false> __g
   // every node the warp updates exists and has all four neighbours, and every row it reads is owned
   const bool interior = c0 >= 1 && c0 + 127 <= a.nx - 2 && J0 >= 1 && jl <= a.ny - 2 && J0 - 1 >= a.tlo && jl + 2 < a.thi;
   const uint32_t ring = smem_u32(base) + wl * STAGES * STAGE_BYTES, bars = smem_u32(bar + wl * (STAGES + 1));
+  pdl_wait(); // everything above reads launch constants only (common.hpp: programmatic dependent launch)
   if (interior) run_warp<NOISE, true, STAGES, RESTRICT>(a, ft, coef, ring, bars, lane, it);
   else run_warp<NOISE, false, STAGES, RESTRICT>(a, ft, coef, ring, bars, lane, it);
 }
