@@ -188,6 +188,10 @@ int pmg_plan_sweep3d(int64_t nx, int64_t ny, int64_t nz, int64_t slo, int64_t sh
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------- */
 /* average device time [ms] and launch count of the kernels the last apply_richardson* call issued */
 int pmg_pc_last_stats(pmg_pc pc, double *ms_total, int64_t *launches, int64_t *dof_updates);
+/* Per-kernel profile of the V-cycle (measurement aid; the analogue of the reference's PetscLogEvent pair MulticolSOR /
+ * VecSetRandN, src/parmgmc.c:123-125, read with -log_view): after pmg_pc_set_option(pc, "-pc_b200_profile", "1") every
+ * labelled launch of pmg_pc_apply_richardson* is bracketed by CUDA events; the totals come back as a JSON array. */
+int pmg_pc_profile(pmg_pc pc, char *buf, size_t len, int reset);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,7 @@ SIGNATURES = {
     "pmg_pc_noise_per_sample": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "pmg_normal_fill": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, _f64p]),
     "pmg_pc_last_stats": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pmg_pc_profile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int]),
 }
 
 _lib = None
@@ -531,6 +532,13 @@ class PC:
         ms, l, u = C.c_double(), C.c_int64(), C.c_int64()
         _check(lib().pmg_pc_last_stats(self._h, C.byref(ms), C.byref(l), C.byref(u)))
         return {"ms": ms.value, "launches": l.value, "dof_updates": u.value}
+
+    def profile(self, reset=True):
+        """Per-kernel totals of the V-cycle since the last reset (enable with set_option("-pc_b200_profile", 1))."""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().pmg_pc_profile(self._h, buf, len(buf), 1 if reset else 0))
+        return json.loads(buf.value.decode())
 
     def close(self):
         if self._h:

@@ -368,6 +368,20 @@ struct pmg_pc_s {
   cudaEvent_t    ev0 = nullptr, ev1 = nullptr;
   double         last_ms = 0;
   int64_t        last_launches = 0, last_updates = 0;
+  // per-kernel profile of the V-cycle (-pc_b200_profile): CUDA events around every labelled launch on the launching stream
+  struct ProfRec {
+    std::string label;
+    double      bytes_min, bytes_survey; // compulsory traffic of the fused kernel; sum of SURVEY 8(d)'s per-unit figures it replaces
+    cudaEvent_t e0, e1;
+  };
+  struct ProfSum {
+    double  ms = 0, bytes_min = 0, bytes_survey = 0;
+    int64_t launches = 0;
+  };
+  bool                           prof_on = false;
+  std::vector<ProfRec>           prof_pending;
+  std::map<std::string, ProfSum> prof_sum;
+  std::vector<std::string>       prof_order;
 
   explicit pmg_pc_s(pmg_ctx c) : ctx(c) { pmg_ctx_retain(c); }
   ~pmg_pc_s()
@@ -402,6 +416,41 @@ static int noise_mode(pmg_pc pc)
   const NoiseStream *ns = &pc->noise;
   while (ns->parent) ns = ns->parent;
   return ns->mode;
+}
+
+// ---- per-kernel profile ----
+static int prof_begin(pmg_pc pc, const std::string &label, double bytes_min, double bytes_survey)
+{
+  if (!pc->prof_on) return 0;
+  pmg_pc_s::ProfRec r;
+  r.label = label; r.bytes_min = bytes_min; r.bytes_survey = bytes_survey;
+  PMG_CUDA(cudaEventCreate(&r.e0));
+  PMG_CUDA(cudaEventCreate(&r.e1));
+  PMG_CUDA(cudaEventRecord(r.e0, pc->ctx->stream));
+  pc->prof_pending.push_back(r);
+  return 0;
+}
+static int prof_end(pmg_pc pc)
+{
+  if (!pc->prof_on || pc->prof_pending.empty()) return 0;
+  PMG_CUDA(cudaEventRecord(pc->prof_pending.back().e1, pc->ctx->stream));
+  return 0;
+}
+static int prof_collect(pmg_pc pc)
+{
+  if (pc->prof_pending.empty()) return 0;
+  PMG_CUDA(cudaStreamSynchronize(pc->ctx->stream));
+  for (auto &r : pc->prof_pending) {
+    float ms = 0;
+    PMG_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (!pc->prof_sum.count(r.label)) pc->prof_order.push_back(r.label);
+    auto &a = pc->prof_sum[r.label];
+    a.ms += ms; a.bytes_min += r.bytes_min; a.bytes_survey += r.bytes_survey; a.launches++;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  pc->prof_pending.clear();
+  return 0;
 }
 
 static int configure_sampler(pmg_pc pc, const std::string &prefix, const std::string &pctype, LevelSampler &s)
@@ -522,7 +571,11 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
 {
   pmg_ctx  ctx = pc->ctx;
   MgLevel &v   = pc->lv[l];
-  if (l == pc->tail_top && zero_guess && b == v.b.p && x == v.x.p) return mg_tail(pc, l); // levels 0..l in one launch
+  if (l == pc->tail_top && zero_guess && b == v.b.p && x == v.x.p) { // levels 0..l in one launch
+    PMG_TRY(prof_begin(pc, "L0-L" + std::to_string(l) + " coarse tail (one cluster launch)", 0, 0));
+    PMG_TRY(mg_tail(pc, l));
+    return prof_end(pc);
+  }
   const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p;
   // stencil-array levels: each directional sweep is one out-of-place pass (box_stream.cuh); the level's iterate
   // ping-pongs between v.x and v.x2, so the current one is always v.x.p
@@ -582,8 +635,9 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   }
   if (!fused) {
     if (zero_guess) PMG_CUDA(cudaMemsetAsync(x, 0, (size_t)v.op->n() * sizeof(double), ctx->stream));
+    if (l == 0 && v.smp.kind == KIND_CHOL) PMG_TRY(prof_begin(pc, "L0 dense Cholesky sample", 16.0 * (double)v.smp.chol.n * (double)v.smp.chol.n, 16.0 * (double)v.smp.chol.n * (double)v.smp.chol.n));
     PMG_TRY(run_level_sampler(pc, v.smp, b, x));
-    if (l == 0) return 0;
+    if (l == 0) return prof_end(pc);
     MgLevel &c = pc->lv[l - 1];
     if (v.P->fused_residual_ok() && !v.op->lrc_data()) PMG_TRY(v.P->restrict_residual(b, x, c.b.p));
     else {
@@ -608,13 +662,24 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
       PMG_CUDA(cudaMemsetAsync(cur, 0, (size_t)v.op->fused_size() * sizeof(double), ctx->stream));
       xin = cur;
     }
+    if (pc->prof_on) {
+      // bytes per DOF: compulsory traffic of this pass (b, x in unless zero, x out, b_c out) | SURVEY 8(d): K1 (24 at omega = 1, else 32) [+ K3 24 + K4 10]
+      const double nn = (double)v.op->n(), k1 = v.smp.gibbs.omega == 1.0 ? 24.0 : 32.0;
+      PMG_TRY(prof_begin(pc, "L" + std::to_string(l) + (last ? " pre-sample+residual+restrict" : " sweep"), nn * ((b ? 8 : 0) + (xin ? 8 : 0) + 8 + (last ? 2 : 0)), nn * (k1 + (last ? 34 : 0))));
+    }
     PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, xin, oth, na, c.op, nullptr, last ? c.b.p : nullptr));
+    PMG_TRY(prof_end(pc));
     std::swap(cur, oth);
   }
   PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
   for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+    if (pc->prof_on) { // K5 (18) + K1
+      const double nn = (double)v.op->n(), k1 = v.smp.gibbs.omega == 1.0 ? 24.0 : 32.0;
+      PMG_TRY(prof_begin(pc, "L" + std::to_string(l) + (s == 0 ? " prolong+post-sample" : " sweep"), nn * ((b ? 8 : 0) + 8 + 8 + (s == 0 ? 2 : 0)), nn * (k1 + (s == 0 ? 18 : 0))));
+    }
     PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? pc->lv[l - 1].x.p : nullptr, nullptr));
+    PMG_TRY(prof_end(pc));
     std::swap(cur, oth);
   }
   if (cur != x) PMG_CUDA(cudaMemcpyAsync(x, cur, (size_t)v.op->fused_size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -884,6 +949,7 @@ static int richardson_dev(pmg_pc pc, const double *b, double *y, int64_t its, in
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   PMG_CUDA(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+  PMG_TRY(prof_collect(pc));
   pc->last_ms       = ms;
   pc->last_launches = ctx->launches - l0;
   pc->last_updates  = ctx->dof_updates - u0;
@@ -1172,6 +1238,10 @@ int pmg_pc_set_option(pmg_pc pc, const char *key, const char *value)
   if (!key) PMG_FAIL(PMG_ERR_ARG, "null option key");
   std::string k = key;
   while (!k.empty() && k[0] == '-') k.erase(0, 1);
+  if (k == "pc_b200_profile") { // measurement switch: does not invalidate the set-up
+    pc->prof_on = opt_true(value ? value : "");
+    return PMG_OK;
+  }
   pc->opts[k]  = value ? value : "";
   pc->is_setup = false;
   return PMG_OK;
@@ -1503,6 +1573,34 @@ int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int
   PMG_TRY(launch_normal_fill(ctx, na, n, d.p));
   PMG_CUDA(cudaMemcpyAsync(z, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMG_OK;
+}
+
+// Per-kernel profile of the V-cycle since the last reset, as JSON: [{"kernel": label, "launches": n, "ms": total,
+// "bytes_min": compulsory bytes, "bytes_survey": SURVEY 8(d) bytes}, ...] in first-launch order.  Enabled with
+// pmg_pc_set_option(pc, "-pc_b200_profile", "1") (may be switched at any time; events are recorded around every labelled launch).
+int pmg_pc_profile(pmg_pc pc, char *buf, size_t len, int reset)
+{
+  pmg_stale("pmg_pc_profile");
+  PMG_TRY(prof_collect(pc));
+  std::string s = "[";
+  char        t[512];
+  bool        first = true;
+  for (const auto &label : pc->prof_order) {
+    const auto &a = pc->prof_sum[label];
+    snprintf(t, sizeof t, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"bytes_min\": %.0f, \"bytes_survey\": %.0f}", first ? "" : ", ", label.c_str(), (long long)a.launches, a.ms, a.bytes_min, a.bytes_survey);
+    s += t;
+    first = false;
+  }
+  s += "]";
+  if (buf && len) {
+    std::strncpy(buf, s.c_str(), len - 1);
+    buf[len - 1] = 0;
+  }
+  if (reset) {
+    pc->prof_sum.clear();
+    pc->prof_order.clear();
+  }
   return PMG_OK;
 }
 
