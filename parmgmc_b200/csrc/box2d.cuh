@@ -69,8 +69,10 @@ struct __align__(16) Cls {
 };
 
 struct Args {
-  CUtensorMap   tm_x, tm_b; // {pitch, ny} FP64 tensors, box 128 x 2
-  int           nx, ny, pitch;
+  CUtensorMap   tm_x, tm_b; // {pitch, rows held} FP64 tensors, box 128 x 2
+  int           nx, ny, pitch; // GLOBAL grid; row stride
+  int           tlo;           // first grid row held by the tensors and by xout (a slab holds its rows plus four ghost rows per side)
+  int           ctlo;          // first coarse row held by xc / bc
   const Item   *items;
   int           nitems;
   int           has_x, has_b; // 0: the iterate / right-hand side is zero and is not read
@@ -218,7 +220,7 @@ template <int NOISE, int MODE, int PC, bool GENERAL> struct Warp {
       acc[q] = s;
     }
     const int I0 = c >> 1;
-    double   *p  = a.bc + (long long)J * a.cpitch + I0;
+    double   *p  = a.bc + (long long)(J - a.ctlo) * a.cpitch + I0;
     if (!GENERAL && (a.cpitch & 1) == 0) st128(p, acc[0], acc[1]);
     else { // pad columns of a pitched coarse vector are written as zeros (an even fine row length leaves a real residual beside them)
       if (I0 < a.ccols) p[0] = I0 < a.cnx ? acc[0] : 0.0;
@@ -233,7 +235,7 @@ template <int NOISE, int MODE, int PC, bool GENERAL> struct Warp {
     const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
     const int    I0 = c >> 1; // c = 0 mod 4: fine columns c .. c+3 see coarse columns I0, I0+1, I0+2
     if (!GENERAL) {
-      const double *p = a.xc + (long long)Jlo * a.cpitch + I0;
+      const double *p = a.xc + (long long)(Jlo - a.ctlo) * a.cpitch + I0;
       for (int q = 0; q < nJ; ++q, p += a.cpitch) {
         const double c0v = p[0], c1v = p[1], c2v = p[2];
         out[0] = fma(wj, c0v, out[0]);
@@ -248,7 +250,7 @@ template <int NOISE, int MODE, int PC, bool GENERAL> struct Warp {
       const int J = Jlo + q;
       if (J >= a.cny) continue;
       double        cv[3];
-      const double *p = a.xc + (long long)J * a.cpitch + I0;
+      const double *p = a.xc + (long long)(J - a.ctlo) * a.cpitch + I0;
 #pragma unroll
       for (int m = 0; m < 3; ++m) cv[m] = (I0 + m >= 0 && I0 + m < a.cnx) ? p[m] : 0.0;
       if (c >= 0 && c < a.nx) out[0] = fma(wj, cv[0], out[0]);
@@ -266,7 +268,7 @@ template <int NOISE, int MODE, int PC, bool GENERAL> struct Warp {
   __device__ __forceinline__ void prefetch_coarse(int j) const // the coarse rows that fine rows j, j+1 will read
   {
     if (GENERAL) return;
-    const double *p = a.xc + (long long)(j >> 1) * a.cpitch + (c >> 1);
+    const double *p = a.xc + (long long)((j >> 1) - a.ctlo) * a.cpitch + (c >> 1);
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cpitch));
@@ -310,8 +312,8 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     const int      s   = t % STAGES;
     const uint32_t dst = ring + s * STAGE_BYTES, bar = bars + s * 8;
     mbar_expect_tx(bar, bytes);
-    if (a.has_x) tma_load_3d(dst, &a.tm_x, c0, e0 + 2 * t + 1, 0, bar);
-    if (a.has_b) tma_load_3d(dst + 2 * ROW_BYTES, &a.tm_b, c0, e0 + 2 * t - 1, 0, bar);
+    if (a.has_x) tma_load_3d(dst, &a.tm_x, c0, e0 + 2 * t + 1 - a.tlo, 0, bar);
+    if (a.has_b) tma_load_3d(dst + 2 * ROW_BYTES, &a.tm_b, c0, e0 + 2 * t - 1 - a.tlo, 0, bar);
   };
   double Rm3[4] = {0, 0, 0, 0}, Rm2[4] = {0, 0, 0, 0}, Rm1[4] = {0, 0, 0, 0}, R0[4] = {0, 0, 0, 0};
   if (bytes == 0) { // nothing to fetch (zero iterate, zero right-hand side): the mbarriers are never armed
@@ -319,7 +321,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     // prologue rows e0-1, e0 travel through the x half of the LAST ring slot, whose first real stage is issued afterwards
     if (lane == 0) {
       mbar_expect_tx(bar_pro, 2 * ROW_BYTES);
-      tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, e0 - 1, 0, bar_pro);
+      tma_load_3d(ring + (STAGES - 1) * STAGE_BYTES, &a.tm_x, c0, e0 - 1 - a.tlo, 0, bar_pro);
       for (int t = 0; t < STAGES - 1 && t < T; ++t) issue(t);
     }
     mbar_wait(bar_pro, 0);
@@ -368,8 +370,8 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     W.row_update(e, R0, Rm1, xa, bA, zA);      // A row e: neighbours rows e-1, e+1 old
     W.row_update(e - 1, Rm1, Rm2, R0, bB, zB); // B row e-1: neighbour rows e-2, e final
     if (out_lane) {
-      if (e >= it.ja && e < it.jb) st256(a.xout + (long long)e * a.pitch + c, R0);
-      if (e - 1 >= it.ja && e - 1 < it.jb) st256(a.xout + (long long)(e - 1) * a.pitch + c, Rm1);
+      if (e >= it.ja && e < it.jb) st256(a.xout + (long long)(e - a.tlo) * a.pitch + c, R0);
+      if (e - 1 >= it.ja && e - 1 < it.jb) st256(a.xout + (long long)(e - 1 - a.tlo) * a.pitch + c, Rm1);
     }
     if (MODE == MODE_RESTRICT) {
       double rX[4], rY[4]; // residual rows e-2, e-1 (rows <= e are final)

@@ -233,6 +233,8 @@ struct LevelOp {
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
+  virtual bool    distributed() const { return false; }  // this rank holds a slab of the level, not the whole level
+  virtual int64_t level_first_row() const { return 0; } // first unit of the slowest dimension held by this level's V-cycle vectors
   virtual bool    box2_capable() const { return false; } // a Galerkin level that can run on the one-pass kernels once its vectors are pitched
   virtual int64_t box2_pitch() const { return 0; }
   virtual bool fused_mg_ok() const { return false; } // fused_sweep also does the prolongation / residual + restriction
@@ -310,6 +312,9 @@ struct Transfer {
     pmg_set_error("pitched prolongation not available for this transfer");
     return PMG_ERR_SUP;
   }
+  // hooks of the fused transfers (the fine level's kernels write b_coarse / read x_coarse themselves): refresh what other ranks own
+  virtual int fused_after_restrict(double *b_coarse) { (void)b_coarse; return 0; }
+  virtual int fused_before_prolong(double *x_coarse) { (void)x_coarse; return 0; }
   virtual int restrict_to(const double *r_fine, double *b_coarse) = 0; // b_c = P^T r
   virtual int prolong_add(const double *x_coarse, double *x_fine) = 0; // x_f += P x_c
 };

@@ -576,7 +576,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(mg_tail(pc, l));
     return prof_end(pc);
   }
-  const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p;
+  const bool fused = l > 0 && v.smp.kind != KIND_CHOL && v.op->fused_mg_ok() && v.x2.p && !(v.op->distributed() && pc->lv[l - 1].op->distributed() && !pc->lv[l - 1].op->level_pitch);
   // stencil-array levels: each directional sweep is one out-of-place pass (box_stream.cuh); the level's iterate
   // ping-pongs between v.x and v.x2, so the current one is always v.x.p
   const bool bstream = !fused && l > 0 && v.smp.kind != KIND_CHOL && v.x2.p && x == v.x.p && v.op->stream_ok() &&
@@ -671,7 +671,9 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     PMG_TRY(prof_end(pc));
     std::swap(cur, oth);
   }
+  PMG_TRY(v.P->fused_after_restrict(c.b.p)); // slabs: ghost rows of the coarse right-hand side (or the gather of a replicated level)
   PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
+  PMG_TRY(v.P->fused_before_prolong(c.x.p));
   for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
     if (pc->prof_on) { // K5 (18) + K1
@@ -843,8 +845,13 @@ static int gamgmc_setup(pmg_pc pc)
     bool chain = pc->lv[L - 1].op->fused_mg_ok();
     for (int l = L - 2; l >= 1 && chain; --l) {
       LevelOp *o = pc->lv[l].op;
-      chain      = o->box2_capable() && o->n() > tail_max;
+      chain      = o->box2_capable() && (o->distributed() || o->n() > tail_max);
       if (chain) o->level_pitch = o->box2_pitch();
+    }
+    // a slab level's fused transfers write / read the level below in place: that level must be pitched too (or held in full)
+    for (int l = 1; l <= L - 2; ++l) {
+      LevelOp *o = pc->lv[l].op, *c = pc->lv[l - 1].op;
+      if (o->level_pitch && o->distributed() && c->distributed() && !c->level_pitch) o->level_pitch = 0;
     }
   }
   // samplers: defaults of src/pc_gamgmc.c:305-349 (levels: richardson + sorgibbs, 1 it; coarse: cholsampler)

@@ -670,7 +670,7 @@ __global__ void box_class_kernel(Geom g, const double *__restrict__ coef, int64_
 {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.nl) return;
-  const int64_t i = idx % g.n0, j = idx / g.n0;
+  const int64_t i = idx % g.n0, j = g.slo + idx / g.n0; // global row
   const int     cc = i == 0 ? 0 : (i == g.n0 - 1 ? 2 : 1), rc = j == 0 ? 0 : (j == g.n1 - 1 ? 2 : 1);
   bool          same = true;
   for (int s = 0; s < 9; ++s) same = same && (__double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(t.c[3 * rc + cc][s]));
@@ -978,6 +978,7 @@ struct GridOp : LevelOp {
   bool           parallel = false;
 
   int64_t n() const override { return g.nl; }
+  bool    distributed() const override { return parallel; }
   bool    matrix_free() const override { return true; }
   int64_t nglobal() const override { return g.n0 * g.n1 * g.n2; }
   int64_t row0() const override { return g.row0(); }
@@ -1097,12 +1098,13 @@ struct LapOp final : GridOp {
   bool fused_ok() const override
   {
     if (std::getenv("PMG_NO_FUSED")) return false; // read per call: the tests switch paths inside one process
-    if (parallel && (min_units < 2 || std::getenv("PMG_NO_FUSED_PARALLEL"))) return false; // two ghost units per side come from ONE neighbour
+    if (parallel && (min_units < GH() || std::getenv("PMG_NO_FUSED_PARALLEL"))) return false; // the ghost units of a side come from ONE neighbour
     if (g.dim == 2) return g.n0 >= 8 && g.n1 >= 4 && g.n0 < (1 << 30) && g.n1 < (1 << 30);
     return g.n0 >= 8 && g.n1 >= 2 && g.n2 >= 2 && g.n0 < (1 << 20) && g.n1 < (1 << 20) && g.n2 < (1 << 20);
   }
-  bool fused_mg_ok() const override { return fused_ok() && !parallel && (g.dim == 2 || !std::getenv("PMG_NO_FUSED_MG3")); }
-  bool fused_null_xin_ok() const override { return g.dim == 2; }
+  // the fused grid transfers run on slabs in 2D (ghost rows of the coarse vectors, common.hpp Transfer::fused_after_restrict)
+  bool fused_mg_ok() const override { return fused_ok() && (g.dim == 2 ? (!parallel || !std::getenv("PMG_NO_FUSED_MG_PARALLEL")) : (!parallel && !std::getenv("PMG_NO_FUSED_MG3"))); }
+  bool fused_null_xin_ok() const override { return g.dim == 2 && !parallel; }
   bool pitched_is_natural() const override { return !parallel && pitch() == g.n0; }
   bool fused_smooth_ok() const override { return parallel && fused_ok() && !std::getenv("PMG_NO_FUSED_SMOOTH"); }
   bool pitched_view(Geom &gp, int64_t &own_offset) const override
@@ -1132,7 +1134,8 @@ struct LapOp final : GridOp {
   // updates both colours, so the boundary unit's second-colour update needs the neighbour's boundary unit AFTER its
   // first-colour update, which is recomputed here from two old ghost units (and the ghost unit of b; the noise is a
   // function of the global index).  One exchange of 2 units per sweep replaces the reference's per-colour scatters.
-  int     GH() const { return parallel ? 2 : 0; }
+  // 2D: six ghost rows, what the pre-smoother with the fused residual + restriction reads beyond its band (sweep2d.cuh RESTRICT)
+  int     GH() const { return parallel ? (g.dim == 2 ? 6 : 2) : 0; }
   int64_t unit_rows() const { return g.dim == 2 ? 1 : g.n1; }
   int     fused_halo(double *pitched)
   {
@@ -1405,13 +1408,15 @@ struct LapOp final : GridOp {
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;
     a.xout  = xout;
-    a.xc = nullptr; a.bc = nullptr; a.cnx = a.cny = a.cpitch = 0;
+    a.xc = nullptr; a.bc = nullptr; a.cnx = a.cny = a.cpitch = a.ctlo = 0;
     if (xc || bc) { // prolongation / residual + restriction fused into the sweep: the coarse level is a whole grid on this device
       int     cd;
       int64_t cn[3];
-      if (!coarse || !coarse->structured(cd, cn) || parallel) PMG_FAIL(PMG_ERR_SUP, "fused grid transfers need a structured coarse level on one device");
+      if (!coarse || !coarse->structured(cd, cn)) PMG_FAIL(PMG_ERR_SUP, "fused grid transfers need a structured coarse level");
       a.xc = xc; a.bc = bc; a.cnx = (int)cn[0]; a.cny = (int)cn[1];
       a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
+      a.ctlo   = (int)coarse->level_first_row();
+      if (parallel && !coarse->level_pitch && coarse->level_first_row() != 0) PMG_FAIL(PMG_ERR_SUP, "fused grid transfers on a slab need a pitched (or whole) coarse level");
     }
     a.tape  = na.tape;
     a.h = t.h; a.idiag = t.idiag[4]; a.sd = t.sqrtdiag[4]; a.omo = 1.0 - co.omega; a.diag = t.diag[4];
@@ -1422,7 +1427,6 @@ struct LapOp final : GridOp {
     if (bc) { // pre-smoother + residual + restriction
       const int rcfg_env = std::getenv("PMG_SW2R_CFG") ? std::atoi(std::getenv("PMG_SW2R_CFG")) : 1; // 168 registers, 12 warps / SM measured fastest (profiles/r2_summary.md)
       static const int rby_env  = std::getenv("PMG_SW2R_BY") ? std::atoi(std::getenv("PMG_SW2R_BY")) : 0;
-      if ((g.slo & 1) != 0) PMG_FAIL(PMG_ERR_SUP, "fused restriction needs an even first row");
       if (items2r_cfg != rcfg_env) {
         a.items = nullptr; a.nitems = 0;
         int slots = 0;
@@ -1745,47 +1749,89 @@ struct BoxOp final : GridOp {
   // ---- one-pass TMA kernels (box2d.cuh): 2D, one device, PITCHED level vectors (LevelOp::level_pitch) ----
   bool        classes_ok = false;
   BoxClassTab cls_tab;
+  // Every rank contributes the class representatives it owns (row class 0 lives on the first rank only, ...); the merged table is
+  // verified against every owned node on every rank, and the verdict is the same everywhere (the kernels are collective on slabs).
   int         detect_classes()
   {
     classes_ok = false;
-    if (g.dim != 2 || parallel || g.slo != 0 || g.shi != g.n1 || g.n0 < 3 || g.n1 < 3 || g.nl >= ((int64_t)1 << 31)) return 0;
+    const int64_t rows = g.shi - g.slo;
+    if (g.dim != 2 || g.n0 < 3 || g.n1 < 3 || g.nl >= ((int64_t)1 << 31)) return 0;
+    if (!parallel && (g.slo != 0 || g.shi != g.n1)) return 0;
     const int64_t ri[3] = {0, 1, g.n0 - 1}, rj[3] = {0, 1, g.n1 - 1};
-    for (int rc = 0; rc < 3; ++rc)
-      for (int cc = 0; cc < 3; ++cc)
-        for (int s = 0; s < 9; ++s) PMG_CUDA(cudaMemcpyAsync(&cls_tab.c[3 * rc + cc][s], coef.p + (size_t)s * g.nl + (size_t)(ri[cc] + g.n0 * rj[rc]), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int64_t> mine(90, 0); // 81 coefficients (bit patterns) + 9 "have it" flags
+    for (int rc = 0; rc < 3; ++rc) {
+      int64_t j = rj[rc];
+      if (rc == 1 && !(j >= g.slo && j < g.shi)) { // any owned interior row serves as the interior representative
+        j = std::max<int64_t>(g.slo, 1);
+        if (j >= std::min<int64_t>(g.shi, g.n1 - 1)) j = -1;
+      }
+      if (j < g.slo || j >= g.shi || rows <= 0) continue;
+      for (int cc = 0; cc < 3; ++cc) {
+        for (int s = 0; s < 9; ++s) PMG_CUDA(cudaMemcpyAsync(&mine[(size_t)(9 * (3 * rc + cc) + s)], coef.p + (size_t)s * g.nl + (size_t)(ri[cc] + g.n0 * (j - g.slo)), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        mine[(size_t)(81 + 3 * rc + cc)] = 1;
+      }
+    }
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    DevBuf<unsigned long long> cnt;
-    PMG_TRY(cnt.alloc(1));
-    PMG_TRY(cnt.zero(ctx->stream));
-    box_class_kernel<<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, cls_tab, cnt.p);
-    PMG_CUDA(cudaGetLastError());
-    unsigned long long bad = 1;
-    PMG_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
-    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    classes_ok = bad == 0;
+    std::vector<int64_t> all((size_t)90 * ctx->nranks, 0);
+    PMG_TRY(comm_allgather_i64(ctx, mine.data(), 90, all.data()));
+    bool have_all = true;
+    for (int q = 0; q < 9; ++q) {
+      int src = -1;
+      for (int r = 0; r < ctx->nranks && src < 0; ++r)
+        if (all[(size_t)90 * r + 81 + q]) src = r;
+      if (src < 0) { have_all = false; continue; }
+      std::memcpy(cls_tab.c[q], &all[(size_t)90 * src + 9 * q], 9 * sizeof(double));
+    }
+    unsigned long long bad = have_all ? 0 : 1;
+    if (have_all && g.nl > 0) {
+      DevBuf<unsigned long long> cnt;
+      PMG_TRY(cnt.alloc(1));
+      PMG_TRY(cnt.zero(ctx->stream));
+      box_class_kernel<<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, cls_tab, cnt.p);
+      PMG_CUDA(cudaGetLastError());
+      PMG_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const int64_t        mybad = (int64_t)bad;
+    std::vector<int64_t> allbad((size_t)ctx->nranks, 0);
+    PMG_TRY(comm_allgather_i64(ctx, &mybad, 1, allbad.data()));
+    classes_ok = true;
+    for (int64_t v : allbad) classes_ok = classes_ok && v == 0;
     return 0;
   }
   int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
+  // a slab keeps four ghost rows per side in its pitched vectors: what one sweep with the fused residual + restriction (zero
+  // iterate) or prolongation reads beyond its band (box2d.cuh band_range / band_steps)
+  int     GHB() const { return parallel ? 4 : 0; }
+  int64_t level_first_row() const override { return level_pitch ? g.slo - GHB() : (parallel ? g.slo : 0); }
   // the level can run on the one-pass kernels; whether it does is the V-cycle's decision (it must keep the vectors pitched)
-  bool box2_capable() const override { return classes_ok && g.n0 >= 16 && g.n1 >= 8 && !std::getenv("PMG_NO_BOX2"); }
+  bool box2_capable() const override { return classes_ok && g.n0 >= 16 && g.n1 >= 8 && (!parallel || min_units >= GHB()) && !std::getenv("PMG_NO_BOX2") && !(parallel && std::getenv("PMG_NO_FUSED_MG_PARALLEL")); }
   int64_t box2_pitch() const override { return pitch(); }
   bool    fused_ok() const override { return level_pitch != 0; }
   bool    fused_mg_ok() const override { return level_pitch != 0; }
-  int64_t fused_size() const override { return level_pitch ? level_pitch * g.n1 : n(); }
-  int     to_pitched(const double *natural, double *pitched) override
+  bool    fused_tape_ok() const override { return !parallel; }
+  int64_t fused_size() const override { return level_pitch ? level_pitch * (g.shi - g.slo + 2 * GHB()) : n(); }
+  int     pitched_halo(double *v) override
   {
-    const Plan pl = plan3(g.n0, g.n1, 1);
+    if (!parallel) return 0;
+    const int64_t U = level_pitch, nu = g.shi - g.slo, G = GHB();
+    double       *own = v + G * U;
+    return comm_halo_exchange(ctx, own, v, own + (nu - G) * U, own + nu * U, (size_t)(G * U), (size_t)(G * U), ctx->stream);
+  }
+  int to_pitched(const double *natural, double *pitched) override
+  {
+    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.n1, pitch(), natural, pitched);
+    repitch_kernel<true><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), natural, pitched + GHB() * pitch());
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
-    return 0;
+    return pitched_halo(pitched);
   }
   int from_pitched(const double *pitched, double *natural) override
   {
-    const Plan pl = plan3(g.n0, g.n1, 1);
+    const Plan pl = plan3(g.n0, g.shi - g.slo, 1);
     PMG_PLAN_CHECK(pl);
-    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.n1, pitch(), pitched, natural);
+    repitch_kernel<false><<<pl.grid, pl.block, 0, ctx->stream>>>(g.n0, g.shi - g.slo, pitch(), pitched + GHB() * pitch(), natural);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -1812,11 +1858,11 @@ struct BoxOp final : GridOp {
       static const int by_min = std::getenv("PMG_BOX2_BY_MIN") ? std::atoi(std::getenv("PMG_BOX2_BY_MIN")) : 4;
       const int        slots   = occ_dev[dv] * WARPS * ctx->sm_count;
       const int        nstrips = (int)((g.n0 + Strip<MODE>::OUT - 1) / Strip<MODE>::OUT);
-      int              by      = by_env > 0 ? by_env : std::max<int>(by_min, (int)((g.n1 * nstrips + slots - 1) / slots));
+      int              by      = by_env > 0 ? by_env : std::max<int>(by_min, (int)(((g.shi - g.slo) * nstrips + slots - 1) / slots));
       by += by & 1;
       std::vector<Item> list;
-      for (int64_t j = 0; j < g.n1; j += by)
-        for (int st = 0; st < nstrips; ++st) list.push_back(Item{st, (int)j, (int)std::min<int64_t>(j + by, g.n1)});
+      for (int64_t j = g.slo; j < g.shi; j += by)
+        for (int st = 0; st < nstrips; ++st) list.push_back(Item{st, (int)j, (int)std::min<int64_t>(j + by, g.shi)});
       b2n[r] = (int)list.size();
       PMG_TRY(b2items[r].upload(list, ctx->stream));
       PMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1846,12 +1892,15 @@ struct BoxOp final : GridOp {
     if (!level_pitch) PMG_FAIL(PMG_ERR_ORDER, "one-pass sweep on a level whose vectors are not pitched");
     if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
     if (xc && !xin) PMG_FAIL(PMG_ERR_ARG, "fused prolongation needs a fine iterate");
+    if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "one-pass sweep on a slab cannot take an injected tape");
+    if (xin) PMG_TRY(pitched_halo(const_cast<double *>(xin))); // replaces the per-colour VecScatter of src/mc_sor.c:318-319: one exchange per sweep
     Args a;
     std::memset(&a, 0, sizeof a);
-    const int64_t P = level_pitch;
-    const int64_t dims[3] = {P, g.n1, 1}, strides[3] = {1, P, P * g.n1};
+    const int64_t P = level_pitch, held = g.shi - g.slo + 2 * GHB();
+    const int64_t dims[3] = {P, held, 1}, strides[3] = {1, P, P * held};
     const int     box[3]  = {128, 2, 1};
     const double *any = xin ? xin : (b ? b : xout);
+    a.tlo = (int)(g.slo - GHB());
     PMG_TRY(make_tensor_map(a.tm_x, xin ? xin : any, 3, dims, strides, box, false));
     PMG_TRY(make_tensor_map(a.tm_b, b ? b : any, 3, dims, strides, box, false));
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.pitch = (int)P;
@@ -1864,6 +1913,8 @@ struct BoxOp final : GridOp {
       a.cnx = (int)cn[0]; a.cny = (int)cn[1];
       a.cpitch = (int)(coarse->level_pitch ? coarse->level_pitch : cn[0]);
       a.ccols  = a.cpitch;
+      a.ctlo   = (int)coarse->level_first_row();
+      if (parallel && !coarse->level_pitch && coarse->level_first_row() != 0) PMG_FAIL(PMG_ERR_SUP, "fused grid transfers on a slab need a pitched (or whole) coarse level");
     }
     a.mode = na.mode; a.tape = na.tape;
     for (int q = 0; q < 16; ++q) {
@@ -1960,6 +2011,10 @@ template <int DIM> __global__ void __launch_bounds__(256) box_restrict_residual_
 struct GridTransfer final : Transfer {
   pmg_ctx ctx;
   GridOp *fine, *coarse;
+  // fused transfers on slabs: the kernels of the fine level write / read the coarse level's pitched vectors directly; the ghost
+  // rows of those vectors are refreshed here (one grouped send / receive per call)
+  int fused_after_restrict(double *b_coarse) override { return coarse->parallel && coarse->level_pitch ? coarse->pitched_halo(b_coarse) : 0; }
+  int fused_before_prolong(double *x_coarse) override { return coarse->parallel && coarse->level_pitch ? coarse->pitched_halo(x_coarse) : 0; }
   bool    tail_ok() const override { return !fine->parallel && !coarse->parallel; }
   bool    fused_residual_ok() const override
   {
@@ -2045,6 +2100,19 @@ struct ReplicatingTransfer final : Transfer {
   Geom                 gc; // this rank's slab of the coarse grid (owner of fine unit 2J owns coarse unit J)
   std::vector<int64_t> counts, displs;
   DevBuf<double>       slab;
+  GridOp              *coarse_full = nullptr;
+  std::vector<int64_t> crows; // coarse units [cs[2r], cs[2r+1]) owned by rank r
+  // fused transfers: every rank's kernel has written its coarse rows into the full vector; gather the others' in place
+  int fused_after_restrict(double *b_coarse_full) override
+  {
+    const int64_t U = coarse_full->level_pitch ? coarse_full->level_pitch : gc.unit;
+    std::vector<int64_t> cnt((size_t)ctx->nranks), dsp((size_t)ctx->nranks);
+    for (int r = 0; r < ctx->nranks; ++r) {
+      cnt[(size_t)r] = U * (crows[2 * (size_t)r + 1] - crows[2 * (size_t)r]);
+      dsp[(size_t)r] = U * crows[2 * (size_t)r];
+    }
+    return comm_allgatherv(ctx, b_coarse_full + dsp[(size_t)ctx->rank], b_coarse_full, cnt.data(), dsp.data(), ctx->stream);
+  }
   int restrict_to(const double *r, double *bcoarse_full) override
   {
     PMG_TRY(fine->halo(r));
@@ -2288,6 +2356,8 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64
       t->ctx    = ctx;
       t->fine   = cur;
       t->gc     = gc;
+      t->coarse_full = full.get();
+      t->crows       = cs;
       t->counts.resize((size_t)R);
       t->displs.resize((size_t)R);
       for (int r = 0; r < R; ++r) {

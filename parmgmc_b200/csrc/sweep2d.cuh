@@ -59,6 +59,7 @@ struct Args {
   double       *xout;
   const double *xc;   // non-null: the sweep starts from xin + P xc (MatInterpolateAdd fused into the post-smoother); xc is the
   int           cnx, cny, cpitch; // coarse level's iterate on its cnx x cny grid, row stride cpitch (Q1)
+  int           ctlo;             // first coarse row held by xc / bc (a slab of the coarse level carries ghost rows)
   double       *bc;   // non-null (RESTRICT kernels): b_c = P^T (b - A xout), MatResidual + MatRestrict fused into the pre-smoother
   const double *tape; // injected noise of this block: natural layout (row stride nx), local rows
   double        h, idiag, sd, omo, diag; // interior coefficients
@@ -236,7 +237,7 @@ template <int NOISE, bool INTERIOR> struct Warp {
     const double rsw = shfl_up1(rs[3]), rmw = shfl_up1(rm[3]), rnw = shfl_up1(rn[3]);
     if (!out_lane) return;
     const int I0 = c >> 1;
-    double   *p  = a.bc + (long long)J * a.cpitch + I0;
+    double   *p  = a.bc + (long long)(J - a.ctlo) * a.cpitch + I0;
 #pragma unroll
     for (int q = 0; q < 2; ++q) { // coarse columns c/2 (fine c) and c/2 + 1 (fine c + 2)
       const double sW = q == 0 ? rsw : rs[1], sC = q == 0 ? rs[0] : rs[2], sE = q == 0 ? rs[1] : rs[3];
@@ -316,7 +317,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
     const double wj = (j & 1) ? 0.5 : 1.0, wh = 0.5 * wj;
     const int    I0 = c >> 1; // c = 0 mod 4: fine columns c .. c+3 see coarse columns I0, I0+1, I0+2
     if (INTERIOR) {
-      const double *p = a.xc + (long long)Jlo * a.cpitch + I0;
+      const double *p = a.xc + (long long)(Jlo - a.ctlo) * a.cpitch + I0;
       for (int q = 0; q < nJ; ++q, p += a.cpitch) {
         const double c0v = p[0], c1v = p[1], c2v = p[2];
         out[0] = fma(wj, c0v, out[0]);
@@ -331,7 +332,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       const int J = Jlo + q;
       if (J >= a.cny) continue;
       double        cv[3];
-      const double *p = a.xc + (long long)J * a.cpitch + I0;
+      const double *p = a.xc + (long long)(J - a.ctlo) * a.cpitch + I0;
 #pragma unroll
       for (int m = 0; m < 3; ++m) cv[m] = (I0 + m >= 0 && I0 + m < a.cnx) ? p[m] : 0.0;
       if (c >= 0 && c < a.nx) out[0] = fma(wj, cv[0], out[0]);
@@ -348,7 +349,7 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   };
   auto prefetch_coarse = [&](int j) { // the coarse rows that fine rows j, j+1 will read
     if (!INTERIOR || a.xc == nullptr) return;
-    const double *p = a.xc + (long long)(j >> 1) * a.cpitch + (c >> 1);
+    const double *p = a.xc + (long long)((j >> 1) - a.ctlo) * a.cpitch + (c >> 1);
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + a.cpitch));
