@@ -79,7 +79,11 @@ int pmg_ctx_comm_init(pmg_ctx ctx, int rank, int nranks, const unsigned char id[
   ctx->nccl_comm = comm;
   ctx->rank      = rank;
   ctx->nranks    = nranks;
-  if (!ctx->comm_stream) PMG_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  if (!ctx->comm_stream) { // highest priority: a halo exchange queued beside a sweep's interior launch must get its CTAs first
+    int lo = 0, hi = 0;
+    PMG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PMG_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+  }
   return PMG_OK;
 }
 

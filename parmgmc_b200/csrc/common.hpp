@@ -233,6 +233,9 @@ struct LevelOp {
   // Fused single-pass sweep (stream2d.cuh), out of place:  xout = sweep_dir(guess) with guess = xin (or 0 when xin is
   // null) plus P xc when xc is given; when bc is given also bc = P^T (b - A xout).  `coarse` supplies the coarse geometry.
   virtual bool fused_ok() const { return false; }
+  // Start refreshing the ghost units of the pitched vector v on the communication stream (ordered after everything queued
+  // on the compute stream so far); the next fused_sweep whose iterate is v waits for it instead of exchanging itself.
+  virtual int halo_begin(double *v) { (void)v; return 0; }
   virtual bool    distributed() const { return false; }  // this rank holds a slab of the level, not the whole level
   virtual int64_t level_first_row() const { return 0; } // first unit of the slowest dimension held by this level's V-cycle vectors
   virtual bool    box2_capable() const { return false; } // a Galerkin level that can run on the one-pass kernels once its vectors are pitched

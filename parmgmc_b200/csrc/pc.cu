@@ -672,6 +672,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     std::swap(cur, oth);
   }
   PMG_TRY(v.P->fused_after_restrict(c.b.p)); // slabs: ghost rows of the coarse right-hand side (or the gather of a replicated level)
+  PMG_TRY(v.op->halo_begin(cur));            // slabs: the post-smoother's ghost rows travel (communication stream) while the coarse levels work
   PMG_TRY(mg_cycle_direct(pc, l - 1, c.b.p, c.x.p, true));
   PMG_TRY(v.P->fused_before_prolong(c.x.p));
   for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c

@@ -1016,6 +1016,43 @@ struct GridOp : LevelOp {
   // pitched layout of the fused sweeps (LapOp): geometry, offset of the owned part, ghost exchange in place
   virtual bool pitched_view(Geom &gp, int64_t &own_offset) const { (void)gp; (void)own_offset; return false; }
   virtual int  pitched_halo(double *pitched) { (void)pitched; return PMG_ERR_SUP; }
+  // ---- halo exchange overlapped with the rows that do not need it (north_star: "exchanged over NVLink with NCCL send/recv,
+  //      overlapped with interior rows"; the reference's scatter is blocking, src/mc_sor.c:318-319) ----
+  // The exchange runs on the context's communication stream.  A sweep then launches the tiles that read no ghost unit,
+  // waits for the exchange on the compute stream, and launches the tiles along the slab boundaries.
+  cudaEvent_t   ev_ready = nullptr, ev_halo = nullptr;
+  const double *halo_inflight = nullptr;
+  virtual int   pitched_halo_on(double *pitched, cudaStream_t s) { (void)pitched; (void)s; return PMG_ERR_SUP; }
+  // early exchange of the post-smoother's ghost rows (V-cycle): on unless PMG_NO_EARLY_HALO; split sweep launches: opt-in with
+  // PMG_OVERLAP_SWEEP (measured on 2 x B200, profiles/r2_summary.md: the exchange kernel only gets CTAs when the interior launch
+  // drains, so the split costs more than the exchange it hides)
+  static bool   overlap_on() { return std::getenv("PMG_NO_EARLY_HALO") == nullptr; }
+  static bool   overlap_sweep_on() { return std::getenv("PMG_OVERLAP_SWEEP") != nullptr; }
+  int halo_begin(double *v) override
+  {
+    if (!parallel || !overlap_on() || !ctx->comm_stream) return 0;
+    if (!ev_ready) {
+      PMG_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+      PMG_CUDA(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
+    }
+    PMG_CUDA(cudaEventRecord(ev_ready, ctx->stream));
+    PMG_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ev_ready, 0));
+    PMG_TRY(pitched_halo_on(v, ctx->comm_stream));
+    PMG_CUDA(cudaEventRecord(ev_halo, ctx->comm_stream));
+    halo_inflight = v;
+    return 0;
+  }
+  int halo_wait() // the compute stream continues after the exchange
+  {
+    PMG_CUDA(cudaStreamWaitEvent(ctx->stream, ev_halo, 0));
+    halo_inflight = nullptr;
+    return 0;
+  }
+  ~GridOp() override
+  {
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_halo) cudaEventDestroy(ev_halo);
+  }
   virtual bool star() const = 0;
   int          ncolors() const override { return star() ? 2 : (g.dim == 3 ? 8 : 4); }
   int32_t      colour_of(int64_t i, int64_t j, int64_t k) const { return star() ? (int32_t)((i + j + k) & 1) : (int32_t)((i & 1) + 2 * (j & 1) + (g.dim == 3 ? 4 * (k & 1) : 0)); }
@@ -1114,6 +1151,7 @@ struct LapOp final : GridOp {
     return true;
   }
   int pitched_halo(double *p) override { return fused_halo(p); }
+  int pitched_halo_on(double *p, cudaStream_t s) override { return fused_halo(p, s); }
   int residual_pitched(const double *b, const double *x, double *r) override
   {
     PMG_TRY(fused_halo(const_cast<double *>(x)));
@@ -1137,12 +1175,12 @@ struct LapOp final : GridOp {
   // 2D: six ghost rows, what the pre-smoother with the fused residual + restriction reads beyond its band (sweep2d.cuh RESTRICT)
   int     GH() const { return parallel ? (g.dim == 2 ? 6 : 2) : 0; }
   int64_t unit_rows() const { return g.dim == 2 ? 1 : g.n1; }
-  int     fused_halo(double *pitched)
+  int     fused_halo(double *pitched, cudaStream_t s = nullptr)
   {
     if (!parallel) return 0;
     const int64_t U = unit_rows() * pitch(), nu = g.shi - g.slo;
     double       *own = pitched + GH() * U;
-    return comm_halo_exchange(ctx, own, pitched, own + (nu - GH()) * U, own + nu * U, (size_t)(GH() * U), (size_t)(GH() * U), ctx->stream);
+    return comm_halo_exchange(ctx, own, pitched, own + (nu - GH()) * U, own + nu * U, (size_t)(GH() * U), (size_t)(GH() * U), s ? s : ctx->stream);
   }
   // Work list of the streaming kernels.  Warps whose tile touches the physical boundary run the predicated loop, which
   // costs about 1.6x the interior loop per row (profiles/r1_summary.md), and the grid is a single wave, so those warps
@@ -1207,7 +1245,7 @@ struct LapOp final : GridOp {
   // ---- 3D: stream3d.cuh ----
   DevBuf<sweep3d::Item> items3;
   DevBuf<double>        r_pitched; // residual of the fused 3D top level (fused_sweep with bc)
-  int                   nitems3 = 0, items3_bz = 0, items3_nw = 0;
+  int                   nitems3 = 0, nitems3_nohalo = 0, items3_bz = 0, items3_nw = 0;
   int build_items3(int bz, int NW3) // NW3 warps per CTA tile: NW3 - 2 output rows + 2 halo rows (narrow strips: 2 NW3 - 2 + 2)
   {
     static const bool narrow_env = std::getenv("PMG_SW3_NONARROW") == nullptr;
@@ -1216,6 +1254,10 @@ struct LapOp final : GridOp {
     sweep3d_plan(g.n0, g.n1, g.n2, g.slo, g.shi, bz, NW3, narrow_env, thin_env, flat);
     std::vector<sweep3d::Item> all(flat.size() / 5);
     for (size_t q = 0; q < all.size(); ++q) all[q] = sweep3d::Item{flat[5 * q], flat[5 * q + 1], flat[5 * q + 2], flat[5 * q + 3], flat[5 * q + 4]};
+    // tiles that read no ghost plane first (they overlap the halo exchange), tiles along the slab boundaries last
+    std::stable_partition(all.begin(), all.end(), [&](const sweep3d::Item &it) { return !parallel || (it.ka - 2 >= g.slo && it.kb + 1 < g.shi); });
+    nitems3_nohalo = 0;
+    for (const auto &it : all) nitems3_nohalo += (!parallel || (it.ka - 2 >= g.slo && it.kb + 1 < g.shi)) ? 1 : 0;
     nitems3 = (int)all.size();
     PMG_TRY(items3.upload(all, ctx->stream));
     PMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1256,9 +1298,20 @@ struct LapOp final : GridOp {
     const int        bz     = bz_env > 0 ? bz_env : 64;
     if (items3_bz != bz || items3_nw != NW) PMG_TRY(build_items3(bz, NW));
     a.items = items3.p;
-    kern<<<(unsigned)nitems3, NW * 32 * (WS ? 2 : 1), sm, ctx->stream>>>(a);
+    if (split_launch && nitems3_nohalo > 0 && nitems3_nohalo < nitems3) { // interior tiles | wait for the halo | boundary tiles
+      kern<<<(unsigned)nitems3_nohalo, NW * 32 * (WS ? 2 : 1), sm, ctx->stream>>>(a);
+      PMG_TRY(halo_wait());
+      a.items = items3.p + nitems3_nohalo;
+      kern<<<(unsigned)(nitems3 - nitems3_nohalo), NW * 32 * (WS ? 2 : 1), sm, ctx->stream>>>(a);
+      ctx->launches++;
+    } else {
+      if (split_launch) PMG_TRY(halo_wait());
+      kern<<<(unsigned)nitems3, NW * 32 * (WS ? 2 : 1), sm, ctx->stream>>>(a);
+    }
+    split_launch = false;
     return 0;
   }
+  bool split_launch = false; // set by the sweep that started its halo exchange on the communication stream
   template <int NOISE> int launch3_cfg(int cfg, sweep3d::Args &a, const double *b, const double *xin)
   {
     switch (cfg) {
@@ -1268,6 +1321,20 @@ struct LapOp final : GridOp {
       if (NOISE == sweep3d::NOISE_PHILOX) return launch3<sweep3d::NOISE_PHILOX, 16, 4, 2, 1, true>(a, b, xin); // warp-specialised
       return launch3<NOISE, 16, 4, 2, 1>(a, b, xin);
     }
+  }
+  // ghost units of the sweep's iterate: already in flight (halo_begin by the caller), started here on the communication
+  // stream (the launch is then split), or exchanged on the compute stream (no communicator stream / PMG_NO_OVERLAP)
+  int start_halo(const double *xin)
+  {
+    split_launch = false;
+    if (!parallel) return 0;
+    if (halo_inflight == xin && xin) return halo_wait(); // exchanged ahead of time: one launch
+    if (overlap_sweep_on() && ctx->comm_stream) {
+      PMG_TRY(halo_begin(const_cast<double *>(xin)));
+      split_launch = true;
+      return 0;
+    }
+    return fused_halo(const_cast<double *>(xin));
   }
   int fused_sweep3(int dir, const SweepCoeffs &co, const double *b, const double *xin, double *xout, const NoiseArgs &na)
   {
@@ -1281,7 +1348,7 @@ struct LapOp final : GridOp {
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();
     if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "fused sweep on a slab cannot take an injected tape");
-    PMG_TRY(fused_halo(const_cast<double *>(xin)));
+    PMG_TRY(start_halo(xin));
     a.pitch  = (int)pitch();
     a.pplane = (long long)pitch() * g.n1;
     a.flip   = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
@@ -1326,8 +1393,16 @@ struct LapOp final : GridOp {
     }
     out = slow;
     out.insert(out.end(), fast.begin(), fast.end());
+    // tiles that read no ghost row first (they overlap the halo exchange), tiles along the slab boundaries last
+    const int lo = restrict_mode ? 5 : 3, hi = restrict_mode ? 3 : 1;
+    auto      nohalo = [&](const Item &it) { return !parallel || (it.ja - lo >= g.slo && it.jb + hi < g.shi); };
+    std::stable_partition(out.begin(), out.end(), nohalo);
+    int &cnt = restrict_mode ? nohalo2r : nohalo2;
+    cnt      = 0;
+    for (const auto &it : out) cnt += nohalo(it) ? 1 : 0;
     return (int)out.size();
   }
+  mutable int nohalo2 = 0, nohalo2r = 0;
   template <int NOISE, int WARPS, int STAGES, int MINB, bool RESTRICT = false> int launch2(const sweep2d::Args &a, int &slots)
   {
     using namespace sweep2d;
@@ -1342,7 +1417,22 @@ struct LapOp final : GridOp {
       occ_dev[dv] = std::max(1, occ);
     }
     slots = occ_dev[dv] * WARPS * ctx->sm_count;
-    if (a.nitems > 0) PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a));
+    if (a.nitems <= 0) return 0;
+    const int nh = RESTRICT ? nohalo2r : nohalo2;
+    if (split_launch && nh > 0 && nh < a.nitems) { // interior tiles | wait for the halo | boundary tiles
+      sweep2d::Args a1 = a, a2 = a;
+      a1.nitems = nh;
+      a2.items  = a.items + nh;
+      a2.nitems = a.nitems - nh;
+      PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a1.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a1));
+      PMG_TRY(halo_wait());
+      kern<<<(unsigned)((a2.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a2);
+      ctx->launches++;
+    } else {
+      if (split_launch) PMG_TRY(halo_wait());
+      PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a));
+    }
+    split_launch = false;
     return 0;
   }
   // the pre-smoother with the fused residual + restriction (sweep2d.cuh RESTRICT)
@@ -1403,7 +1493,7 @@ struct LapOp final : GridOp {
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();
     if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "fused sweep on a slab cannot take an injected tape");
-    PMG_TRY(fused_halo(const_cast<double *>(xin)));
+    PMG_TRY(start_halo(xin));
     a.pitch = (int)pitch();
     a.flip  = dir == PMG_SOR_BACKWARD_SWEEP ? 1 : 0;
     a.has_b = b ? 1 : 0;
@@ -1811,12 +1901,13 @@ struct BoxOp final : GridOp {
   bool    fused_mg_ok() const override { return level_pitch != 0; }
   bool    fused_tape_ok() const override { return !parallel; }
   int64_t fused_size() const override { return level_pitch ? level_pitch * (g.shi - g.slo + 2 * GHB()) : n(); }
-  int     pitched_halo(double *v) override
+  int     pitched_halo(double *v) override { return pitched_halo_on(v, ctx->stream); }
+  int     pitched_halo_on(double *v, cudaStream_t s) override
   {
     if (!parallel) return 0;
     const int64_t U = level_pitch, nu = g.shi - g.slo, G = GHB();
     double       *own = v + G * U;
-    return comm_halo_exchange(ctx, own, v, own + (nu - G) * U, own + nu * U, (size_t)(G * U), (size_t)(G * U), ctx->stream);
+    return comm_halo_exchange(ctx, own, v, own + (nu - G) * U, own + nu * U, (size_t)(G * U), (size_t)(G * U), s);
   }
   int to_pitched(const double *natural, double *pitched) override
   {
@@ -1893,7 +1984,11 @@ struct BoxOp final : GridOp {
     if (xc && bc) PMG_FAIL(PMG_ERR_SUP, "fused sweep: prolongation and restriction in one pass are not combined");
     if (xc && !xin) PMG_FAIL(PMG_ERR_ARG, "fused prolongation needs a fine iterate");
     if (parallel && na.mode == PMG_NOISE_INJECTED) PMG_FAIL(PMG_ERR_SUP, "one-pass sweep on a slab cannot take an injected tape");
-    if (xin) PMG_TRY(pitched_halo(const_cast<double *>(xin))); // replaces the per-colour VecScatter of src/mc_sor.c:318-319: one exchange per sweep
+    if (xin && parallel) { // replaces the per-colour VecScatter of src/mc_sor.c:318-319: one exchange per sweep, started by the
+                           // V-cycle right after the pre-smoother where it can be (it then overlaps the whole coarse-grid correction)
+      if (halo_inflight == xin) PMG_TRY(halo_wait());
+      else PMG_TRY(pitched_halo(const_cast<double *>(xin)));
+    }
     Args a;
     std::memset(&a, 0, sizeof a);
     const int64_t P = level_pitch, held = g.shi - g.slo + 2 * GHB();
