@@ -650,7 +650,7 @@ def main():
     ap.add_argument("--n", type=int, default=4097)
     ap.add_argument("--n3", type=int, default=512, help="edge of the 3D grid per GPU for the gibbs3d / mgmc3d measurements")
     ap.add_argument("--n-csr", type=int, default=256, help="edge of the assembled 3D operator of the K2 measurement")
-    ap.add_argument("--levels", type=int, default=0, help="0: 8 + log2(gpus): the coarsest grid is 33 nodes wide (SURVEY 8(d): cut at <= 33x33 + dense Cholesky) as the grid grows")
+    ap.add_argument("--levels", type=int, default=0, help="0: coarsen until the coarsest grid has at most 1200 nodes (8 levels, 33x33, at N = 1)")
     ap.add_argument("--kappa", type=float, default=1.0)
     ap.add_argument("--samples-per-step", type=int, default=120, help="MGMC samples per sampler call; 120 makes a step >= 50 ms")
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
@@ -665,8 +665,12 @@ def main():
     ap.add_argument("--bytes-per-update", type=float, default=24.0, help="algorithmic bytes per DOF update of the omega = 1 colour sweep (SURVEY 8(d) K1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.levels <= 0:
-        args.levels = 8 + max(0, (max(1, args.gpus) - 1).bit_length())
+    if args.levels <= 0:  # coarsen until the coarsest grid has at most ~1200 nodes (33x33 at N = 1; SURVEY 8(d): cut at <= 33x33 + dense Cholesky)
+        nx, ny = grid_of(args, max(1, args.gpus))
+        args.levels = 1
+        while nx * ny > 1200 and (nx - 1) % 2 == 0 and (ny - 1) % 2 == 0:
+            nx, ny = (nx + 1) // 2, (ny + 1) // 2
+            args.levels += 1
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

@@ -418,6 +418,9 @@ PetscErrorCode MatDestroy(Mat *A)
     free((*A)->j);
     free((*A)->a);
     free((*A)->colmap);
+    free((*A)->d);
+    free((*A)->fac);
+    free((*A)->piv);
     free(*A);
   }
   *A = NULL;
@@ -465,6 +468,10 @@ PetscErrorCode MatSeqAIJGetCSRAndMemType(Mat A, const PetscInt **i, const PetscI
 }
 PetscErrorCode MatGetDiagonal(Mat A, Vec d)
 {
+  if (A->d) {
+    for (PetscInt r = 0; r < A->m; ++r) d->a[r] = A->d[(size_t)r + (size_t)r * A->m];
+    return 0;
+  }
   Mat S = strcmp(A->type, MATMPIAIJ) == 0 ? A->Ad : A;
   for (PetscInt r = 0; r < S->m; ++r) {
     d->a[r] = 0.0;
@@ -479,24 +486,7 @@ PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left)
   if (left) PetscCall(VecStubCreate(A->hdr.comm, A->m, A->M, A->rstart, NULL, left));
   return 0;
 }
-#define STUB_UNSUPPORTED(name) return PetscStubError(PETSC_ERR_SUP, __FILE__, __LINE__, "petsc_stub: " name " belongs to the low-rank (MATLRC) path, which the stub does not emulate")
-PetscErrorCode MatMult(Mat A, Vec x, Vec y) { (void)A; (void)x; (void)y; STUB_UNSUPPORTED("MatMult"); }
-PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y) { (void)A; (void)x; (void)y; STUB_UNSUPPORTED("MatMultTranspose"); }
-PetscErrorCode MatMultAdd(Mat A, Vec x, Vec y, Vec z) { (void)A; (void)x; (void)y; (void)z; STUB_UNSUPPORTED("MatMultAdd"); }
-PetscErrorCode MatLRCGetMats(Mat A, Mat *b, Mat *U, Vec *c, Mat *V) { (void)A; (void)b; (void)U; (void)c; (void)V; STUB_UNSUPPORTED("MatLRCGetMats"); }
-PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption o, Mat *B) { (void)A; (void)o; (void)B; STUB_UNSUPPORTED("MatDuplicate"); }
-PetscErrorCode MatDenseGetColumnVecRead(Mat A, PetscInt c, Vec *v) { (void)A; (void)c; (void)v; STUB_UNSUPPORTED("MatDenseGetColumnVecRead"); }
-PetscErrorCode MatDenseRestoreColumnVecRead(Mat A, PetscInt c, Vec *v) { (void)A; (void)c; (void)v; STUB_UNSUPPORTED("MatDenseRestoreColumnVecRead"); }
-PetscErrorCode MatDenseGetColumnVecWrite(Mat A, PetscInt c, Vec *v) { (void)A; (void)c; (void)v; STUB_UNSUPPORTED("MatDenseGetColumnVecWrite"); }
-PetscErrorCode MatDenseRestoreColumnVecWrite(Mat A, PetscInt c, Vec *v) { (void)A; (void)c; (void)v; STUB_UNSUPPORTED("MatDenseRestoreColumnVecWrite"); }
-PetscErrorCode MatTransposeMatMult(Mat A, Mat B, MatReuse r, PetscReal f, Mat *C) { (void)A; (void)B; (void)r; (void)f; (void)C; STUB_UNSUPPORTED("MatTransposeMatMult"); }
-PetscErrorCode MatMatMult(Mat A, Mat B, MatReuse r, PetscReal f, Mat *C) { (void)A; (void)B; (void)r; (void)f; (void)C; STUB_UNSUPPORTED("MatMatMult"); }
-PetscErrorCode MatDiagonalSet(Mat A, Vec d, InsertMode m) { (void)A; (void)d; (void)m; STUB_UNSUPPORTED("MatDiagonalSet"); }
-PetscErrorCode MatShift(Mat A, PetscScalar s) { (void)A; (void)s; STUB_UNSUPPORTED("MatShift"); }
-PetscErrorCode KSPCreate(MPI_Comm comm, KSP *ksp) { (void)comm; (void)ksp; STUB_UNSUPPORTED("KSPCreate"); }
-PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P) { (void)ksp; (void)A; (void)P; STUB_UNSUPPORTED("KSPSetOperators"); }
-PetscErrorCode KSPMatSolve(KSP ksp, Mat B, Mat X) { (void)ksp; (void)B; (void)X; STUB_UNSUPPORTED("KSPMatSolve"); }
-PetscErrorCode KSPDestroy(KSP *ksp) { (void)ksp; STUB_UNSUPPORTED("KSPDestroy"); }
+/* MatMult*, MATLRC, dense matrices, factorisations, KSP, MatSOR: petsc_stub_dense.c */
 
 /* ---- MatColoring: hands back the colouring the driver injected (PETSc's JP is randomised and rank dependent) ---- */
 struct _p_MatColoring {

@@ -222,6 +222,15 @@ struct _p_Mat {
   /* mpiaij */
   Mat       Ad, Ao;
   PetscInt *colmap; /* compressed off-diagonal column -> global column (PETSc's garray) */
+  /* seqdense: column-major values, leading dimension m */
+  double *d;
+  /* lrc: A + U diag(c) U^T (MatCreateLRC); borrowed references */
+  Mat lrc_A, lrc_U;
+  Vec lrc_c;
+  /* factor objects (MatGetFactor): dense LU with partial pivoting / dense Cholesky of the matrix given to the numeric phase */
+  double *fac;
+  int    *piv;
+  int     fac_kind; /* 0 none, 1 LU, 2 Cholesky (lower) */
   /* colouring the driver wants MatColoringApply to return for this matrix (local rows), and its global colour count */
   const ISColoringValue *inject_colors;
   PetscInt               inject_ncolors;
@@ -241,8 +250,8 @@ PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left);
 PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y);
 PetscErrorCode MatMultAdd(Mat A, Vec x, Vec y, Vec z);
-/* MATLRC / dense / KSP pieces of the low-rank path (out of this tier's scope): present so that the
- * reference files link, they fail with PETSC_ERR_SUP when reached */
+/* MATLRC / dense / KSP pieces of the low-rank path and of the estimators (petsc_stub_dense.c): small dense column-major
+ * matrices, an exact dense solve behind KSP, PETSc's MatSOR_SeqAIJ semantics restated */
 PetscErrorCode MatLRCGetMats(Mat A, Mat *base, Mat *U, Vec *c, Mat *V);
 PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption o, Mat *B);
 PetscErrorCode MatDenseGetColumnVecRead(Mat A, PetscInt c, Vec *v);
@@ -257,6 +266,76 @@ PetscErrorCode KSPCreate(MPI_Comm comm, KSP *ksp);
 PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P);
 PetscErrorCode KSPMatSolve(KSP ksp, Mat B, Mat X);
 PetscErrorCode KSPDestroy(KSP *ksp);
+
+#define MATAIJ "aij"
+#define MATSBAIJ "sbaij"
+#define MATSEQDENSE "seqdense"
+#define MATDENSE "dense"
+#define PETSC_DECIDE (-1)
+#define PETSC_DEFAULT (-2)
+#define PETSC_ERR_SUP_SYS 57
+#define PETSC_ERR_ARG_OUTOFRANGE 63
+#define PETSC_ERR_MAT_CH_ZRPVT 81
+typedef enum { DIFFERENT_NONZERO_PATTERN, SUBSET_NONZERO_PATTERN, SAME_NONZERO_PATTERN, UNKNOWN_NONZERO_PATTERN } MatStructure;
+typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
+typedef enum { MAT_FACTOR_NONE, MAT_FACTOR_LU, MAT_FACTOR_CHOLESKY } MatFactorType;
+typedef enum { MAT_SYMMETRIC = 1, MAT_SPD = 2 } MatOption;
+typedef const char *MatSolverType;
+typedef const char *MatOrderingType;
+#define MATSOLVERPETSC "petsc"
+#define MATORDERINGNATURAL "natural"
+#define MATORDERINGMETISND "metisnd"
+#define MATORDERINGEXTERNAL "external"
+typedef struct { PetscReal fill, dtcol; } MatFactorInfo;
+typedef struct { PetscReal nz_used, nz_allocated, memory; } MatInfo;
+typedef enum { MAT_LOCAL = 1, MAT_GLOBAL_MAX = 2, MAT_GLOBAL_SUM = 3 } MatInfoType;
+PetscErrorCode MatCreateDense(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt M, PetscInt N, PetscScalar *data, Mat *A);
+PetscErrorCode MatCreateSeqDense(MPI_Comm comm, PetscInt m, PetscInt n, PetscScalar *data, Mat *A);
+PetscErrorCode MatCreateLRC(Mat A, Mat U, Vec c, Mat V, Mat *N);
+PetscErrorCode MatDenseGetArray(Mat A, PetscScalar **a);
+PetscErrorCode MatDenseRestoreArray(Mat A, PetscScalar **a);
+PetscErrorCode MatDenseGetArrayRead(Mat A, const PetscScalar **a);
+PetscErrorCode MatDenseRestoreArrayRead(Mat A, const PetscScalar **a);
+PetscErrorCode MatZeroEntries(Mat A);
+PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure s);
+PetscErrorCode MatNorm(Mat A, NormType t, PetscReal *nrm);
+PetscErrorCode MatConvert(Mat A, MatType t, MatReuse r, Mat *B);
+PetscErrorCode MatDiagonalScale(Mat A, Vec l, Vec r);
+PetscErrorCode MatMatTransposeMult(Mat A, Mat B, MatReuse r, PetscReal fill, Mat *C);
+PetscErrorCode MatSetOption(Mat A, MatOption o, PetscBool v);
+PetscErrorCode MatFactorInfoInitialize(MatFactorInfo *info);
+PetscErrorCode MatGetFactor(Mat A, MatSolverType st, MatFactorType ft, Mat *F);
+PetscErrorCode MatGetOrdering(Mat A, MatOrderingType t, IS *r, IS *c);
+PetscErrorCode MatLUFactorSymbolic(Mat F, Mat A, IS r, IS c, const MatFactorInfo *info);
+PetscErrorCode MatLUFactorNumeric(Mat F, Mat A, const MatFactorInfo *info);
+PetscErrorCode MatCholeskyFactorSymbolic(Mat F, Mat A, IS perm, const MatFactorInfo *info);
+PetscErrorCode MatCholeskyFactorNumeric(Mat F, Mat A, const MatFactorInfo *info);
+PetscErrorCode MatMatSolve(Mat F, Mat B, Mat X);
+PetscErrorCode MatForwardSolve(Mat F, Vec b, Vec x);
+PetscErrorCode MatBackwardSolve(Mat F, Vec b, Vec x);
+PetscErrorCode MatGetInfo(Mat A, MatInfoType t, MatInfo *info);
+/* PETSc's MatSOR on a SeqAIJ matrix: its x (lits) directional sweeps, no SOR_ZERO_INITIAL_GUESS */
+PetscErrorCode MatSOR(Mat A, Vec b, PetscReal omega, MatSORType flag, PetscReal shift, PetscInt its, PetscInt lits, Vec x);
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x);
+PetscErrorCode VecGetOwnershipRange(Vec v, PetscInt *lo, PetscInt *hi);
+PetscErrorCode VecGetLocalVector(Vec v, Vec w);
+PetscErrorCode VecRestoreLocalVector(Vec v, Vec w);
+PetscErrorCode VecGetLocalVectorRead(Vec v, Vec w);
+PetscErrorCode VecRestoreLocalVectorRead(Vec v, Vec w);
+PetscErrorCode PetscStrcmp(const char *a, const char *b, PetscBool *flg);
+#define PetscArraycpy(dst, src, n) (memcpy((dst), (src), sizeof(*(dst)) * (size_t)(n)), PETSC_SUCCESS)
+#define PetscRealPart(a) creal(a)
+/* BLAS / LAPACK (reference implementations, column-major, petsc_stub_dense.c) */
+typedef int PetscBLASInt;
+#define PetscBLASInt_FMT "d"
+#define PetscBLASIntCast(a, b) (*(b) = (PetscBLASInt)(a), PETSC_SUCCESS)
+#define PetscCallBLAS(name, call) do { call; } while (0)
+typedef enum { PETSC_FP_TRAP_OFF = 0, PETSC_FP_TRAP_ON = 1 } PetscFPTrap;
+#define PetscFPTrapPush(t) PETSC_SUCCESS
+#define PetscFPTrapPop() PETSC_SUCCESS
+void LAPACKpotrf_(const char *uplo, const PetscBLASInt *n, PetscScalar *a, const PetscBLASInt *lda, PetscBLASInt *info);
+void BLAStrsv_(const char *uplo, const char *trans, const char *diag, const PetscBLASInt *n, const PetscScalar *a, const PetscBLASInt *lda, PetscScalar *x, const PetscBLASInt *incx);
+PetscErrorCode PetscOptionsInt(const char *opt, const char *text, const char *man, PetscInt cur, PetscInt *v, PetscBool *set);
 
 /* ---- MatColoring ---- */
 PetscErrorCode MatColoringCreate(Mat A, MatColoring *mc);
@@ -290,6 +369,8 @@ struct _PCOps {
   PetscErrorCode (*reset)(PC);
   PetscErrorCode (*destroy)(PC);
   PetscErrorCode (*view)(PC, PetscViewer);
+  PetscErrorCode (*presolve)(PC, KSP, Vec, Vec);
+  PetscErrorCode (*postsolve)(PC, KSP, Vec, Vec);
 };
 struct _p_PC {
   struct _p_PetscObject hdr;
@@ -300,6 +381,12 @@ struct _p_PC {
 };
 PetscErrorCode PCRegister(const char *name, PetscErrorCode (*create)(PC));
 PetscErrorCode PCStubCreate(const char *type, Mat pmat, PC *pc); /* PCCreate + PCSetType + PCSetOperators */
+typedef const char *PCType;
+PetscErrorCode PCCreate(MPI_Comm comm, PC *pc);
+PetscErrorCode PCSetType(PC pc, PCType type);
+PetscErrorCode PCSetOperators(PC pc, Mat A, Mat P);
+PetscErrorCode PCSetUp(PC pc);
+PetscErrorCode PCDestroy(PC *pc);
 PetscErrorCode PCStubDestroy(PC *pc);
 PetscErrorCode PetscViewerASCIIPrintf(PetscViewer v, const char *fmt, ...);
 

@@ -12,6 +12,8 @@
 #include "parmgmc/mc_sor.h"
 #include "parmgmc/parmgmc.h"
 #include "parmgmc/pc/pc_mcgibbs.h"
+#include "parmgmc/iact.h"
+#include "parmgmc/stats.h"
 #include "petsc_stub.h"
 
 const char *PetscStubLastError(void);
@@ -23,11 +25,14 @@ const char *PetscStubLastError(void);
     (void)pc;                                                                                           \
     return PetscStubError(PETSC_ERR_SUP, __FILE__, __LINE__, #fn " is not part of oracle/_ref");        \
   }
-ABSENT_PC(PCCreate_SORGibbs)
-ABSENT_PC(PCCreate_GAMGMC)
-ABSENT_PC(PCCreate_CholSampler)
-ABSENT_PC(PCCreate_PARSOR)
+ABSENT_PC(PCCreate_GAMGMC)  /* wraps PETSc's PCMG / PCGAMG: nothing to run without PETSc */
+ABSENT_PC(PCCreate_PARSOR)  /* raw MPI point-to-point: out of scope */
 ABSENT_PC(PCCreate_Woodbury)
+PetscErrorCode PCPARSORApplySOR(PC pc, Vec b, PetscInt its, PetscBool zero, Vec y)
+{
+  (void)pc; (void)b; (void)its; (void)zero; (void)y;
+  return PetscStubError(PETSC_ERR_SUP, __FILE__, __LINE__, "PCPARSOR is not part of oracle/_ref");
+}
 
 const char *ref_last_error(void) { return PetscStubLastError(); }
 
@@ -244,5 +249,134 @@ int ref_normal_fill(long long seed, int n, int ncalls, double *out)
   }
   PetscCall(PetscRandomDestroy(&pr));
   PetscCall(ParMGMCFinalize());
+  return 0;
+}
+
+/* ---- a generic one-rank sampler run: PCSORGIBBS (src/pc_sorgibbs.c) / PCCHOLSAMPLER (src/pc_chols.c, dense LAPACK branch) /
+ *      PCMCGIBBS, optionally on a MATLRC operator A + B diag(S) B^T (k > 0): setfromoptions + setup + applyrichardson (its > 0)
+ *      or apply (its == 0), noise from the library's global rander48 stream ------------------------------------------------- */
+int ref_sampler_run(const char *pctype, int n, const int *rowptr, const int *col, const double *val, int k, const double *B, const double *S, int ncolors, const unsigned short *color,
+                    const char *opt1, const char *val1, const char *opt2, const char *val2, long long seed, int its, const double *b, double *y, ref_sample_cb cb, void *cbctx)
+{
+  Mat                         A, P, U = NULL;
+  PC                          pc;
+  Vec                         vb = NULL, vy, vw, vS = NULL;
+  PetscRandom                 pr;
+  PetscInt                    outits = 0;
+  PCRichardsonConvergedReason reason = PCRICHARDSON_CONVERGED_ITS;
+  PetscStubWorldBegin(color && ncolors > 1 ? 2 : 1);
+  PetscCall(ParMGMCInitialize());
+  PetscCall(ParMGMCGetPetscRandom(&pr));
+  PetscCall(PetscRandomSetSeed(pr, seed));
+  PetscCall(PetscRandomSeed(pr));
+  PetscCall(PetscRandomDestroy(&pr));
+  PetscCall(MatStubCreateSeqAIJ(MPI_COMM_WORLD, n, n, rowptr, col, val, &A));
+  if (color && ncolors > 1) PetscCall(MatStubInjectColoring(A, ncolors, color));
+  P = A;
+  if (k > 0) {
+    PetscCall(MatCreateSeqDense(MPI_COMM_WORLD, n, k, (double *)B, &U));
+    PetscCall(VecStubCreate(MPI_COMM_SELF, k, k, 0, (double *)S, &vS));
+    PetscCall(MatCreateLRC(A, U, vS, NULL, &P));
+  }
+  PetscCall(PetscStubOptionsClear());
+  if (opt1 && opt1[0]) PetscCall(PetscStubOptionsSet(opt1, val1 ? val1 : ""));
+  if (opt2 && opt2[0]) PetscCall(PetscStubOptionsSet(opt2, val2 ? val2 : ""));
+  PetscCall(PCStubCreate(pctype, P, &pc));
+  if (pc->ops->setfromoptions) PetscCall(pc->ops->setfromoptions(pc, NULL));
+  PetscCall(pc->ops->setup(pc));
+  pc->setupcalled = PETSC_TRUE;
+  g_cb            = cb;
+  g_cbctx         = cbctx;
+  if (cb) PetscCall(PCSetSampleCallback(pc, cb_tramp, NULL, NULL));
+  if (b) PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, (double *)b, &vb));
+  else PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, NULL, &vb));
+  PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, y, &vy));
+  PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, NULL, &vw));
+  if (its > 0) {
+    PetscCall(pc->ops->applyrichardson(pc, vb, vy, vw, 0, 0, 0, its, PETSC_FALSE, &outits, &reason));
+    if (outits != its || reason != PCRICHARDSON_CONVERGED_ITS) return PetscStubError(PETSC_ERR_PLIB, __FILE__, __LINE__, "unexpected outits/reason");
+  } else PetscCall(pc->ops->apply(pc, vb, vy));
+  PetscCall(VecDestroy(&vb));
+  PetscCall(VecDestroy(&vy));
+  PetscCall(VecDestroy(&vw));
+  PetscCall(PCStubDestroy(&pc));
+  if (k > 0) {
+    PetscCall(MatDestroy(&P));
+    PetscCall(MatDestroy(&U));
+    PetscCall(VecDestroy(&vS));
+  }
+  PetscCall(MatDestroy(&A));
+  PetscCall(PetscStubOptionsClear());
+  PetscCall(ParMGMCFinalize());
+  PetscStubWorldEnd();
+  return 0;
+}
+
+/* MCSORApply on a MATLRC operator (src/mc_sor.c:565-595 set-up, :480-544 MCSORBuildLRCCorrection, :101-112 post-correction) */
+int ref_mcsor_lrc(int n, const int *rowptr, const int *col, const double *val, int k, const double *B, const double *S, int ncolors, const unsigned short *color, double omega, int type, int nsweeps, const double *b, double *y)
+{
+  Mat   A, U, P;
+  MCSOR mc;
+  Vec   vb, vy, vS;
+  PetscStubWorldBegin(color && ncolors > 1 ? 2 : 1);
+  PetscCall(MatStubCreateSeqAIJ(MPI_COMM_WORLD, n, n, rowptr, col, val, &A));
+  if (color && ncolors > 1) PetscCall(MatStubInjectColoring(A, ncolors, color));
+  PetscCall(MatCreateSeqDense(MPI_COMM_WORLD, n, k, (double *)B, &U));
+  PetscCall(VecStubCreate(MPI_COMM_SELF, k, k, 0, (double *)S, &vS));
+  PetscCall(MatCreateLRC(A, U, vS, NULL, &P));
+  PetscCall(PetscStubOptionsClear());
+  PetscCall(MCSORCreate(P, &mc));
+  PetscCall(MCSORSetUp(mc));
+  PetscCall(MCSORSetOmega(mc, omega));
+  PetscCall(MCSORSetSweepType(mc, (MatSORType)type));
+  PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, (double *)b, &vb));
+  PetscCall(VecStubCreate(MPI_COMM_WORLD, n, n, 0, y, &vy));
+  for (int s = 0; s < nsweeps; ++s) PetscCall(MCSORApply(mc, vb, vy));
+  PetscCall(VecDestroy(&vb));
+  PetscCall(VecDestroy(&vy));
+  PetscCall(MCSORDestroy(&mc));
+  PetscCall(MatDestroy(&P));
+  PetscCall(MatDestroy(&U));
+  PetscCall(VecDestroy(&vS));
+  PetscCall(MatDestroy(&A));
+  PetscStubWorldEnd();
+  return 0;
+}
+
+/* src/iact.c: Autocorrelation (FFT, zero-padded) and IACT (Sokal windowing, c = 5) */
+int ref_iact(int n, const double *x, double *tau, double *acf_out, int *valid)
+{
+  PetscScalar *acf = NULL;
+  PetscBool    v   = PETSC_FALSE;
+  PetscCall(IACT(n, x, tau, acf_out ? &acf : NULL, &v));
+  if (acf_out) {
+    memcpy(acf_out, acf, sizeof(double) * (size_t)n);
+    free(acf);
+  }
+  *valid = v ? 1 : 0;
+  return 0;
+}
+int ref_autocorrelation(int n, const double *x, double *acf_out)
+{
+  PetscScalar *acf = NULL;
+  PetscCall(Autocorrelation(n, x, &acf));
+  memcpy(acf_out, acf, sizeof(double) * (size_t)n);
+  free(acf);
+  return 0;
+}
+
+/* src/stats.c: EstimateCovarianceMatErrors; samples[(i * chains + c) * n ...] = sample i of chain c */
+int ref_cov_errors(int n, const int *rowptr, const int *col, const double *val, int chains, int samples_per_chain, const double *samples, double *errs)
+{
+  Mat  A;
+  Vec *vs = malloc(sizeof(Vec) * (size_t)chains * (size_t)samples_per_chain);
+  PetscStubWorldBegin(1);
+  PetscCall(MatStubCreateSeqAIJ(MPI_COMM_SELF, n, n, rowptr, col, val, &A));
+  for (int q = 0; q < chains * samples_per_chain; ++q) PetscCall(VecStubCreate(MPI_COMM_SELF, n, n, 0, (double *)samples + (size_t)q * n, &vs[q]));
+  PetscCall(EstimateCovarianceMatErrors(A, chains, samples_per_chain, vs, errs));
+  for (int q = 0; q < chains * samples_per_chain; ++q) PetscCall(VecDestroy(&vs[q]));
+  free(vs);
+  PetscCall(MatDestroy(&A));
+  PetscStubWorldEnd();
   return 0;
 }

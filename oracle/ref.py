@@ -1,5 +1,5 @@
-"""ctypes front-end of oracle/_ref/libparmgmc_ref.so: the reference's OWN mc_sor.c / pc_mcgibbs.c / parmgmc.c,
-compiled unmodified from /root/reference against oracle/petsc_stub (see oracle/Makefile target `ref`).
+"""ctypes front-end of oracle/_ref/libparmgmc_ref.so: the reference's OWN mc_sor.c / pc_mcgibbs.c / parmgmc.c / pc_sorgibbs.c /
+pc_chols.c / iact.c / stats.c, compiled unmodified from /root/reference against oracle/petsc_stub (see oracle/Makefile target `ref`).
 
 TEST INFRASTRUCTURE ONLY: used by tests/test_oracle_ref.py to pin the oracle restatement, and by
 tests/golden/make_golden.py to write the committed golden vectors.  Never imported by parmgmc_b200.
@@ -43,6 +43,12 @@ def lib():
         L.ref_mcsor_mpi.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, i32p, C.c_int, u16p, C.c_double, C.c_int, C.c_int, f64p, f64p]
         L.ref_mcgibbs_richardson.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_longlong, C.c_int, C.c_void_p, f64p, CB, C.c_void_p]
         L.ref_normal_fill.argtypes = [C.c_longlong, C.c_int, C.c_int, f64p]
+        L.ref_sampler_run.argtypes = [C.c_char_p, C.c_int, i32p, i32p, f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                      C.c_longlong, C.c_int, C.c_void_p, f64p, CB, C.c_void_p]
+        L.ref_mcsor_lrc.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, f64p, f64p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int, f64p, f64p]
+        L.ref_iact.argtypes = [C.c_int, f64p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_autocorrelation.argtypes = [C.c_int, f64p, f64p]
+        L.ref_cov_errors.argtypes = [C.c_int, i32p, i32p, f64p, C.c_int, C.c_int, f64p, f64p]
         _lib = L
     return _lib
 
@@ -101,3 +107,59 @@ def normal_fill(seed, n, ncalls=1):
     out = np.empty(n * ncalls, np.float64)
     _check(lib().ref_normal_fill(seed, n, ncalls, out))
     return out
+
+
+def sampler_run(pctype, A, b, y, its, seed, coloring=None, opts=(), lrc=None, callback=None):
+    """PCSetFromOptions + PCSetUp + PCApplyRichardson (its > 0) or PCApply (its == 0) of `pctype` in {"mcgibbs", "sorgibbs",
+    "cholsampler"} on one rank (src/pc_sorgibbs.c:76-134, :181-262; src/pc_chols.c:100-342), optionally on the MATLRC operator
+    A + B diag(S) B^T (lrc = (B, S)); at most two (option, value) pairs; noise from the library's global rander48 stream."""
+    n, rp, cj, va = _csr32(A)
+    col16 = None if coloring is None else np.ascontiguousarray(coloring.color, np.uint16)
+    bb = None if b is None else np.ascontiguousarray(b, np.float64)
+    k, Bf, Sf = 0, None, None
+    if lrc is not None:
+        Bf = np.asfortranarray(np.asarray(lrc[0], np.float64))
+        Sf = np.ascontiguousarray(lrc[1], np.float64)
+        k = Bf.shape[1]
+    o = [(str(a).encode(), str(v).encode()) for a, v in opts] + [(b"", b""), (b"", b"")]
+    cbf = C.cast(None, CB) if callback is None else CB(lambda it, yp, m, _c: int(callback(int(it), np.ctypeslib.as_array(yp, shape=(m,))) or 0))
+    _check(lib().ref_sampler_run(pctype.encode(), n, rp, cj, va, k, None if Bf is None else Bf.ctypes.data, None if Sf is None else Sf.ctypes.data,
+                                 0 if coloring is None else coloring.ncolors, None if col16 is None else col16.ctypes.data, o[0][0], o[0][1], o[1][0], o[1][1],
+                                 seed, its, None if bb is None else bb.ctypes.data, y, cbf, None))
+    return y
+
+
+def mcsor_apply_lrc(A, B, S, b, y, coloring=None, omega=1.0, sweep=1, nsweeps=1):
+    """MCSORCreate / SetUp / Apply on the MATLRC operator A + B diag(S) B^T: the sweep on A followed by MCSORPostSOR_LRC with the
+    correction MCSORBuildLRCCorrection built at set-up (src/mc_sor.c:101-112, :480-544, :565-595)."""
+    n, rp, cj, va = _csr32(A)
+    Bf = np.asfortranarray(np.asarray(B, np.float64))
+    col16 = None if coloring is None else np.ascontiguousarray(coloring.color, np.uint16)
+    _check(lib().ref_mcsor_lrc(n, rp, cj, va, Bf.shape[1], Bf.ravel(order="K"), np.ascontiguousarray(S, np.float64), 0 if coloring is None else coloring.ncolors,
+                               None if col16 is None else col16.ctypes.data, omega, sweep, nsweeps, np.ascontiguousarray(b, np.float64), y))
+    return y
+
+
+def iact(x):
+    x = np.ascontiguousarray(x, np.float64)
+    tau, valid = C.c_double(), C.c_int()
+    acf = np.empty_like(x)
+    _check(lib().ref_iact(x.size, x, C.byref(tau), acf.ctypes.data, C.byref(valid)))
+    return tau.value, bool(valid.value), acf
+
+
+def autocorrelation(x):
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.empty_like(x)
+    _check(lib().ref_autocorrelation(x.size, x, out))
+    return out
+
+
+def cov_errors(A, samples):
+    """EstimateCovarianceMatErrors (src/stats.c:94-117); samples[s, chain, :]."""
+    samples = np.ascontiguousarray(samples, np.float64)
+    S, K, n = samples.shape
+    _, rp, cj, va = _csr32(A)
+    errs = np.empty(S, np.float64)
+    _check(lib().ref_cov_errors(n, rp, cj, va, K, S, samples.ravel(), errs))
+    return errs

@@ -180,8 +180,11 @@ struct HostCsr {
 // omega-dependent per-row coefficients of a sweep (src/mc_sor.c:114-124, src/pc_mcgibbs.c:142-153)
 struct SweepCoeffs {
   double         omega = -1;
-  DevBuf<double> idiag, sqrtdiag; // layout is private to the operator that made them
+  DevBuf<double> idiag, sqrtdiag; // layout is private to the operator that made them ...
+  const void    *made_for = nullptr; // ... and to its sweep layout: the operator and its layout version at make_coeffs time
+  uint64_t       made_version = 0;
 };
+uint64_t pmg_next_layout_version(); // process-wide counter: a new value whenever an operator is created or re-coloured
 
 // Low-rank part of an operator A + B diag(S) B^T (MATLRC) and its sweep corrections (lrc.cu).
 struct LevelOp;
@@ -193,6 +196,8 @@ struct LrcData {
   DevBuf<double>      B, S, sqrtS, Bb_f, Bb_b, partial, rhs; // n x k column-major; k; k; n x k (forward / backward); chunk sums; n
   bool                built       = false;
   double              omega_built = 0;
+  const void         *built_for = nullptr; // base operator and its layout version the corrections were built with
+  uint64_t            built_version = 0;
   int init(pmg_ctx ctx, int64_t n, int k, const double *B_host, const double *S_host);
   int build(LevelOp *base, double omega_build);                      // MCSORBuildLRCCorrection, both directions
   int prepare_rhs(const double *b, const NoiseArgs &na_eta, double *out); // out = b + B (sqrt|S| eta)
@@ -206,6 +211,9 @@ struct LrcData {
 // An operator on one level on one device.
 struct LevelOp {
   pmg_ctx ctx = nullptr;
+  // changes whenever the order / padding of the sweep rows changes (creation, set_coloring*): cached per-row coefficients
+  // (SweepCoeffs, the low-rank corrections) are rebuilt when it differs from the one they were made for
+  uint64_t layout_version = pmg_next_layout_version();
   // Row stride of this level's V-cycle vectors (b, x) when the cycle keeps them PITCHED (box2d.cuh: a Galerkin level between
   // two one-pass levels); 0: natural layout.  Set by the V-cycle set-up, read by the kernels that write / read the level's
   // vectors from the level above (fused restriction / prolongation).

@@ -302,7 +302,8 @@ struct CsrOp final : LevelOp {
     for (int c = 0; c < ncol; ++c) pos[c] = color_slice[c] * 32;
     for (int64_t r = 0; r < A.n; ++r) sweep_rows[(size_t)pos[color[r]]++] = (int32_t)r; // ascending rows per colour (ISColoringGetIS)
     PMG_TRY(build_sell(ctx, A, sweep_rows, true, sw_sell));
-    sweep_ready = true;
+    sweep_ready    = true;
+    layout_version = pmg_next_layout_version(); // cached per-row coefficients of the old layout are stale now
     return 0;
   }
 
@@ -313,10 +314,23 @@ struct CsrOp final : LevelOp {
   }
   int set_coloring(int nc, const int32_t *c) override
   {
-    if (nc < 1) PMG_FAIL(PMG_ERR_ARG, "need at least one colour");
+    // every rank must take the same decision before the first collective (a rank that fails alone would leave the others
+    // blocked in NCCL), and the sweep issues one collective halo per colour, so the colour count must be the same everywhere
+    int64_t local_ok = nc >= 1 ? 1 : 0, first_bad = -1;
     std::vector<int32_t> cand(c, c + A.n);
-    for (int64_t r = 0; r < A.n; ++r)
-      if (cand[r] < 0 || cand[r] >= nc) PMG_FAIL(PMG_ERR_ARG, "colour of row %lld out of range", (long long)r);
+    for (int64_t r = 0; r < A.n && local_ok; ++r)
+      if (cand[r] < 0 || cand[r] >= nc) { local_ok = 0; first_bad = r; }
+    if (dist) {
+      std::vector<int64_t> mine{local_ok, (int64_t)nc}, all((size_t)2 * ctx->nranks);
+      PMG_TRY(comm_allgather_i64(ctx, mine.data(), 2, all.data()));
+      for (int r = 0; r < ctx->nranks; ++r) {
+        if (!all[(size_t)2 * r]) PMG_FAIL(PMG_ERR_ARG, "rank %d passed an invalid colouring (colour count < 1 or a colour out of range)", r);
+        if (all[(size_t)2 * r + 1] != nc) PMG_FAIL(PMG_ERR_ARG, "the colour count must be the GLOBAL one on every rank: rank %d passed %lld, this rank %d", r, (long long)all[(size_t)2 * r + 1], nc);
+      }
+    } else if (!local_ok) {
+      if (nc < 1) PMG_FAIL(PMG_ERR_ARG, "need at least one colour");
+      PMG_FAIL(PMG_ERR_ARG, "colour of row %lld out of range", (long long)first_bad);
+    }
     int64_t bad = 0;
     if (dist) PMG_TRY(global_violations(cand, bad)); // collective: the colouring must be valid ACROSS ranks (src/mc_sor.c:383-395)
     else bad = host_coloring_violations(A, cand);
@@ -366,6 +380,9 @@ struct CsrOp final : LevelOp {
       ncol = star ? 2 : (gdim == 3 ? 8 : 4);
       if (host_coloring_violations(A, color)) PMG_FAIL(PMG_ERR_COLORING, "parity colouring is not valid for this operator");
     } else PMG_FAIL(PMG_ERR_ARG, "unknown colouring policy %d", policy);
+    // the greedy / level-set policies look at the entries of row r only: on a structurally non-symmetric pattern two coupled rows
+    // could share a colour and the sweep kernel would race
+    if (const int64_t bad = host_coloring_violations(A, color)) PMG_FAIL(PMG_ERR_COLORING, "automatic colouring is not a distance-1 colouring of this (structurally non-symmetric?) operator: %lld violations", (long long)bad);
     return rebuild_sweep();
   }
 

@@ -144,7 +144,9 @@ int LrcData::init(pmg_ctx c, int64_t n_, int k_, const double *B_host, const dou
 // MCSORBuildLRCCorrection (src/mc_sor.c:480-544) for both directions, with the deterministic sweep of `base` at omega_build
 int LrcData::build(LevelOp *base, double omega_build)
 {
-  if (built && omega_build == omega_built) return 0;
+  if (built && omega_build == omega_built && built_for == (const void *)base && built_version == base->layout_version) return 0;
+  built_for     = base;
+  built_version = base->layout_version;
   SweepCoeffs co;
   PMG_TRY(base->make_coeffs(omega_build, co));
   NoiseArgs      none{PMG_NOISE_NONE, nullptr, 0, 0, 0};

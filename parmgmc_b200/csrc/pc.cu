@@ -9,12 +9,19 @@
 //   src/pc_chols.c     PCCHOLSAMPLER                                          -> pmg_pc type "cholsampler"
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 
 #include "common.hpp"
 
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string g_error;
+
+uint64_t pmg_next_layout_version()
+{
+  static std::atomic<uint64_t> v{1};
+  return v.fetch_add(1);
+}
 
 void pmg_set_error(const char *fmt, ...)
 {
@@ -255,7 +262,13 @@ struct GibbsCore {
 
   int ensure()
   {
-    if (coeffs.omega != omega) PMG_TRY(op->make_coeffs(omega, coeffs)); // omega_changed, src/pc_mcgibbs.c:165
+    // omega_changed (src/pc_mcgibbs.c:165), or another operator / another colouring since the coefficients were made: they
+    // are stored per padded sweep position of ONE matrix and colouring
+    if (coeffs.omega != omega || coeffs.made_for != (const void *)op || coeffs.made_version != op->layout_version) {
+      PMG_TRY(op->make_coeffs(omega, coeffs));
+      coeffs.made_for     = op;
+      coeffs.made_version = op->layout_version;
+    }
     return 0;
   }
   // one directional sweep of an operator with a low-rank term: PrepareRHS_LRC (src/pc_mcgibbs.c:130-140: the k extra

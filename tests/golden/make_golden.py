@@ -1,5 +1,5 @@
 """Writes tests/golden/*.npz from the reference's OWN compiled code (oracle/_ref, i.e. /root/reference/src/mc_sor.c,
-pc_mcgibbs.c and parmgmc.c built unmodified against oracle/petsc_stub).  Run in the build container, where
+pc_mcgibbs.c, parmgmc.c, pc_sorgibbs.c, pc_chols.c, iact.c and stats.c built unmodified against oracle/petsc_stub).  Run in the build container, where
 /root/reference exists:   python tests/golden/make_golden.py
 The GPU box has no /root/reference; there the committed files are the reference's voice (tests/test_golden.py).
 Inputs are regenerated from the seeds below by the tests; only reference OUTPUTS (and the reference's own normal
@@ -79,5 +79,62 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def lrc_problem(seed=SEED):
+    """The MATLRC operator of the round-2 golden cases: 13x11 grid, k = 4 sparse observation columns."""
+    rng = np.random.default_rng([seed, 4242])
+    A = orc.laplace(2, 13, 11, kappa=2.0)
+    B = rng.standard_normal((A.n, 4)) * (rng.random((A.n, 4)) < 0.2)
+    S = 1.0 + 10.0 * rng.random(4)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    return A, B, S, b, y0
+
+
+def ar1(n, seed):
+    rng = np.random.default_rng([SEED, seed])
+    x = np.empty(n)
+    x[0] = rng.standard_normal()
+    for i in range(1, n):
+        x[i] = 0.8 * x[i - 1] + rng.standard_normal()
+    return x
+
+
+def main_round2():
+    """pc_sorgibbs.c, pc_chols.c (dense branch), iact.c, stats.c and the MATLRC branches, from the same library."""
+    out = {}
+    A = orc.laplace(2, 33, 21, kappa=3.0)
+    b, y0 = sweep_inputs("sorgibbs", A.n)
+    out["sorgibbs_33x21__z"] = ref.normal_fill(4711, A.n, 3)
+    out["sorgibbs_33x21__y"] = ref.sampler_run("sorgibbs", A, b, y0.copy(), 3, 4711)
+    out["sorgibbs_33x21__pcapply"] = ref.sampler_run("sorgibbs", A, b, y0.copy(), 0, 4711)
+    Ac = orc.laplace(2, 7, 9, kappa=2.0)
+    bc, _ = sweep_inputs("chol", Ac.n)
+    out["chol_7x9__z"] = ref.normal_fill(31337, Ac.n, 3)
+    out["chol_7x9__y1"] = ref.sampler_run("cholsampler", Ac, bc, np.zeros(Ac.n), 1, 31337)
+    out["chol_7x9__y3"] = ref.sampler_run("cholsampler", Ac, bc, np.zeros(Ac.n), 3, 31337)
+    for n in (500, 5000):
+        tau, valid, acf = ref.iact(ar1(n, n))
+        out[f"iact_{n}__tau_valid"] = np.array([tau, float(valid)])
+        out[f"iact_{n}__acf"] = acf
+    As = orc.laplace(2, 4, 5, kappa=1.5)
+    samples = np.random.default_rng([SEED, 12]).standard_normal((6, 9, As.n))
+    out["cov_4x5__errs"] = ref.cov_errors(As, samples)
+    A, B, S, b, y0 = lrc_problem()
+    for name, sweep in (("fwd", 1), ("bwd", 2), ("sym", 3)):
+        out[f"lrc_mcsor_{name}"] = ref.mcsor_apply_lrc(A, B, S, b, y0.copy(), None, 1.0, sweep, nsweeps=2)
+    # stream consumed per directional sweep: a fill of n normals, then one of k (PrepareRHS_LRC).  The reference library only
+    # exposes equal-sized fills from a fresh seed (ref.normal_fill), so this tape comes from the oracle's rander48 + Box-Muller,
+    # which tests/test_oracle_ref.py::test_box_muller_stream pins to the reference's stream
+    ns = orc.Noise.rander48(2024)
+    out["lrc_gibbs__z"] = np.concatenate([orc.noise_fill(ns, m) for _ in range(6) for m in (A.n, 4)])
+    out["lrc_mcgibbs_sym_w13__y"] = ref.sampler_run("mcgibbs", A, b, y0.copy(), 3, 2024, opts=(("-pc_mcgibbs_omega", 1.3), ("-pc_mcgibbs_symmetric", "")), lrc=(B, S))
+    out["lrc_sorgibbs__y"] = ref.sampler_run("sorgibbs", A, b, y0.copy(), 3, 2024, lrc=(B, S))
+    out["lrc_chol__y"] = ref.sampler_run("cholsampler", A, b, np.zeros(A.n), 1, 2024, lrc=(B, S))
+    np.savez(os.path.join(HERE, "round2_pins.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    main_round2()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -155,3 +155,147 @@ def test_cuda_sampler_matches_reference_output(pmg, ctx, orc, name):
         yy = y.copy()
         pc.apply_richardson(b, yy, its=its)
         assert rel(yy, GIBBS[name + "__y"]) < RTOL
+
+
+# ---- round 2: pc_sorgibbs.c, pc_chols.c (dense branch), iact.c, stats.c and the MATLRC branches (tests/golden/round2_pins.npz,
+#      written by make_golden.main_round2 from the same reference library) ---------------------------------------------------
+R2 = np.load(os.path.join(HERE, "golden", "round2_pins.npz"))
+
+
+def lrc_problem(orc):
+    rng = np.random.default_rng([C["SEED"], 4242])
+    A = orc.laplace(2, 13, 11, kappa=2.0)
+    B = rng.standard_normal((A.n, 4)) * (rng.random((A.n, 4)) < 0.2)
+    S = 1.0 + 10.0 * rng.random(4)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    return A, B, S, b, y0
+
+
+def ar1(n, seed):
+    rng = np.random.default_rng([C["SEED"], seed])
+    x = np.empty(n)
+    x[0] = rng.standard_normal()
+    for i in range(1, n):
+        x[i] = 0.8 * x[i - 1] + rng.standard_normal()
+    return x
+
+
+def test_oracle_sorgibbs_and_cholsampler_match_reference_output(orc):
+    A = orc.laplace(2, 33, 21, kappa=3.0)
+    b, y0 = inputs("sorgibbs", A.n)
+    y = orc.gibbs_richardson(A, b, y0.copy(), 3, orc.Noise.tape(R2["sorgibbs_33x21__z"]), None, 1.0, orc.SOR_FORWARD)
+    assert rel(y, R2["sorgibbs_33x21__y"]) < RTOL_ORACLE
+    y = orc.gibbs_richardson(A, b, np.zeros(A.n), 1, orc.Noise.rander48(4711), None, 1.0, orc.SOR_FORWARD)  # PCApply zeroes y
+    assert rel(y, R2["sorgibbs_33x21__pcapply"]) < RTOL_ORACLE
+    Ac = orc.laplace(2, 7, 9, kappa=2.0)
+    bc, _ = inputs("chol", Ac.n)
+    lflat = orc.potrf_lower(Ac.to_scipy().toarray())
+    ns = orc.Noise.tape(R2["chol_7x9__z"])
+    y1 = orc.chol_sample(lflat, Ac.n, ns, bc)
+    assert rel(y1, R2["chol_7x9__y1"]) < 1e-12
+    y3 = orc.chol_sample(lflat, Ac.n, ns, bc)
+    y3 = orc.chol_sample(lflat, Ac.n, ns, bc)
+    assert rel(y3, R2["chol_7x9__y3"]) < 1e-12
+
+
+@pytest.mark.parametrize("n", [500, 5000])
+def test_oracle_iact_matches_reference_output(orc, n):
+    x = ar1(n, n)
+    tau, valid = orc.iact(x)
+    assert abs(tau - R2[f"iact_{n}__tau_valid"][0]) < 1e-10 * abs(tau) and float(valid) == R2[f"iact_{n}__tau_valid"][1]
+    assert np.abs(orc.autocorrelation(x) - R2[f"iact_{n}__acf"]).max() < 1e-12
+
+
+def test_oracle_cov_errors_match_reference_output(orc):
+    As = orc.laplace(2, 4, 5, kappa=1.5)
+    samples = np.random.default_rng([C["SEED"], 12]).standard_normal((6, 9, As.n))
+    errs = orc.cov_errors(As.to_scipy().toarray(), samples)
+    assert np.abs(errs - R2["cov_4x5__errs"]).max() < 1e-12 * np.abs(errs).max()
+
+
+def test_oracle_matlrc_paths_match_reference_output(orc):
+    A, B, S, b, y0 = lrc_problem(orc)
+    Bb = {d: orc.lrc_build_correction(A, B, S, None, 1.0, d) for d in (orc.SOR_FORWARD, orc.SOR_BACKWARD)}
+    for name, sweep in (("fwd", orc.SOR_FORWARD), ("bwd", orc.SOR_BACKWARD), ("sym", orc.SOR_SYMMETRIC)):
+        y = y0.copy()
+        orc.lrc_mcsor_apply(A, B, Bb, b, y, None, 1.0, sweep)
+        orc.lrc_mcsor_apply(A, B, Bb, b, y, None, 1.0, sweep)
+        assert rel(y, R2[f"lrc_mcsor_{name}"]) < 1e-11
+    z = R2["lrc_gibbs__z"]
+    y = orc.lrc_gibbs_richardson(A, B, S, b, y0.copy(), 3, orc.Noise.tape(z), None, 1.3, orc.SOR_SYMMETRIC)
+    assert rel(y, R2["lrc_mcgibbs_sym_w13__y"]) < 1e-11
+    y = orc.lrc_gibbs_richardson(A, B, S, b, y0.copy(), 3, orc.Noise.tape(z), None, 1.0, orc.SOR_FORWARD)
+    assert rel(y, R2["lrc_sorgibbs__y"]) < 1e-11
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    y = orc.chol_sample(orc.potrf_lower(P), A.n, orc.Noise.tape(z), b)
+    assert rel(y, R2["lrc_chol__y"]) < 1e-11
+
+
+@pytest.mark.gpu
+def test_cuda_sorgibbs_and_cholsampler_match_reference_output(pmg, ctx, orc):
+    A = orc.laplace(2, 33, 21, kappa=3.0)
+    b, y0 = inputs("sorgibbs", A.n)
+    mat = device_mat(pmg, ctx, orc, A, "single", (33, 21))
+    pc = pmg.PC(ctx, "sorgibbs")
+    pc.set_operator(mat)
+    pc.setup()
+    pc.set_noise_tape(R2["sorgibbs_33x21__z"])
+    y = y0.copy()
+    pc.apply_richardson(b, y, its=3)
+    assert rel(y, R2["sorgibbs_33x21__y"]) < RTOL
+    pc.set_noise_tape(R2["sorgibbs_33x21__z"])
+    assert rel(pc.apply(b), R2["sorgibbs_33x21__pcapply"]) < RTOL  # PCApply_SORGibbs zeroes y (src/pc_sorgibbs.c:110)
+    Ac = orc.laplace(2, 7, 9, kappa=2.0)
+    bc, _ = inputs("chol", Ac.n)
+    for solve in ("trsv", "gemv"):
+        ch = pmg.PC(ctx, "cholsampler")
+        ch.set_operator(pmg.Mat.from_csr(ctx, Ac.rowptr, Ac.col, Ac.val))
+        ch.set_option("-pc_cholsampler_b200_solve", solve)
+        ch.setup()
+        ch.set_noise_tape(R2["chol_7x9__z"])
+        y1 = np.zeros(Ac.n)
+        ch.apply_richardson(bc, y1, its=1)
+        assert rel(y1, R2["chol_7x9__y1"]) < RTOL
+        ch.set_noise_tape(R2["chol_7x9__z"])
+        y3 = np.zeros(Ac.n)
+        ch.apply_richardson(bc, y3, its=3)
+        assert rel(y3, R2["chol_7x9__y3"]) < RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [500, 5000])
+def test_cuda_iact_matches_reference_output(pmg, ctx, n):
+    x = ar1(n, n)
+    tau, valid = pmg.iact(ctx, x)
+    assert abs(tau - R2[f"iact_{n}__tau_valid"][0]) < 1e-9 * abs(tau) and float(valid) == R2[f"iact_{n}__tau_valid"][1]
+    assert np.abs(pmg.autocorrelation(ctx, x) - R2[f"iact_{n}__acf"]).max() < 1e-11
+
+
+@pytest.mark.gpu
+def test_cuda_matlrc_paths_match_reference_output(pmg, ctx, orc):
+    A, B, S, b, y0 = lrc_problem(orc)
+    base = device_mat(pmg, ctx, orc, A, "single", (13, 11))
+    mat = pmg.Mat.lrc(base, B, S)
+    for name, sweep in (("fwd", 1), ("bwd", 2), ("sym", 3)):
+        mc = pmg.MCSOR(mat)
+        mc.set_sweep_type(sweep)
+        y = mc.apply(b, y0.copy())
+        y = mc.apply(b, y)
+        assert rel(y, R2[f"lrc_mcsor_{name}"]) < 1e-10
+    z = R2["lrc_gibbs__z"]
+    for pctype, opts, key in (("mcgibbs", {"-pc_mcgibbs_omega": 1.3, "-pc_mcgibbs_symmetric": ""}, "lrc_mcgibbs_sym_w13__y"), ("sorgibbs", {}, "lrc_sorgibbs__y")):
+        pc = pmg.PC(ctx, pctype)
+        pc.set_operator(mat)
+        pc.set_options(opts)
+        pc.setup()
+        pc.set_noise_tape(z)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=3)
+        assert rel(y, R2[key]) < 1e-10
+    ch = pmg.PC(ctx, "cholsampler")
+    ch.set_operator(mat)
+    ch.setup()
+    ch.set_noise_tape(z)
+    y = np.zeros(A.n)
+    ch.apply_richardson(b, y, its=1)
+    assert rel(y, R2["lrc_chol__y"]) < 1e-10

@@ -165,6 +165,52 @@ def test_error_codes(pmg, ctx, orc):
     assert e.value.code == 5  # PETSC_ERR_MAT_CH_ZRPVT, src/pc_chols.c:192
 
 
+def test_recolouring_and_operator_swap_after_setup_rebuild_the_coefficients(pmg, ctx, orc):
+    """The per-row sweep coefficients (omega / a_ii, sqrt a_ii) are stored per padded sweep position of ONE matrix and colouring
+    (src/mc_sor.c:114-124, src/pc_mcgibbs.c:142-153 keep them per row): re-colouring a matrix that already has a sampler, or
+    handing the sampler another operator, must rebuild them -- PCSetUp called again without PCReset does exactly this."""
+    rng = np.random.default_rng(SEED)
+    A = orc.laplace(2, 41, 29, kappa=2.0)
+    A.val[A.diag_ptrs()] *= 1.0 + rng.random(A.n)  # a non-constant diagonal: stale coefficients would show
+    col1 = orc.Coloring.parity((41, 29))
+    mat = make_mat(pmg, ctx, A, col1)
+    pc = pmg.PC(ctx, "mcgibbs")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_mcgibbs_omega": 1.3})
+    pc.setup()
+    mc = pmg.MCSOR(mat)
+    mc.set_omega(1.3)
+    b = rng.standard_normal(A.n)
+
+    def check(Aref, colref, pcx, mcx):
+        z = rng.standard_normal(2 * Aref.n)
+        pcx.set_noise_tape(z)
+        y = np.zeros(Aref.n)
+        bb = b[:Aref.n] if Aref.n <= b.size else np.resize(b, Aref.n)
+        pcx.apply_richardson(bb, y, its=2)
+        ref = orc.gibbs_richardson(Aref, bb, np.zeros(Aref.n), 2, orc.Noise.tape(z), colref, 1.3, orc.SOR_FORWARD)
+        assert np.array_equal(y, ref)
+        if mcx is not None:
+            ym = np.full(Aref.n, 0.25)
+            mcx.apply(bb, ym)
+            assert np.array_equal(ym, orc.MCSOR(Aref, colref, 1.3, orc.SOR_FORWARD).apply(bb, np.full(Aref.n, 0.25)))
+
+    check(A, col1, pc, mc)
+    # (1) re-colour the matrix under the live sampler and MCSOR (lexicographic level sets: a different, longer layout)
+    col2 = orc.Coloring.levelset(A)
+    mat.set_coloring(col2.color, col2.ncolors)
+    pc.setup()
+    check(A, col2, pc, mc)
+    # (2) hand the same PC a larger operator
+    A2 = orc.laplace(2, 57, 44, kappa=3.0)
+    A2.val[A2.diag_ptrs()] *= 1.0 + np.random.default_rng(3).random(A2.n)
+    colA2 = orc.Coloring.greedy(A2)
+    mat2 = make_mat(pmg, ctx, A2, colA2)
+    pc.set_operator(mat2)
+    pc.setup()
+    check(A2, colA2, pc, None)
+
+
 # ---- a10-a13: the Gibbs samplers -----------------------------------------------------------------
 @pytest.mark.parametrize("pctype,opts,osweep,omega", [
     ("mcgibbs", {}, 1, 1.0),
@@ -918,6 +964,7 @@ def test_fused_residual_restriction_is_bit_identical(pmg, ctx, dim, dims, levels
     n = dims[0] * dims[1] * dims[2]
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
     out = []
+    monkeypatch.setenv("PMG_NO_BOX2", "1")  # the stand-alone fused kernel, not the one-pass levels that superseded it (box2d.cuh)
     for fused in (True, False):
         if fused:
             monkeypatch.setenv("PMG_FUSED_RESIDUAL", "1")

@@ -133,3 +133,125 @@ def test_ex5_identity_on_reference():
     ref.mcsor_apply(A, b, y1, None, 1.0, orc.SOR_BACKWARD)
     y2 = ref.mcsor_apply(A, b, y0.copy(), None, 1.0, orc.SOR_SYMMETRIC)
     assert np.linalg.norm(y1 - y2) < 1e-15
+
+
+# ---- round 2: pc_sorgibbs.c, pc_chols.c (dense LAPACK branch), iact.c, stats.c and the MATLRC branches of mc_sor.c /
+#      pc_mcgibbs.c / pc_sorgibbs.c / pc_chols.c compiled into oracle/_ref as well ----------------------------------------
+def test_sorgibbs_richardson_and_apply():
+    """PCSORGIBBS on one rank = w = b + sqrt(a_ii) z, then PETSc's MatSOR forward sweep at omega = 1 (src/pc_sorgibbs.c:76-103);
+    the callback counts samples from 0 per call (:125-129); PCApply zeroes y first (:105-113)."""
+    rng = np.random.default_rng(SEED + 10)
+    A = orc.laplace(2, 33, 21, kappa=3.0)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    seen_ref, seen = [], []
+    y_ref = ref.sampler_run("sorgibbs", A, b, y0.copy(), 4, 4711, callback=lambda it, y: seen_ref.append((it, y.copy())))
+    y = orc.gibbs_richardson(A, b, y0.copy(), 4, orc.Noise.rander48(4711), None, 1.0, orc.SOR_FORWARD, callback=lambda it, y: seen.append((it, y.copy())))
+    assert rel(y, y_ref) < RTOL
+    assert [i for i, _ in seen_ref] == [0, 1, 2, 3]
+    for (_, a), (_, r) in zip(seen, seen_ref):
+        assert rel(a, r) < RTOL
+    y_ref = ref.sampler_run("sorgibbs", A, b, y0.copy(), 0, 99)  # PCApply
+    y = orc.gibbs_richardson(A, b, np.zeros(A.n), 1, orc.Noise.rander48(99), None, 1.0, orc.SOR_FORWARD)
+    assert rel(y, y_ref) < RTOL
+
+
+@pytest.mark.parametrize("shape,its", [((7, 9), 1), ((7, 9), 3), ((8, 8), 1)])
+def test_cholsampler_dense_branch(shape, its):
+    """PCCHOLSAMPLER, dense fast path (n <= 64: LAPACK potrf + two trsv, src/pc_chols.c:173-195, :220-291); its > 1 caches the
+    forward solve (:306-336)."""
+    rng = np.random.default_rng(SEED + 11)
+    A = orc.laplace(2, *shape, kappa=2.0)
+    b = rng.standard_normal(A.n)
+    y_ref = ref.sampler_run("cholsampler", A, b, np.zeros(A.n), its, 31337)
+    lflat = orc.potrf_lower(A.to_scipy().toarray())
+    ns = orc.Noise.rander48(31337)
+    y = None
+    for _ in range(its):  # the cached forward solve does not change the arithmetic
+        y = orc.chol_sample(lflat, A.n, ns, b)
+    assert rel(y, y_ref) < 1e-12
+    # the callback-less PCApply path is the same sample (:262-291)
+    y_ref0 = ref.sampler_run("cholsampler", A, b, np.zeros(A.n), 0, 31337)
+    assert rel(orc.chol_sample(lflat, A.n, orc.Noise.rander48(31337), b), y_ref0) < 1e-12
+
+
+def test_cholsampler_not_spd_error():
+    A = orc.laplace(2, 5, 5, kappa=1.0)
+    A.val[A.diag_ptrs()] = -1.0
+    with pytest.raises(RuntimeError, match="not positive definite"):
+        ref.sampler_run("cholsampler", A, np.ones(A.n), np.zeros(A.n), 1, 1)
+
+
+@pytest.mark.parametrize("n", [2, 17, 500, 4096, 5000])
+def test_iact_and_autocorrelation(n):
+    """src/iact.c:17-92: FFT autocorrelation (zero-padded to 2 nextpow2(n), normalised by lag 0) and Sokal's window (c = 5)."""
+    rng = np.random.default_rng(SEED + n)
+    x = np.empty(n)
+    x[0] = rng.standard_normal()
+    for i in range(1, n):  # AR(1), tau = (1 + rho) / (1 - rho)
+        x[i] = 0.8 * x[i - 1] + rng.standard_normal()
+    acf_ref = ref.autocorrelation(x)
+    assert np.abs(orc.autocorrelation(x) - acf_ref).max() < 1e-12
+    tau_ref, valid_ref, acf2 = ref.iact(x)
+    tau, valid = orc.iact(x)
+    assert abs(tau - tau_ref) < 1e-10 * max(1.0, abs(tau_ref)) and valid == valid_ref
+    assert np.abs(acf2 - acf_ref).max() == 0.0
+
+
+def test_cov_errors():
+    """src/stats.c:94-117: || C_i - A^-1 ||_F / || A^-1 ||_F across chains for every sample index."""
+    rng = np.random.default_rng(SEED + 12)
+    A = orc.laplace(2, 4, 5, kappa=1.5)
+    samples = rng.standard_normal((6, 9, A.n))
+    ref_errs = ref.cov_errors(A, samples)
+    errs = orc.cov_errors(A.to_scipy().toarray(), samples)
+    assert np.abs(errs - ref_errs).max() < 1e-12 * np.abs(ref_errs).max()
+
+
+def _lrc_problem(rng, shape=(13, 11), k=4):
+    A = orc.laplace(2, *shape, kappa=2.0)
+    B = rng.standard_normal((A.n, k)) * (rng.random((A.n, k)) < 0.2)
+    S = 1.0 + 10.0 * rng.random(k)
+    return A, B, S
+
+
+@pytest.mark.parametrize("omega,sweep", [(1.0, orc.SOR_FORWARD), (1.0, orc.SOR_SYMMETRIC), (1.0, orc.SOR_BACKWARD)])
+def test_mcsor_apply_on_matlrc(omega, sweep):
+    """MCSORApply on A + B S B^T: the sweep on A, then y -= Bb_dir (B^T y) with Bb from MCSORBuildLRCCorrection
+    (src/mc_sor.c:101-112, :480-544; built with the MCSOR's omega at set-up time, :583-593).  One rank, the reference's own
+    one-colour ordering (an injected colouring needs the two-rank branch, whose set-up scatter of S is collective)."""
+    rng = np.random.default_rng(SEED + 13)
+    A, B, S = _lrc_problem(rng)
+    col = None
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    y_ref = ref.mcsor_apply_lrc(A, B, S, b, y0.copy(), col, omega, sweep, nsweeps=2)
+    Bb = {d: orc.lrc_build_correction(A, B, S, col, 1.0, d) for d in (orc.SOR_FORWARD, orc.SOR_BACKWARD)}
+    y = y0.copy()
+    for _ in range(2):
+        orc.lrc_mcsor_apply(A, B, Bb, b, y, col, omega, sweep)
+    assert rel(y, y_ref) < 1e-11
+
+
+@pytest.mark.parametrize("pctype,opts,omega,sweep", [
+    ("mcgibbs", (), 1.0, orc.SOR_FORWARD),
+    ("mcgibbs", (("-pc_mcgibbs_omega", 1.3), ("-pc_mcgibbs_symmetric", "")), 1.3, orc.SOR_SYMMETRIC),
+    ("sorgibbs", (), 1.0, orc.SOR_FORWARD),
+])
+def test_gibbs_samplers_on_matlrc(pctype, opts, omega, sweep):
+    """PrepareRHS_LRC (n draws, then k; src/pc_mcgibbs.c:130-140, src/pc_sorgibbs.c:86-90) + sweep + post-correction, end to end."""
+    rng = np.random.default_rng(SEED + 14)
+    A, B, S = _lrc_problem(rng)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    y_ref = ref.sampler_run(pctype, A, b, y0.copy(), 3, 2024, opts=opts, lrc=(B, S))
+    y = orc.lrc_gibbs_richardson(A, B, S, b, y0.copy(), 3, orc.Noise.rander48(2024), None, omega, sweep, omega_build=1.0)
+    assert rel(y, y_ref) < 1e-11
+
+
+def test_cholsampler_on_matlrc():
+    """PCCHOLSAMPLER factors A + B S B^T (src/pc_chols.c:119-157)."""
+    rng = np.random.default_rng(SEED + 15)
+    A, B, S = _lrc_problem(rng, (6, 7), 3)
+    b = rng.standard_normal(A.n)
+    y_ref = ref.sampler_run("cholsampler", A, b, np.zeros(A.n), 1, 77, lrc=(B, S))
+    P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
+    y = orc.chol_sample(orc.potrf_lower(P), A.n, orc.Noise.rander48(77), b)
+    assert rel(y, y_ref) < 1e-11
