@@ -67,8 +67,23 @@ PetscErrorCode PetscObjectReference(PetscObject o)
 }
 PetscErrorCode PetscObjectComposeFunction_Stub(PetscObject o, const char *name, void (*f)(void))
 {
-  (void)name;
-  o->composed = f;
+  for (int k = 0; k < 4; ++k)
+    if (!o->composed[k].name || strcmp(o->composed[k].name, name) == 0) {
+      o->composed[k].name = name;
+      o->composed[k].f    = f;
+      return 0;
+    }
+  return PETSC_ERR_PLIB;
+}
+void (*PetscStubQueryFunction(PetscObject o, const char *name))(void)
+{
+  for (int k = 0; k < 4; ++k)
+    if (o->composed[k].name && strcmp(o->composed[k].name, name) == 0) return o->composed[k].f;
+  return NULL;
+}
+int MPI_Bcast(void *buf, int count, int datatype, int root, MPI_Comm comm)
+{
+  (void)buf; (void)count; (void)datatype; (void)root; (void)comm;
   return 0;
 }
 PetscErrorCode PetscClassIdRegister(const char *name, PetscClassId *id)

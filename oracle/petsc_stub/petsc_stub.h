@@ -67,6 +67,7 @@ typedef const char    *MatColoringType;
 #define PETSC_ERR_PLIB 77
 #define PETSC_ERR_LIB 76
 #define PETSC_ERR_ARG_WRONG 62
+#define PETSC_ERR_ORDER 58
 #define PetscInt_FMT "d"
 #define PETSC_PI 3.1415926535897932384626433832795029
 #define PetscSqrtReal(a) sqrt(a)
@@ -84,6 +85,8 @@ typedef int MPI_Comm;
 #define MPI_SUCCESS 0
 int MPI_Comm_size(MPI_Comm comm, int *size);
 int MPI_Comm_rank(MPI_Comm comm, int *rank);
+#define MPI_BYTE 1
+int MPI_Bcast(void *buf, int count, int datatype, int root, MPI_Comm comm); /* one rank per process in the stub: a no-op */
 
 /* ---- error handling / memory ---- */
 #define PetscFunctionBegin
@@ -126,8 +129,9 @@ struct _p_PetscObject {
   MPI_Comm comm;
   int      refct;
   const char *prefix;
-  void (*composed)(void); /* the one composed function a PC carries ("PCSetSampleCallback_C") */
+  struct { const char *name; void (*f)(void); } composed[4]; /* PetscObjectComposeFunction table ("PCSetSampleCallback_C", "PCMGGetLevels_C") */
 };
+void (*PetscStubQueryFunction(PetscObject o, const char *name))(void);
 MPI_Comm       PetscObjectComm(PetscObject o);
 PetscErrorCode PetscObjectGetComm(PetscObject o, MPI_Comm *comm);
 PetscErrorCode PetscObjectReference(PetscObject o);
@@ -135,7 +139,7 @@ PetscErrorCode PetscObjectComposeFunction_Stub(PetscObject o, const char *name, 
 #define PetscObjectComposeFunction(o, name, f) PetscObjectComposeFunction_Stub((o), (name), (void (*)(void))(f))
 #define PetscUseMethod(obj, name, proto, args)                                                 \
   do {                                                                                         \
-    PetscErrorCode(*f_) proto = (PetscErrorCode(*) proto)((obj)->composed);                    \
+    PetscErrorCode(*f_) proto = (PetscErrorCode(*) proto)PetscStubQueryFunction((obj), (name)); \
     PetscCheck(f_, PETSC_COMM_SELF, PETSC_ERR_SUP, "no method %s", name);                      \
     PetscCall((*f_)args);                                                                      \
   } while (0)

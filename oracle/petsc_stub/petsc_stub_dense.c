@@ -488,7 +488,7 @@ PetscErrorCode PCSetType(PC pc, PCType type)
   PetscCall(PCStubCreate(type, keep ? keep : dummy, &made));
   pc->data = made->data;
   memcpy(pc->ops, made->ops, sizeof(pc->ops));
-  pc->hdr.composed = made->hdr.composed;
+  memcpy(pc->hdr.composed, made->hdr.composed, sizeof(pc->hdr.composed));
   free(made);
   return MatDestroy(&dummy);
 }

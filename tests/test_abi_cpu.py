@@ -70,6 +70,30 @@ def test_petsc_shim_builds_and_fails_loudly_without_device():
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
+def test_petsc_shim_exports_the_reference_api_of_the_sampling_path():
+    """nm -D of the shim object must contain every function the reference's headers export for the sampling path
+    (include/parmgmc/parmgmc.h:33-44, mc_sor.h:21-30, iact.h:14-15, pc/pc_mcgibbs.h:16-18, pc/pc_sorgibbs.h:15,
+    pc/pc_gamgmc.h:15-18, pc/pc_chols.h:15-16, pc/woodbury.h:15-17).  Out of scope: ms.h, obs.h, problems.h,
+    stats.h (DM / FE set-up and host-side post-processing) and pc/pc_parsor.h."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(pmg.HEADER_PATH))
+    shim = os.path.join(root, "shim", "petsc")
+    subprocess.check_call(["make", "-s", "-C", shim])
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(shim, "build", "libparmgmc_b200_petsc.so")], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    wanted = """PARMGMC_CLASSID MULTICOL_SOR VEC_SET_RANDOM_NORMAL ParMGMCInitialize ParMGMCFinalize PCRegisterSetSampleCallback
+        PCSetSampleCallback ParMGMCGetPetscRandom VecSetRandomStandardNormal
+        MCSORCreate MCSORSetUp MCSORDestroy MCSORApply MCSORSetOmega MCSORSetSweepType MCSORGetSweepType MCSORGetISColoring
+        MCSORGetNumColors MCSORBuildLRCCorrection Autocorrelation IACT
+        PCCreate_MulticolorGibbs PCMulticolorGibbsSetOmega PCMulticolorGibbsSetSweepType PCCreate_SORGibbs
+        PCGAMGMCSetLevels PCCreate_GAMGMC PCGAMGMCGetInternalPC PCGAMGMCSetInternalPC
+        PCCreate_CholSampler PCCholSamplerSetIsCoarseGAMG PCCreate_Woodbury PCWoodburySetSolver PCWoodburySetSampler""".split()
+    missing = [w for w in wanted if w not in exported]
+    assert not missing, missing
+    for exe in ("host_ex1", "host_ex5", "host_api"):
+        assert os.path.exists(os.path.join(shim, "build", exe))
+
+
 # ---- host logic of the fused 3D sweep: the work list (pmg_plan_sweep3d; csrc/stencil_op.cu sweep3d_plan) -----------------------
 @pytest.mark.parametrize("dims,slab,bz,nw", [
     ((512, 512, 512), None, 64, 16),      # config 3: 4 full strips + a 32-column narrow strip, thin z-edge bands

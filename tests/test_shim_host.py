@@ -31,3 +31,21 @@ def test_ex1_shaped_c_host_program(exe, args):
     r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "relative mean error" in r.stdout
+
+
+@pytest.mark.parametrize("args", [[], ["17", "1.3"]])
+def test_ex5_shaped_c_host_program_typed_mcsor_api(exe, args):
+    """examples/ex5.c through the PETSc-typed MCSOR API of the shim (forward + backward == symmetric to 1e-15), the same
+    operator as a one-rank MATMPIAIJ, MCSOR on a MATLRC operator against MCSORBuildLRCCorrection (examples/ex3.c -with_lr),
+    MCSORGetISColoring / GetNumColors."""
+    r = subprocess.run([os.path.join(SHIM, "build", "host_ex5")] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host_ex5 ok" in r.stdout
+
+
+def test_c_host_program_rest_of_the_exported_api(exe):
+    """ParMGMCGetPetscRandom / VecSetRandomStandardNormal, PC woodbury (option keys and PCWoodburySet*), mcgibbs on MATLRC,
+    PCGAMGMCGet/SetInternalPC + "PCMGGetLevels_C", cholsampler presolve / postsolve callback rules, IACT / Autocorrelation."""
+    r = subprocess.run([os.path.join(SHIM, "build", "host_api"), "100000", "0.05"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host_api ok" in r.stdout
