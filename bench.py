@@ -650,7 +650,8 @@ def main():
     ap.add_argument("--n", type=int, default=4097)
     ap.add_argument("--n3", type=int, default=512, help="edge of the 3D grid per GPU for the gibbs3d / mgmc3d measurements")
     ap.add_argument("--n-csr", type=int, default=256, help="edge of the assembled 3D operator of the K2 measurement")
-    ap.add_argument("--levels", type=int, default=0, help="0: coarsen until the coarsest grid has at most 1200 nodes (8 levels, 33x33, at N = 1)")
+    ap.add_argument("--levels", type=int, default=0, help="0: coarsen until the coarsest grid has at most --coarsest-max nodes (10 levels, 9x9, at N = 1)")
+    ap.add_argument("--coarsest-max", type=int, default=100, help="largest coarsest grid of the automatic level count (dense Cholesky sampler there); 1200 gives round 1's 8 levels / 33x33")
     ap.add_argument("--kappa", type=float, default=1.0)
     ap.add_argument("--samples-per-step", type=int, default=120, help="MGMC samples per sampler call; 120 makes a step >= 50 ms")
     ap.add_argument("--ref-samples-per-step", type=int, default=1)
@@ -665,10 +666,10 @@ def main():
     ap.add_argument("--bytes-per-update", type=float, default=24.0, help="algorithmic bytes per DOF update of the omega = 1 colour sweep (SURVEY 8(d) K1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.levels <= 0:  # coarsen until the coarsest grid has at most ~1200 nodes (33x33 at N = 1; SURVEY 8(d): cut at <= 33x33 + dense Cholesky)
+    if args.levels <= 0:  # coarsen until the coarsest grid is small (cut at <= 33x33 + dense Cholesky; 9x9 at N = 1: the levels up to 65x65 run in one shared-memory launch)
         nx, ny = grid_of(args, max(1, args.gpus))
         args.levels = 1
-        while nx * ny > 1200 and (nx - 1) % 2 == 0 and (ny - 1) % 2 == 0:
+        while nx * ny > args.coarsest_max and (nx - 1) % 2 == 0 and (ny - 1) % 2 == 0 and min((nx + 1) // 2, (ny + 1) // 2) >= 3:
             nx, ny = (nx + 1) // 2, (ny + 1) // 2
             args.levels += 1
     if args.warmup < 3 and args.impl == "b200":

@@ -660,7 +660,7 @@ PetscErrorCode PCStubCreate(const char *type, Mat pmat, PC *pc)
 }
 PetscErrorCode PCStubDestroy(PC *pc)
 {
-  if (*pc) {
+  if (*pc && --(*pc)->hdr.refct <= 0) { /* reference counted like PetscObjectDereference */
     if ((*pc)->ops->destroy) PetscCall((*pc)->ops->destroy(*pc));
     free(*pc);
   }

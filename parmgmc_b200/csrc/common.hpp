@@ -393,6 +393,7 @@ struct TailLevelSpec {
   double            *b = nullptr, *x = nullptr, *r = nullptr;
 };
 bool grid_tail_level_ok(LevelOp *op);
+bool grid_tail_smem_fits(int nlev, LevelOp *const *ops, int64_t chol_n); // levels 0 .. nlev-1 fit the one-CTA shared-memory tail (tail2d.cuh)
 int  grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns);
 
 int launch_normal_fill(pmg_ctx ctx, const NoiseArgs &na, int64_t n, double *z_dev);

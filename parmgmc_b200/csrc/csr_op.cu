@@ -110,6 +110,13 @@ __global__ void gather_kernel(int64_t n, const int32_t *__restrict__ idx, const 
   if (q < n) out[q] = y[idx[q]];
 }
 
+// unpack a per-colour receive buffer into the ghost array
+__global__ void scatter_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ in, double *__restrict__ ghost)
+{
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) ghost[idx[q]] = in[q];
+}
+
 enum ApplyMode { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2 };
 
 // out_r = sum_k a_k x[c_k]          (SPMV: MatMult / MatMultTranspose with the transposed matrix)
@@ -187,6 +194,101 @@ struct CsrOp final : LevelOp {
       ctx->launches++;
     }
     return comm_exchange_v(ctx, send_buf.p, send_off.data(), ghost.p, recv_off.data(), ctx->stream);
+  }
+  // ---- per-colour ghost plans: the reference builds one VecScatter per colour holding only the ghost columns that rows of
+  //      that colour reference (src/mc_sor.c:152-214, gathered before the colour at :318-319).  Same here: colour c moves
+  //      only the values its rows read. ----
+  struct ColourPlan {
+    std::vector<int64_t> send_off, recv_off; // per-rank offsets into this colour's packed buffers
+    int64_t              send_base = 0, recv_base = 0; // offsets of this colour in csend_idx / crecv_idx
+  };
+  std::vector<ColourPlan> cplan;
+  DevBuf<int32_t>         csend_idx, crecv_idx; // all colours back to back
+  DevBuf<double>          crecv_buf;
+  bool                    cplan_ok = false;
+  int build_colour_plans()
+  {
+    cplan_ok = false;
+    cplan.clear();
+    if (!dist || ctx->nranks == 1) return 0;
+    const int P = ctx->nranks, me = ctx->rank;
+    // which colours of MY rows read ghost column q (bit c of mask[q]); more than 62 colours: keep the all-ghost plan
+    int64_t use = ncol <= 62 ? 1 : 0;
+    std::vector<int64_t> flags((size_t)P);
+    PMG_TRY(comm_allgather_i64(ctx, &use, 1, flags.data()));
+    for (int64_t f : flags)
+      if (!f) return 0;
+    std::vector<int64_t> mask((size_t)n_ghost, 0);
+    for (int64_t r = 0; r < n_local; ++r)
+      for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k)
+        if (A.col[k] >= n_local) mask[(size_t)(A.col[k] - n_local)] |= (int64_t)1 << color[(size_t)r];
+    std::vector<int64_t> cnts((size_t)P), mine1{n_ghost};
+    PMG_TRY(comm_allgather_i64(ctx, mine1.data(), 1, cnts.data()));
+    int64_t mx = 1;
+    for (int64_t v : cnts) mx = std::max(mx, v);
+    std::vector<int64_t> pad_gid((size_t)mx, -1), pad_mask((size_t)mx, 0), all_gid((size_t)mx * P), all_mask((size_t)mx * P);
+    std::copy(ghost_gid.begin(), ghost_gid.end(), pad_gid.begin());
+    std::copy(mask.begin(), mask.end(), pad_mask.begin());
+    PMG_TRY(comm_allgather_i64(ctx, pad_gid.data(), (int)mx, all_gid.data()));
+    PMG_TRY(comm_allgather_i64(ctx, pad_mask.data(), (int)mx, all_mask.data()));
+    // owner of each of my ghost columns (the ghost array is grouped by owner in rank order, recv_off)
+    std::vector<int32_t> sidx, ridx;
+    cplan.resize((size_t)ncol);
+    int64_t max_recv = 1;
+    for (int c = 0; c < ncol; ++c) {
+      ColourPlan &pl = cplan[(size_t)c];
+      pl.send_base = (int64_t)sidx.size();
+      pl.recv_base = (int64_t)ridx.size();
+      pl.send_off.assign((size_t)P + 1, 0);
+      pl.recv_off.assign((size_t)P + 1, 0);
+      for (int r = 0; r < P; ++r) {
+        if (r != me) {
+          for (int64_t q = 0; q < cnts[(size_t)r]; ++q) { // rank r's ghosts that I own and that its colour-c rows read, in r's ghost order
+            const int64_t g = all_gid[(size_t)r * mx + (size_t)q];
+            if (g >= row_start && g < row_start + n_local && ((all_mask[(size_t)r * mx + (size_t)q] >> c) & 1)) sidx.push_back((int32_t)(g - row_start));
+          }
+          for (int64_t q = recv_off[(size_t)r]; q < recv_off[(size_t)r + 1]; ++q) // my ghosts owned by r that my colour-c rows read, in my ghost order
+            if ((mask[(size_t)q] >> c) & 1) ridx.push_back((int32_t)q);
+        }
+        pl.send_off[(size_t)r + 1] = (int64_t)sidx.size() - pl.send_base;
+        pl.recv_off[(size_t)r + 1] = (int64_t)ridx.size() - pl.recv_base;
+      }
+      max_recv = std::max(max_recv, pl.recv_off[(size_t)P]);
+    }
+    if (sidx.empty()) sidx.push_back(0);
+    if (ridx.empty()) ridx.push_back(0);
+    PMG_TRY(csend_idx.upload(sidx, ctx->stream));
+    PMG_TRY(crecv_idx.upload(ridx, ctx->stream));
+    PMG_TRY(crecv_buf.alloc((size_t)max_recv));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cplan_ok = true;
+    return 0;
+  }
+  // bytes one sweep moves to this rank: per-colour plans against the all-ghost plan before every colour
+  void halo_volume(int64_t &per_colour, int64_t &all_ghosts) const
+  {
+    per_colour = 0;
+    for (const ColourPlan &pl : cplan) per_colour += pl.recv_off.back();
+    all_ghosts = (int64_t)ncol * n_ghost;
+  }
+  int halo_colour(int c, const double *y)
+  {
+    if (!dist || ctx->nranks == 1) return 0;
+    if (!cplan_ok || std::getenv("PMG_CSR_HALO_ALL")) return halo(y);
+    const ColourPlan &pl = cplan[(size_t)c];
+    const int64_t     ns = pl.send_off.back(), nr = pl.recv_off.back();
+    if (ns) {
+      gather_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(ns, csend_idx.p + pl.send_base, y, send_buf.p);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    PMG_TRY(comm_exchange_v(ctx, send_buf.p, pl.send_off.data(), crecv_buf.p, pl.recv_off.data(), ctx->stream));
+    if (nr) {
+      scatter_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, ctx->stream>>>(nr, crecv_idx.p + pl.recv_base, crecv_buf.p, ghost.p);
+      PMG_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return 0;
   }
   // colours of the ghost columns (for validating / building a GLOBAL distance-1 colouring)
   int ghost_colours(const std::vector<int32_t> &mine, std::vector<int32_t> &gc)
@@ -302,6 +404,7 @@ struct CsrOp final : LevelOp {
     for (int c = 0; c < ncol; ++c) pos[c] = color_slice[c] * 32;
     for (int64_t r = 0; r < A.n; ++r) sweep_rows[(size_t)pos[color[r]]++] = (int32_t)r; // ascending rows per colour (ISColoringGetIS)
     PMG_TRY(build_sell(ctx, A, sweep_rows, true, sw_sell));
+    PMG_TRY(build_colour_plans()); // collective on a row-partitioned operator (set_coloring* are collective there)
     sweep_ready    = true;
     layout_version = pmg_next_layout_version(); // cached per-row coefficients of the old layout are stale now
     return 0;
@@ -409,7 +512,7 @@ struct CsrOp final : LevelOp {
 
   int sweep_colour(int c, const SweepCoeffs &co, const double *b, double *y, const NoiseArgs &na)
   {
-    PMG_TRY(halo(y)); // collective: every rank takes part for every colour, also for colours it has no rows of
+    PMG_TRY(halo_colour(c, y)); // collective: every rank takes part for every colour, also for colours it has no rows of
     const int64_t s0 = color_slice[c], ns = color_slice[c + 1] - s0;
     if (ns == 0) return 0;
     const int  wpb = 8;
@@ -448,6 +551,12 @@ struct CsrOp final : LevelOp {
     if (dist) {
       snprintf(buf, sizeof buf, "; rows %lld..%lld of %lld, %lld ghost columns", (long long)row_start, (long long)(row_start + n_local), (long long)n_global, (long long)n_ghost);
       out += buf;
+      if (cplan_ok) {
+        int64_t pc = 0, ag = 0;
+        halo_volume(pc, ag);
+        snprintf(buf, sizeof buf, "; per-colour ghost plans: %lld values per sweep (all ghosts before every colour: %lld)", (long long)pc, (long long)ag);
+        out += buf;
+      }
     }
   }
 };

@@ -585,7 +585,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   pmg_ctx  ctx = pc->ctx;
   MgLevel &v   = pc->lv[l];
   if (l == pc->tail_top && zero_guess && b == v.b.p && x == v.x.p) { // levels 0..l in one launch
-    PMG_TRY(prof_begin(pc, "L0-L" + std::to_string(l) + " coarse tail (one cluster launch)", 0, 0));
+    PMG_TRY(prof_begin(pc, "L0-L" + std::to_string(l) + " coarse tail (one launch)", 0, 0));
     PMG_TRY(mg_tail(pc, l));
     return prof_end(pc);
   }
@@ -852,6 +852,18 @@ static int gamgmc_setup(pmg_pc pc)
   pc->direct_cycle = cyc == "direct";
   const char   *tm_env   = std::getenv("PMG_TAIL_MAX");
   const int64_t tail_max = (int64_t)std::atof(pc->get("pc_b200_tail_max_n", tm_env ? tm_env : "1500").c_str());
+  // Levels 0 .. tail_fit fit the one-CTA shared-memory tail (tail2d.cuh) whatever -pc_b200_tail_max_n says (which bounds the
+  // cluster tail through global memory); only asked for when the tail's other conditions can hold and the size is not user-set
+  int tail_fit = -1;
+  if (pc->direct_cycle && L >= 3 && tail_max > 0 && !pc->has("pc_b200_tail_max_n") && !tm_env && pc->get("gamgmc_mg_coarse_pc_type", "cholsampler") == "cholsampler" &&
+      std::atoi(pc->get("gamgmc_mg_coarse_ksp_max_it", "1").c_str()) == 1 && pc->get("gamgmc_mg_levels_pc_type", "sorgibbs") != "cholsampler") {
+    std::vector<LevelOp *> ops;
+    for (int l = 0; l < L - 1; ++l) {
+      ops.push_back(pc->lv[l].op);
+      if (l >= 1 && !ops[l]->distributed() && grid_tail_smem_fits(l + 1, ops.data(), ops[0]->n())) tail_fit = l;
+    }
+  }
+  auto tail_sized = [&](int l) { return pc->lv[l].op->n() <= tail_max || l <= tail_fit; };
   // Galerkin levels that run on the one-pass kernels (box2d.cuh) keep their vectors PITCHED: a chain of levels below a fused
   // finest level, down to the first level that is small enough for the one-launch tail (or cannot run the kernels)
   for (int l = 0; l < L - 1; ++l) pc->lv[l].op->level_pitch = 0;
@@ -859,7 +871,7 @@ static int gamgmc_setup(pmg_pc pc)
     bool chain = pc->lv[L - 1].op->fused_mg_ok();
     for (int l = L - 2; l >= 1 && chain; --l) {
       LevelOp *o = pc->lv[l].op;
-      chain      = o->box2_capable() && (o->distributed() || o->n() > tail_max);
+      chain      = o->box2_capable() && (o->distributed() || !tail_sized(l));
       if (chain) o->level_pitch = o->box2_pitch();
     }
     // a slab level's fused transfers write / read the level below in place: that level must be pitched too (or held in full)
@@ -919,7 +931,7 @@ static int gamgmc_setup(pmg_pc pc)
       int lt = 0;
       for (int l = 1; l < L - 1; ++l) {
         MgLevel &v = pc->lv[l];
-        if (v.smp.kind == KIND_CHOL || !grid_tail_level_ok(v.op) || !v.P || !v.P->tail_ok() || v.op->n() > tail_max || v.smp.its * (v.smp.gibbs.type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) > 8) break;
+        if (v.smp.kind == KIND_CHOL || !grid_tail_level_ok(v.op) || !v.P || !v.P->tail_ok() || !tail_sized(l) || v.smp.its * (v.smp.gibbs.type == PMG_SOR_SYMMETRIC_SWEEP ? 2 : 1) > 8) break;
         lt = l;
       }
       if (lt >= 1 && lt + 1 <= 10) pc->tail_top = lt;

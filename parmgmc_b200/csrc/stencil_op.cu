@@ -27,6 +27,8 @@
 #include "sweep3d.cuh"
 #include "box_stream.cuh"
 #include "box2d.cuh"
+#include "box3d.cuh"
+#include "tail2d.cuh"
 
 void laplace_assemble(int dim, int64_t nx, int64_t ny, int64_t nz, double kappa, HostCsr &a);
 int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, size_t count_lo, size_t count_hi, cudaStream_t stream);
@@ -674,6 +676,33 @@ __global__ void box_class_kernel(Geom g, const double *__restrict__ coef, int64_
   const int     cc = i == 0 ? 0 : (i == g.n0 - 1 ? 2 : 1), rc = j == 0 ? 0 : (j == g.n1 - 1 ? 2 : 1);
   bool          same = true;
   for (int s = 0; s < 9; ++s) same = same && (__double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(t.c[3 * rc + cc][s]));
+  if (!same) atomicAdd(mismatches, 1ull);
+}
+
+// the 3D analogue for the plane kernels (box3d.cuh): class = (x class, y class, z class); `raw` holds the 27 x 27 coefficients
+struct BoxClass3Raw {
+  double c[27][27]; // [cx + 3 cy + 9 cz][stencil entry]
+};
+__global__ void box_class3_gather_kernel(Geom g, const double *__restrict__ coef, int64_t stride, const int64_t *__restrict__ rep, double *__restrict__ out)
+{
+  const int q = blockIdx.x, s = threadIdx.x; // class q, entry s
+  if (s < 27 && rep[q] >= 0) out[27 * q + s] = coef[(int64_t)s * stride + rep[q]];
+}
+__global__ void box_class3_check_kernel(Geom g, const double *__restrict__ coef, int64_t stride, const double *__restrict__ tab, unsigned long long *__restrict__ mismatches)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nl) return;
+  int64_t i, j, k;
+  decode<3>(g, idx, i, j, k);
+  const int cx = i == 0 ? 0 : (i == g.n0 - 1 ? 2 : 1), cy = j == 0 ? 0 : (j == g.n1 - 1 ? 2 : 1), cz = k == 0 ? 0 : (k == g.n2 - 1 ? 2 : 1);
+  const double *t = tab + 27 * (cx + 3 * cy + 9 * cz);
+  bool          same = true;
+  for (int s = 0; s < 27; ++s) {
+    const int  di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+    const bool ex = i + di >= 0 && i + di < g.n0 && j + dj >= 0 && j + dj < g.n1 && k + dk >= 0 && k + dk < g.n2;
+    // structurally absent entries are never read by the per-node kernels: the class table holds zeros for them
+    same = same && (ex ? __double_as_longlong(coef[(int64_t)s * stride + idx]) == __double_as_longlong(t[s]) : true);
+  }
   if (!same) atomicAdd(mismatches, 1ull);
 }
 
@@ -1738,6 +1767,7 @@ struct BoxOp final : GridOp {
       k.sqrtdiag     = std::sqrt(std::fabs(d)) * std::sqrt((2 - co.omega) / co.omega);
     }
     const int  nc = ncolors();
+    if (box3_on()) return box3_sweep(dir, co, b, y, na); // four colours per launch, one CTA per plane (box3d.cuh)
     if (g.dim == 3 && !parallel && g.n0 <= 512 && (g.n2 + 1) / 2 <= 65535 && !std::getenv("PMG_NO_BOX_PAIR")) { // colour pairs (ci = 0, 1) in one launch
       const unsigned bx = (unsigned)((((g.n0 + 1) / 2) + 31) / 32 * 32);
       const dim3     grid((unsigned)((g.n1 + 1) / 2), (unsigned)((g.n2 + 1) / 2));
@@ -1839,6 +1869,10 @@ struct BoxOp final : GridOp {
   // ---- one-pass TMA kernels (box2d.cuh): 2D, one device, PITCHED level vectors (LevelOp::level_pitch) ----
   bool        classes_ok = false;
   BoxClassTab cls_tab;
+  // class tables of the shared-memory tail whose top level this is (tail2d.cuh): device copy + the (level, omega) list it was built for
+  DevBuf<box2d::Cls>                      tail_cls;
+  std::vector<box2d::Cls>                 tail_cls_host;
+  std::vector<std::pair<const void *, double>> tail_cls_key;
   // Every rank contributes the class representatives it owns (row class 0 lives on the first rank only, ...); the merged table is
   // verified against every owned node on every rank, and the verdict is the same everywhere (the kernels are collective on slabs).
   int         detect_classes()
@@ -1889,6 +1923,168 @@ struct BoxOp final : GridOp {
     for (int64_t v : allbad) classes_ok = classes_ok && v == 0;
     return 0;
   }
+  // ---- plane kernels of the 27-point levels (box3d.cuh) ----
+  bool                 classes3_ok = false;
+  BoxClass3Raw         cls3_raw;
+  DevBuf<box3d::Tab>   tab3_dev;
+  double               tab3_omega = -1;
+  // Every rank contributes the class representatives it owns; the merged table is verified against every owned node on every
+  // rank and the verdict is the same everywhere (the sweeps are collective on slabs).
+  int detect_classes3()
+  {
+    classes3_ok = false;
+    tab3_omega  = -1;
+    if (g.dim != 3 || g.n0 < 3 || g.n1 < 3 || g.n2 < 3 || g.n0 * g.n1 >= ((int64_t)1 << 30)) return 0;
+    if (!parallel && (g.slo != 0 || g.shi != g.n2)) return 0;
+    const int64_t ri[3] = {0, 1, g.n0 - 1}, rj[3] = {0, 1, g.n1 - 1}, rk[3] = {0, 1, g.n2 - 1};
+    std::vector<int64_t> rep(27, -1);
+    for (int cz = 0; cz < 3; ++cz) {
+      int64_t k = rk[cz];
+      if (cz == 1 && !(k >= g.slo && k < g.shi)) { // any owned interior plane serves as the interior representative
+        k = std::max<int64_t>(g.slo, 1);
+        if (k >= std::min<int64_t>(g.shi, g.n2 - 1)) k = -1;
+      }
+      if (k < g.slo || k >= g.shi) continue;
+      for (int cy = 0; cy < 3; ++cy)
+        for (int cx = 0; cx < 3; ++cx) rep[(size_t)(cx + 3 * cy + 9 * cz)] = ri[cx] + g.n0 * (rj[cy] + g.n1 * (k - g.slo));
+    }
+    DevBuf<int64_t> rep_dev;
+    DevBuf<double>  raw_dev;
+    PMG_TRY(rep_dev.upload(rep, ctx->stream));
+    PMG_TRY(raw_dev.alloc(729));
+    PMG_TRY(raw_dev.zero(ctx->stream));
+    box_class3_gather_kernel<<<27, 32, 0, ctx->stream>>>(g, coef.p, g.nl, rep_dev.p, raw_dev.p);
+    PMG_CUDA(cudaGetLastError());
+    std::vector<int64_t> mine(729 + 27, 0); // coefficients (bit patterns) + "have it" flags
+    PMG_CUDA(cudaMemcpyAsync(mine.data(), raw_dev.p, 729 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 27; ++q) mine[(size_t)(729 + q)] = rep[(size_t)q] >= 0 ? 1 : 0;
+    std::vector<int64_t> all((size_t)756 * ctx->nranks, 0);
+    PMG_TRY(comm_allgather_i64(ctx, mine.data(), 756, all.data()));
+    bool have_all = true;
+    for (int q = 0; q < 27; ++q) {
+      int src = -1;
+      for (int r = 0; r < ctx->nranks && src < 0; ++r)
+        if (all[(size_t)756 * r + 729 + q]) src = r;
+      if (src < 0) { have_all = false; continue; }
+      std::memcpy(cls3_raw.c[q], &all[(size_t)756 * src + 27 * q], 27 * sizeof(double));
+      const int cx = q % 3, cy = (q / 3) % 3, cz = q / 9; // entries towards a missing neighbour are never read: zero them
+      for (int s = 0; s < 27; ++s) {
+        const int di = s % 3 - 1, dj = (s / 3) % 3 - 1, dk = s / 9 - 1;
+        if ((cx == 0 && di < 0) || (cx == 2 && di > 0) || (cy == 0 && dj < 0) || (cy == 2 && dj > 0) || (cz == 0 && dk < 0) || (cz == 2 && dk > 0)) cls3_raw.c[q][s] = 0.0;
+      }
+    }
+    unsigned long long bad = have_all ? 0 : 1;
+    if (have_all && g.nl > 0) {
+      DevBuf<unsigned long long> cnt;
+      PMG_TRY(cnt.alloc(1));
+      PMG_TRY(cnt.zero(ctx->stream));
+      PMG_CUDA(cudaMemcpyAsync(raw_dev.p, &cls3_raw.c[0][0], 729 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      box_class3_check_kernel<<<nblocks(g.nl, 256), 256, 0, ctx->stream>>>(g, coef.p, g.nl, raw_dev.p, cnt.p);
+      PMG_CUDA(cudaGetLastError());
+      PMG_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const int64_t        mybad = (int64_t)bad;
+    std::vector<int64_t> allbad((size_t)ctx->nranks, 0);
+    PMG_TRY(comm_allgather_i64(ctx, &mybad, 1, allbad.data()));
+    classes3_ok = true;
+    for (int64_t v : allbad) classes3_ok = classes3_ok && v == 0;
+    return 0;
+  }
+  bool box3_on() const { return g.dim == 3 && classes3_ok && !std::getenv("PMG_NO_BOX3"); }
+  // class table for this omega on the device (box_coeffs_kernel's idiag / sqrtdiag per class)
+  int box3_args(double omega, box3d::Args &a)
+  {
+    if (tab3_omega != omega) {
+      static box3d::Tab t; // host staging (set-up path, one stream)
+      const double      f = std::sqrt((2 - omega) / omega);
+      for (int q = 0; q < 27; ++q) {
+        const double d = cls3_raw.c[q][13];
+        for (int s = 0; s < 27; ++s) t.c[q].nc[s] = -cls3_raw.c[q][s];
+        double inv   = 1.0 / d;
+        t.c[q].idiag = inv * omega;
+        t.c[q].sd    = std::sqrt(std::fabs(d)) * f;
+        t.c[q].pad   = 0.0;
+      }
+      PMG_TRY(tab3_dev.alloc(1));
+      PMG_CUDA(cudaMemcpyAsync(tab3_dev.p, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+      PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      tab3_host  = t;
+      tab3_omega = omega;
+    }
+    std::memset(&a, 0, sizeof a);
+    a.n0 = (int)g.n0; a.n1 = (int)g.n1; a.n2 = (int)g.n2;
+    a.slo = (int)g.slo; a.shi = (int)g.shi;
+    a.pitch4 = (int)((g.n0 + 3) & ~(int64_t)3);
+    a.omo    = 1.0 - omega;
+    a.in     = tab3_host.c[13];
+    a.tab    = tab3_dev.p;
+    a.glo    = ghost_lo.p;
+    a.ghi    = ghost_hi.p;
+    return 0;
+  }
+  box3d::Tab tab3_host;
+  static int box3_nt()
+  {
+    static const int nt = std::getenv("PMG_BOX3_NT") ? std::atoi(std::getenv("PMG_BOX3_NT")) : 512;
+    return nt == 1024 ? 1024 : (nt == 256 ? 256 : 512);
+  }
+  int box3_sweep(int dir, const SweepCoeffs &co, const double *b, double *y, const NoiseArgs &na)
+  {
+    box3d::Args a;
+    PMG_TRY(box3_args(co.omega, a));
+    a.b = b;
+    a.x = y;
+    const int nt = box3_nt();
+    const int np = (int)((g.n0 + 1) / 2);
+    static const int r_env = std::getenv("PMG_BOX3_R") ? std::atoi(std::getenv("PMG_BOX3_R")) : 0;
+    a.R = r_env > 0 ? r_env : std::max(1, std::min(16, nt / np));
+    const size_t sm = sizeof(box3d::Tab) + (size_t)(2 * a.R + 1) * a.pitch4 * sizeof(double);
+    if (sm > 200 * 1024) PMG_FAIL(PMG_ERR_SUP, "27-point plane sweep: grid rows of %lld nodes do not fit the shared-memory staging", (long long)g.n0);
+    auto kern = nt == 1024 ? box3d::box3_sweep_kernel<1024> : (nt == 256 ? box3d::box3_sweep_kernel<256> : box3d::box3_sweep_kernel<512>);
+    static size_t sm_set[16] = {0};
+    const int     dv = ctx->device & 15;
+    if (sm > sm_set[dv]) {
+      PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+      sm_set[dv] = std::max<size_t>(sm, 48 * 1024);
+    }
+    // ghost planes have the other k parity than the boundary planes that read them: refresh them before a parity whose
+    // neighbours have been swept since the last exchange -- twice per sweep (src/mc_sor.c:318-319 scatters before every colour)
+    bool dirty[2] = {true, true};
+    for (int s = 0; s < 2; ++s) {
+      const int kp = dir == PMG_SOR_FORWARD_SWEEP ? s : 1 - s;
+      if (dirty[1 - kp]) {
+        PMG_TRY(halo(y));
+        dirty[0] = dirty[1] = false;
+      }
+      dirty[kp] = true;
+      const int64_t first = g.slo + ((kp ^ g.slo) & 1);
+      const int64_t np_k  = first < g.shi ? (g.shi - first + 1) / 2 : 0;
+      if (np_k > 0) {
+        kern<<<(unsigned)np_k, nt, sm, ctx->stream>>>(a, kp, dir == PMG_SOR_FORWARD_SWEEP ? 0 : 1, na);
+        PMG_CUDA(cudaGetLastError());
+        ctx->launches++;
+      }
+    }
+    ctx->dof_updates += g.nl;
+    return 0;
+  }
+  template <bool RES> int box3_apply(const double *b, const double *x, double *out)
+  {
+    box3d::Args a;
+    PMG_TRY(box3_args(tab3_omega > 0 ? tab3_omega : 1.0, a));
+    a.x     = const_cast<double *>(x);
+    a.out_b = b;
+    a.out   = out;
+    const int nt = box3_nt();
+    auto      kern = nt == 1024 ? box3d::box3_apply_kernel<1024, RES> : (nt == 256 ? box3d::box3_apply_kernel<256, RES> : box3d::box3_apply_kernel<512, RES>);
+    kern<<<(unsigned)(g.shi - g.slo), nt, sizeof(box3d::Tab), ctx->stream>>>(a);
+    PMG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
+
   int64_t pitch() const { return (g.n0 + 3) / 4 * 4; }
   // a slab keeps four ghost rows per side in its pitched vectors: what one sweep with the fused residual + restriction (zero
   // iterate) or prolongation reads beyond its band (box2d.cuh band_range / band_steps)
@@ -2031,6 +2227,7 @@ struct BoxOp final : GridOp {
   template <bool RES> int apply(const double *b, const double *x, double *out)
   {
     PMG_TRY(halo(x));
+    if (box3_on() && g.n0 * g.n1 < ((int64_t)1 << 30)) return box3_apply<RES>(b, x, out);
     const Plan pl = g.dim == 2 ? plan_nodes<2>(g) : plan_nodes<3>(g);
     PMG_PLAN_CHECK(pl);
     if (g.dim == 2) box_apply_kernel<2, RES><<<pl.grid, pl.block, 0, ctx->stream>>>(g, coef.p, g.nl, bc, b, x, ghost_lo.p, ghost_hi.p, out);
@@ -2275,8 +2472,94 @@ bool grid_tail_level_ok(LevelOp *op)
   return bx && !bx->parallel && bx->g.slo == 0 && bx->g.shi == bx->g.nslow() && bx->g.nl < (1 << 30);
 }
 
+// The same tail in ONE CTA with every level vector in shared memory (tail2d.cuh), when the levels are 2D, have boundary
+// classes and fit; `done` tells whether it ran.
+static int grid_tail_smem_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns, bool &done)
+{
+  using namespace tail2d;
+  done = false;
+  if (std::getenv("PMG_NO_TAIL_SMEM") || nlev < 2 || nlev > MAX_LEVELS || nns > MAX_NOISE || chol.n > 512 || !chol.use_gemv) return 0;
+  static Args a;
+  a.nlev = nlev;
+  const int top = nlev - 1;
+  int64_t   off = 0, updates = 0;
+  std::vector<std::pair<const void *, double>> key;
+  for (int l = 0; l < nlev; ++l) {
+    auto *bx = dynamic_cast<BoxOp *>(lv[l].op);
+    if (!bx || bx->g.dim != 2 || bx->parallel || bx->g.slo != 0 || bx->g.shi != bx->g.n1 || (l > 0 && !bx->classes_ok)) return 0;
+    Level &L = a.lv[l];
+    L.n0 = (int)bx->g.n0; L.n1 = (int)bx->g.n1; L.n = (int)bx->g.nl;
+    L.xoff = (int)off; off += L.n;
+    if (l < top) { L.boff = (int)off; off += L.n; }
+    else L.boff = -1;
+    L.ndirs = 0;
+    L.omo   = 0;
+    if (l == 0) continue;
+    if (lv[l].ndirs > 8) return 0;
+    L.ndirs = lv[l].ndirs;
+    for (int q = 0; q < L.ndirs; ++q) L.dirs[q] = lv[l].dirs[q];
+    L.omo = 1.0 - lv[l].coeffs->omega;
+    key.emplace_back((const void *)bx, lv[l].coeffs->omega);
+    updates += 2 * (int64_t)L.ndirs * bx->g.nl;
+  }
+  if ((int64_t)a.lv[0].n != chol.n) return 0;
+  a.tmpoff = (int)off; off += chol.n;
+  a.zoff   = (int)off; off += a.lv[top].n;
+  const size_t sm = (size_t)off * sizeof(double);
+  if (sm > 224 * 1024) return 0;
+  auto *tb = dynamic_cast<BoxOp *>(lv[top].op);
+  if (tb->tail_cls_key != key) {
+    tb->tail_cls_host.assign((size_t)9 * nlev, box2d::Cls{});
+    for (int l = 1; l < nlev; ++l) {
+      auto *bx = dynamic_cast<BoxOp *>(lv[l].op);
+      for (int q = 0; q < 9; ++q) BoxOp::fill_class(tb->tail_cls_host[(size_t)9 * l + q], bx->cls_tab.c[q], lv[l].coeffs->omega);
+    }
+    PMG_TRY(tb->tail_cls.upload(tb->tail_cls_host, ctx->stream));
+    PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    tb->tail_cls_key = key;
+  }
+  a.cls  = tb->tail_cls.p;
+  a.btop = lv[top].b;
+  a.xtop = lv[top].x;
+  a.nc = (int)chol.n; a.W = chol.L.p; a.WT = chol.LT.p;
+  a.mode = noise_mode; a.seed = seed;
+  for (int q = 0; q < nns; ++q) a.ns[q] = ns[q];
+  static size_t sm_set[16] = {0};
+  const int     dv = ctx->device & 15;
+  if (sm > sm_set[dv]) {
+    PMG_CUDA(cudaFuncSetAttribute(tail2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+    sm_set[dv] = std::max<size_t>(sm, 48 * 1024);
+  }
+  PMG_CUDA(launch_pdl(ctx->stream, tail2d_kernel, dim3(1), dim3(NT), sm, a));
+  ctx->launches++;
+  ctx->dof_updates += updates;
+  done = true;
+  return 0;
+}
+
+// size / type test of the shared-memory tail for levels 0 .. nlev-1 (the V-cycle set-up asks before it lays the levels out)
+bool grid_tail_smem_fits(int nlev, LevelOp *const *ops, int64_t chol_n)
+{
+  if (std::getenv("PMG_NO_TAIL_SMEM") || nlev < 2 || nlev > tail2d::MAX_LEVELS || chol_n > 512) return false;
+  int64_t off = 0;
+  for (int l = 0; l < nlev; ++l) {
+    auto *bx = dynamic_cast<BoxOp *>(ops[l]);
+    if (!bx || bx->g.dim != 2 || bx->parallel || bx->g.slo != 0 || bx->g.shi != bx->g.n1 || (l > 0 && !bx->classes_ok)) return false;
+    off += (l < nlev - 1 ? 2 : 1) * bx->g.nl;
+    if (l == 0 && bx->g.nl != chol_n) return false;
+  }
+  auto *tb = dynamic_cast<BoxOp *>(ops[nlev - 1]);
+  off += chol_n + tb->g.nl;
+  return (size_t)off * sizeof(double) <= 224 * 1024;
+}
+
 int grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns)
 {
+  {
+    bool done = false;
+    PMG_TRY(grid_tail_smem_cycle(ctx, nlev, lv, chol, noise_mode, seed, ns, nns, done));
+    if (done) return 0;
+  }
   if (nlev < 2 || nlev > TAIL_MAX_LEVELS || nns > TAIL_MAX_NOISE) PMG_FAIL(PMG_ERR_SUP, "coarse tail: %d levels / %d noise blocks exceed the kernel's tables", nlev, nns);
   static TailArgs a; // ~4 KB: filled per launch, passed by value
   a.nlev = nlev;
@@ -2433,6 +2716,7 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64
       PMG_TRY(c->exchange_coef_ghosts());
       PMG_TRY(c->detect_interior());
       PMG_TRY(c->detect_classes());
+      PMG_TRY(c->detect_classes3());
       auto t    = std::make_unique<GridTransfer>();
       t->ctx    = ctx;
       t->fine   = cur;
@@ -2464,6 +2748,7 @@ int build_structured_hierarchy(pmg_ctx ctx, LevelOp *fine_op, int nlevels, int64
       PMG_CUDA(cudaStreamSynchronize(ctx->stream));
       PMG_TRY(full->detect_interior());
       PMG_TRY(full->detect_classes());
+      PMG_TRY(full->detect_classes3());
       transfers[(size_t)l] = std::move(t);
       cur                  = full.get();
       ops[(size_t)l - 1]   = std::move(full);

@@ -301,8 +301,21 @@ static PetscErrorCode run(int argc, char **argv)
 }
 
 const char *PetscStubLastError(void);
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void on_segv(int sig)
+{
+  void *bt[32];
+  const int n = backtrace(bt, 32);
+  (void)sig;
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(139);
+}
 int main(int argc, char **argv)
 {
+  setvbuf(stdout, NULL, _IONBF, 0);
+  signal(SIGSEGV, on_segv);
   PetscErrorCode e = run(argc, argv);
   if (e) fprintf(stderr, "host_api failed (%d): %s\n", e, PetscStubLastError());
   return e ? 1 : 0;

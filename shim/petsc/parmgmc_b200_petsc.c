@@ -49,6 +49,7 @@ typedef struct {
   PC  wb_solver, wb_sampler;        /* PCWoodburySetSolver / SetSampler (src/woodbury.c:188-214) */
   PetscBool is_gamg_coarse;         /* PCCholSamplerSetIsCoarseGAMG (src/pc_chols.c:398-406) */
   PetscBool in_solve, richardson;   /* PCPreSolve / PCPostSolve_CholSampler (src/pc_chols.c:344-370) */
+  PetscBool in_apply;               /* inside PCApply: the shim notifies the callback itself, with the in-solve sample index */
   PetscInt  sample_index;
   pmg_mat   base;                   /* base matrix of a MATLRC operator (kept alive next to d->mat) */
 } PC_B200;
@@ -188,7 +189,7 @@ static int B200SampleTrampoline(int64_t it, const double *y_host, int64_t n, voi
 {
   PC_B200     *d = ctx;
   PetscScalar *a;
-  if (!d->scb) return 0;
+  if (!d->scb || d->in_apply) return 0;
   if (VecGetArray(d->cbvec, &a)) return 1;
   memcpy(a, y_host, sizeof(double) * (size_t)n);
   if (VecRestoreArray(d->cbvec, &a)) return 1;
@@ -230,7 +231,9 @@ static PetscErrorCode PCApply_B200(PC pc, Vec x, Vec y)
   PetscCall(VecGetArray(y, &yarr));
   /* src/pc_chols.c:267: outside Richardson a callback is only legal between PCPreSolve and PCPostSolve */
   PetscCheck(strcmp(d->type, PCCHOLSAMPLER) != 0 || d->richardson || !d->scb || d->in_solve, PetscObjectComm((PetscObject)pc), PETSC_ERR_SUP, "Setting a sample callback is only supported for Cholesky sampler during KSPSolve");
+  d->in_apply = PETSC_TRUE;
   PMGCall(pmg_pc_apply(d->pc, xarr, yarr));
+  d->in_apply = PETSC_FALSE;
   PetscCall(VecRestoreArray(y, &yarr));
   PetscCall(VecRestoreArrayRead(x, &xarr));
   if (d->in_solve && d->scb) PetscCall(d->scb(d->sample_index++, y, d->cbctx)); /* PCCholSamplerNotifySample inside a KSPSolve */

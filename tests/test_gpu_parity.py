@@ -650,8 +650,14 @@ def test_matrix_free_hierarchy_equals_assembled_hierarchy(pmg, ctx, orc, dim, di
     (3, (41, 25, 17), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
 ])
 @pytest.mark.parametrize("noise", ["philox", "tape"])
-def test_coarse_tail_launch_is_bit_identical(pmg, ctx, dim, dims, levels, extra, noise):
-    """One cluster launch for levels 0..lt must give exactly the launch-per-colour result, with the same noise blocks."""
+@pytest.mark.parametrize("smem", [True, False])
+def test_coarse_tail_launch_is_bit_identical(pmg, ctx, dim, dims, levels, extra, noise, smem, monkeypatch):
+    """One launch for levels 0..lt -- one CTA with the level vectors in shared memory (tail2d.cuh; 2D) or one cluster through
+    global memory (grid_tail_kernel) -- must give exactly the launch-per-colour result, with the same noise blocks."""
+    if smem and dim == 3:
+        pytest.skip("the shared-memory tail is 2D")
+    if not smem:
+        monkeypatch.setenv("PMG_NO_TAIL_SMEM", "1")
     rng = np.random.default_rng(SEED)
     n = dims[0] * dims[1] * dims[2]
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
@@ -1272,6 +1278,7 @@ def test_box_colour_pair_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, n
     n = dims[0] * dims[1] * dims[2]
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
     out = []
+    monkeypatch.setenv("PMG_NO_BOX3", "1")  # the plane kernels (box3d.cuh) would take over both runs
     for pair in (True, False):
         if pair:
             monkeypatch.delenv("PMG_NO_BOX_PAIR", raising=False)
@@ -1289,6 +1296,101 @@ def test_box_colour_pair_sweep_is_bit_identical(pmg, ctx, dims, levels, extra, n
             ctx.set_seed(31)
         y = y0.copy()
         pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
+
+
+# ---- 27-point Galerkin levels: four colours per launch, one CTA per plane (box3d.cuh) against one launch per colour --------------
+@pytest.mark.parametrize("noise", ["philox", "tape"])
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((65, 65, 65), 4, {}),
+    ((33, 41, 25), 3, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.3}),
+    ((129, 17, 33), 3, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    ((21, 37, 19), 3, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_backward": ""}),  # odd and even row counts per block
+    ((257, 9, 9), 3, {}),
+])
+def test_box3_plane_sweep_and_residual_are_bit_identical(pmg, ctx, dims, levels, extra, noise, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for plane in (True, False):
+        if plane:
+            monkeypatch.delenv("PMG_NO_BOX3", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_BOX3", "1")
+            monkeypatch.setenv("PMG_NO_BOX_PAIR", "1")
+        lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.8)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_tail_max_n": 0}))
+        pc.setup()
+        if noise == "tape":
+            pc.set_noise_tape(np.random.default_rng(7).standard_normal(2 * pc.noise_per_sample()))
+        else:
+            pc.set_noise_mode(pmg.NOISE_PHILOX)
+            ctx.set_seed(31)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append((y, pc.last_stats()["launches"]))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][1] < out[1][1]
+
+
+@pytest.mark.parametrize("dims", [(1025, 14, 5), (257, 22, 7), (33, 70, 9)])
+def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims, monkeypatch):
+    """The number of grid rows per block follows from the row length (level 1 of these grids: 513 nodes -> 1 even row per
+    block, 129 -> 7, 17 -> 16): the result must equal the per-colour path for all of them, symmetric sweeps included."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for plane in (True, False):
+        if plane:
+            monkeypatch.delenv("PMG_NO_BOX3", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_BOX3", "1")
+            monkeypatch.setenv("PMG_NO_BOX_PAIR", "1")
+        lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.8)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options({"-gamgmc_pc_mg_levels": 3, "-pc_b200_tail_max_n": 0, "-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": ""})
+        pc.setup()
+        pc.set_noise_mode(pmg.NOISE_PHILOX)
+        ctx.set_seed(5)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=1)
+        out.append(y)
+    assert np.array_equal(out[0], out[1]), relerr(out[0], out[1])
+
+
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((257, 257), 6, {}),                                    # default sizing: levels 0..3 (65^2 and below) in the shared-memory tail
+    ((513, 129), 7, {"-gamgmc_mg_levels_ksp_max_it": 2}),
+    ((300, 140), 5, {"-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 0.8}),  # even sizes
+])
+def test_shared_memory_tail_default_sizing_is_bit_identical(pmg, ctx, dims, levels, extra, monkeypatch):
+    """Without -pc_b200_tail_max_n the V-cycle puts every level that fits into the one-CTA tail; the result must equal the
+    level-by-level path on the one-pass kernels (PMG_NO_TAIL_SMEM), and use fewer launches."""
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for smem in (True, False):
+        if smem:
+            monkeypatch.delenv("PMG_NO_TAIL_SMEM", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_TAIL_SMEM", "1")
+        lap = pmg.Mat.laplace(ctx, 2, *dims, 1, kappa=1.0)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels}))
+        pc.setup()
+        pc.set_noise_mode(pmg.NOISE_PHILOX)
+        ctx.set_seed(123)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=3)
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1]

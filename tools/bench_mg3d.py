@@ -20,3 +20,10 @@ e0.record(stream); mg.apply_richardson_dev(b, y, its=reps); e1.record(stream); t
 ms = e0.elapsed_time(e1) / reps
 print({"n": n, "levels": levels, "fused_top": os.environ.get("PMG_NO_FUSED_MG3") is None, "ms_per_sample": round(ms, 3), "samples_per_s": round(1e3 / ms, 2),
        "launches_per_sample": mg.last_stats()["launches"] / reps}, flush=True)
+if os.environ.get("PMG_PROFILE"):
+    mg.set_option("-pc_b200_profile", "1")
+    mg.apply_richardson_dev(b, y, its=reps)
+    torch.cuda.synchronize()
+    import json
+    for row in mg.profile():
+        print(row, flush=True)
