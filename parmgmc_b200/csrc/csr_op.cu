@@ -212,49 +212,71 @@ struct CsrOp final : LevelOp {
     cplan.clear();
     if (!dist || ctx->nranks == 1) return 0;
     const int P = ctx->nranks, me = ctx->rank;
-    // which colours of MY rows read ghost column q (bit c of mask[q]); more than 62 colours: keep the all-ghost plan
-    int64_t use = ncol <= 62 ? 1 : 0;
-    std::vector<int64_t> flags((size_t)P);
-    PMG_TRY(comm_allgather_i64(ctx, &use, 1, flags.data()));
-    for (int64_t f : flags)
-      if (!f) return 0;
-    std::vector<int64_t> mask((size_t)n_ghost, 0);
+    // (colour, ghost column) pairs: colour c of MY rows reads ghost column q; sorted by colour, then by ghost index (= owner, global id)
+    std::vector<std::pair<int32_t, int32_t>> pairs;
     for (int64_t r = 0; r < n_local; ++r)
       for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k)
-        if (A.col[k] >= n_local) mask[(size_t)(A.col[k] - n_local)] |= (int64_t)1 << color[(size_t)r];
-    std::vector<int64_t> cnts((size_t)P), mine1{n_ghost};
+        if (A.col[k] >= n_local) pairs.emplace_back(color[(size_t)r], (int32_t)(A.col[k] - n_local));
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    // everybody learns everybody's pairs as (colour, GLOBAL id) (set-up only)
+    std::vector<int64_t> cnts((size_t)P), mine1{(int64_t)pairs.size()};
     PMG_TRY(comm_allgather_i64(ctx, mine1.data(), 1, cnts.data()));
     int64_t mx = 1;
     for (int64_t v : cnts) mx = std::max(mx, v);
-    std::vector<int64_t> pad_gid((size_t)mx, -1), pad_mask((size_t)mx, 0), all_gid((size_t)mx * P), all_mask((size_t)mx * P);
-    std::copy(ghost_gid.begin(), ghost_gid.end(), pad_gid.begin());
-    std::copy(mask.begin(), mask.end(), pad_mask.begin());
-    PMG_TRY(comm_allgather_i64(ctx, pad_gid.data(), (int)mx, all_gid.data()));
-    PMG_TRY(comm_allgather_i64(ctx, pad_mask.data(), (int)mx, all_mask.data()));
-    // owner of each of my ghost columns (the ghost array is grouped by owner in rank order, recv_off)
+    std::vector<int64_t> pad((size_t)2 * mx, -1), all((size_t)2 * mx * P);
+    for (size_t q = 0; q < pairs.size(); ++q) {
+      pad[2 * q]     = pairs[q].first;
+      pad[2 * q + 1] = ghost_gid[(size_t)pairs[q].second];
+    }
+    PMG_TRY(comm_allgather_i64(ctx, pad.data(), (int)(2 * mx), all.data()));
+    // per rank: first pair of each colour (the lists are sorted by colour)
+    auto colour_range = [&](int r, int c, int64_t &lo, int64_t &hi) {
+      const int64_t *base = &all[(size_t)2 * mx * r];
+      int64_t        a0 = 0, a1 = cnts[(size_t)r];
+      while (a0 < a1) { const int64_t m = (a0 + a1) / 2; if (base[2 * m] < c) a0 = m + 1; else a1 = m; }
+      lo = a0;
+      a1 = cnts[(size_t)r];
+      while (a0 < a1) { const int64_t m = (a0 + a1) / 2; if (base[2 * m] <= c) a0 = m + 1; else a1 = m; }
+      hi = a0;
+    };
+    std::vector<int64_t> starts((size_t)P + 1, 0); // row ownership, from the all-ghost plan's set-up
+    {
+      std::vector<int64_t> me2{row_start, n_local}, a2((size_t)2 * P);
+      PMG_TRY(comm_allgather_i64(ctx, me2.data(), 2, a2.data()));
+      for (int r = 0; r < P; ++r) starts[(size_t)r] = a2[(size_t)2 * r];
+      starts[(size_t)P] = a2[(size_t)2 * (P - 1)] + a2[(size_t)2 * (P - 1) + 1];
+    }
     std::vector<int32_t> sidx, ridx;
     cplan.resize((size_t)ncol);
-    int64_t max_recv = 1;
+    int64_t max_recv = 1, max_send = 1;
     for (int c = 0; c < ncol; ++c) {
       ColourPlan &pl = cplan[(size_t)c];
       pl.send_base = (int64_t)sidx.size();
       pl.recv_base = (int64_t)ridx.size();
       pl.send_off.assign((size_t)P + 1, 0);
       pl.recv_off.assign((size_t)P + 1, 0);
+      int64_t mlo, mhi;
+      colour_range(me, c, mlo, mhi);
+      int64_t mq = mlo; // my pairs of this colour are sorted by ghost index, i.e. grouped by owner in rank order
       for (int r = 0; r < P; ++r) {
         if (r != me) {
-          for (int64_t q = 0; q < cnts[(size_t)r]; ++q) { // rank r's ghosts that I own and that its colour-c rows read, in r's ghost order
-            const int64_t g = all_gid[(size_t)r * mx + (size_t)q];
-            if (g >= row_start && g < row_start + n_local && ((all_mask[(size_t)r * mx + (size_t)q] >> c) & 1)) sidx.push_back((int32_t)(g - row_start));
+          int64_t lo, hi;
+          colour_range(r, c, lo, hi);
+          for (int64_t q = lo; q < hi; ++q) { // rank r's colour-c ghosts that I own, in r's ghost order
+            const int64_t g = all[(size_t)2 * mx * r + 2 * (size_t)q + 1];
+            if (g >= row_start && g < row_start + n_local) sidx.push_back((int32_t)(g - row_start));
           }
-          for (int64_t q = recv_off[(size_t)r]; q < recv_off[(size_t)r + 1]; ++q) // my ghosts owned by r that my colour-c rows read, in my ghost order
-            if ((mask[(size_t)q] >> c) & 1) ridx.push_back((int32_t)q);
         }
+        for (; mq < mhi && all[(size_t)2 * mx * me + 2 * (size_t)mq + 1] < starts[(size_t)r + 1]; ++mq) // my colour-c ghosts owned by r
+          ridx.push_back(pairs[(size_t)mq].second);
         pl.send_off[(size_t)r + 1] = (int64_t)sidx.size() - pl.send_base;
         pl.recv_off[(size_t)r + 1] = (int64_t)ridx.size() - pl.recv_base;
       }
       max_recv = std::max(max_recv, pl.recv_off[(size_t)P]);
+      max_send = std::max(max_send, pl.send_off[(size_t)P]);
     }
+    (void)max_send; // a colour sends a subset of the all-ghost send list: send_buf is large enough
     if (sidx.empty()) sidx.push_back(0);
     if (ridx.empty()) ridx.push_back(0);
     PMG_TRY(csend_idx.upload(sidx, ctx->stream));
@@ -445,9 +467,40 @@ struct CsrOp final : LevelOp {
   // A global distance-1 colouring without PETSc's Jones-Plassmann (which is PETSc-internal and unpinned):
   // greedy on the local graph with K = the largest local colour count, then colour + K (rank mod 2) when every rank's
   // ghost owners have the other parity (contiguous row blocks of banded matrices), else colour + K rank.
+  // PMG_COLORING_LEXICOGRAPHIC on a row-partitioned operator: the level sets of the GLOBAL natural order, level(r) = 1 + max level
+  // of the coupled rows with a smaller global index.  Sweeping the levels in ascending order IS the lexicographic Gauss-Seidel
+  // sweep over all ranks' rows (what the reference's PCPARSOR computes with its pipelined exact parallel SOR,
+  // src/pc_parsor.c:703-878, and its 1-rank MatSOR path), so a multi-GPU run reproduces the one-rank natural-order sampler.
+  // Rows of rank p only depend on ranks < p through their ghost columns: P rounds, in round p rank p finishes its levels.
+  int set_coloring_lexicographic_dist()
+  {
+    const int            P = ctx->nranks, me = ctx->rank;
+    std::vector<int32_t> lev((size_t)n_local, 0), gl;
+    for (int p = 0; p < P; ++p) {
+      PMG_TRY(ghost_colours(lev, gl)); // collective: current levels of my ghost columns (final for the ranks below p)
+      if (p != me) continue;
+      for (int64_t r = 0; r < n_local; ++r) {
+        int32_t L = 0;
+        for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) {
+          const int64_t c = A.col[k];
+          if (c < n_local) {
+            if (c < r) L = std::max(L, lev[(size_t)c] + 1);
+          } else if (ghost_gid[(size_t)(c - n_local)] < row_start + r) L = std::max(L, gl[(size_t)(c - n_local)] + 1);
+        }
+        lev[(size_t)r] = L;
+      }
+    }
+    int64_t mymax = 0;
+    for (int32_t v : lev) mymax = std::max<int64_t>(mymax, v);
+    std::vector<int64_t> all((size_t)P);
+    PMG_TRY(comm_allgather_i64(ctx, &mymax, 1, all.data()));
+    for (int64_t v : all) mymax = std::max(mymax, v);
+    return set_coloring((int)(mymax + 1), lev.data());
+  }
   int set_coloring_auto_dist(int policy)
   {
-    if (policy != PMG_COLORING_GREEDY && policy != PMG_COLORING_LEXICOGRAPHIC) PMG_FAIL(PMG_ERR_SUP, "row-partitioned operators: greedy colouring only");
+    if (policy == PMG_COLORING_LEXICOGRAPHIC) return set_coloring_lexicographic_dist();
+    if (policy != PMG_COLORING_GREEDY) PMG_FAIL(PMG_ERR_SUP, "row-partitioned operators: greedy or lexicographic (global level-set) colouring");
     std::vector<int32_t> loc;
     const int            P = ctx->nranks, me = ctx->rank;
     int64_t              kloc = host_coloring_greedy(Aloc, loc), parity_ok = 1;

@@ -860,7 +860,9 @@ static int gamgmc_setup(pmg_pc pc)
     std::vector<LevelOp *> ops;
     for (int l = 0; l < L - 1; ++l) {
       ops.push_back(pc->lv[l].op);
-      if (l >= 1 && !ops[l]->distributed() && grid_tail_smem_fits(l + 1, ops.data(), ops[0]->n())) tail_fit = l;
+      // one SM runs the whole tail: beyond a 65 x 65 top level (profiles/r2_summary.md: +27 us) the one-pass kernels on all SMs are faster
+      static const int64_t top_max = std::getenv("PMG_TAIL_SMEM_MAX") ? std::atoll(std::getenv("PMG_TAIL_SMEM_MAX")) : 4500;
+      if (l >= 1 && !ops[l]->distributed() && ops[l]->n() <= top_max && grid_tail_smem_fits(l + 1, ops.data(), ops[0]->n())) tail_fit = l;
     }
   }
   auto tail_sized = [&](int l) { return pc->lv[l].op->n() <= tail_max || l <= tail_fit; };

@@ -2142,7 +2142,7 @@ struct BoxOp final : GridOp {
     const int r = MODE == MODE_RESTRICT ? 1 : 0;
     if (!b2n[r]) { // about one resident wave of warps; bands start on even rows (the band that owns fine row 2J emits coarse row J)
       static const int by_env = std::getenv("PMG_BOX2_BY") ? std::atoi(std::getenv("PMG_BOX2_BY")) : 0;
-      static const int by_min = std::getenv("PMG_BOX2_BY_MIN") ? std::atoi(std::getenv("PMG_BOX2_BY_MIN")) : 4;
+      static const int by_min = std::getenv("PMG_BOX2_BY_MIN") ? std::atoi(std::getenv("PMG_BOX2_BY_MIN")) : 2; // short bands on small levels: a band step costs ~1.8 us of dependent FP64 latency (profiles/r2_summary.md)
       const int        slots   = occ_dev[dv] * WARPS * ctx->sm_count;
       const int        nstrips = (int)((g.n0 + Strip<MODE>::OUT - 1) / Strip<MODE>::OUT);
       int              by      = by_env > 0 ? by_env : std::max<int>(by_min, (int)(((g.shi - g.slo) * nstrips + slots - 1) / slots));
@@ -2505,8 +2505,14 @@ static int grid_tail_smem_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, 
   if ((int64_t)a.lv[0].n != chol.n) return 0;
   a.tmpoff = (int)off; off += chol.n;
   a.zoff   = (int)off; off += a.lv[top].n;
-  const size_t sm = (size_t)off * sizeof(double);
-  if (sm > 224 * 1024) return 0;
+  const size_t fixed = sizeof(fastnormal::SharedTables) + (size_t)9 * MAX_LEVELS * sizeof(box2d::Cls);
+  if (fixed + (size_t)off * sizeof(double) > 224 * 1024) return 0;
+  a.woff = a.wtoff = -1;
+  if (fixed + (size_t)(off + 2 * chol.n * chol.n) * sizeof(double) <= 224 * 1024) { // the coarsest sampler's factors fit as well
+    a.woff  = (int)off; off += chol.n * chol.n;
+    a.wtoff = (int)off; off += chol.n * chol.n;
+  }
+  const size_t sm = fixed + (size_t)off * sizeof(double);
   auto *tb = dynamic_cast<BoxOp *>(lv[top].op);
   if (tb->tail_cls_key != key) {
     tb->tail_cls_host.assign((size_t)9 * nlev, box2d::Cls{});
@@ -2550,7 +2556,7 @@ bool grid_tail_smem_fits(int nlev, LevelOp *const *ops, int64_t chol_n)
   }
   auto *tb = dynamic_cast<BoxOp *>(ops[nlev - 1]);
   off += chol_n + tb->g.nl;
-  return (size_t)off * sizeof(double) <= 224 * 1024;
+  return sizeof(fastnormal::SharedTables) + (size_t)9 * tail2d::MAX_LEVELS * sizeof(box2d::Cls) + (size_t)off * sizeof(double) <= 224 * 1024;
 }
 
 int grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns)

@@ -34,6 +34,7 @@ struct Args {
   int               zoff, tmpoff; // scratch (noise / residual) and the coarsest sampler's intermediate vector
   int               nc;
   const double     *W, *WT;
+  int               woff, wtoff; // >= 0: W / W^T are staged in the arena too (they fit), at these offsets
   int               mode;
   uint64_t          seed;
   TailNoise         ns[MAX_NOISE];
@@ -41,7 +42,7 @@ struct Args {
 
 __device__ __forceinline__ int cls1(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
 
-__device__ __forceinline__ void sweep(const Level &L, const box2d::Cls *cls, double *x, const double *b, double *zs, int dir, int mode, uint64_t seed, const TailNoise &tn)
+__device__ __forceinline__ void sweep(const Level &L, const box2d::Cls *cls, const fastnormal::Tables &ft, double *x, const double *b, double *zs, int dir, int mode, uint64_t seed, const TailNoise &tn)
 {
   const int n0 = L.n0, n1 = L.n1, tid = threadIdx.x;
   if (mode == PMG_NOISE_PHILOX) { // the level's normals, four per generator call (padded index space, philox.cuh)
@@ -50,7 +51,10 @@ __device__ __forceinline__ void sweep(const Level &L, const box2d::Cls *cls, dou
     for (int q = tid; q < nq; q += NT) {
       const int row = (int)(((float)q + 0.5f) * rq), qi = q - row * qrow;
       double    z[4];
-      philox_normal_quad(seed, tn.call, (uint64_t)q, z);
+      uint32_t  w0, w1, w2, w3;
+      philox4x32_10((uint32_t)q, 0u, (uint32_t)tn.call, (uint32_t)(tn.call >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), w0, w1, w2, w3); // philox_normal_quad, tables in shared memory
+      fastnormal::box_muller(ft, w0, w1, z[0], z[1]);
+      fastnormal::box_muller(ft, w2, w3, z[2], z[3]);
 #pragma unroll
       for (int m = 0; m < 4; ++m)
         if (4 * qi + m < n0) zs[row * n0 + 4 * qi + m] = z[m];
@@ -102,9 +106,21 @@ __device__ __forceinline__ void sweep(const Level &L, const box2d::Cls *cls, dou
 
 __global__ void __launch_bounds__(NT, 1) tail2d_kernel(const __grid_constant__ Args a)
 {
-  extern __shared__ __align__(16) double arena[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fastnormal::SharedTables *fts  = reinterpret_cast<fastnormal::SharedTables *>(smem_raw);
+  box2d::Cls               *clss = reinterpret_cast<box2d::Cls *>(fts + 1);
+  double                   *arena = reinterpret_cast<double *>(clss + 9 * MAX_LEVELS);
   const int tid = threadIdx.x;
   pdl_launch_dependents();
+  // everything constant comes into shared memory first, while the kernel before this one is still running: a kernel starts
+  // with a cold L1, and every table line fetched on demand would cost an L2 round trip on the critical path of a phase
+  const fastnormal::Tables ft = fastnormal::load_tables(*fts);
+  for (int q = tid; q < 9 * a.nlev * (int)(sizeof(box2d::Cls) / sizeof(double)); q += NT) reinterpret_cast<double *>(clss)[q] = reinterpret_cast<const double *>(a.cls)[q];
+  if (a.woff >= 0)
+    for (int q = tid; q < a.nc * a.nc; q += NT) {
+      arena[a.woff + q]  = a.W[q];
+      arena[a.wtoff + q] = a.WT[q];
+    }
   const int top = a.nlev - 1;
   int       kn  = 0; // cursor into the noise blocks, in the reference's consumption order (SURVEY 8(c) tape contract)
   double   *zs  = arena + a.zoff;
@@ -113,10 +129,10 @@ __global__ void __launch_bounds__(NT, 1) tail2d_kernel(const __grid_constant__ A
   __syncthreads();
   for (int l = top; l >= 1; --l) {
     const Level      &F = a.lv[l], &C = a.lv[l - 1];
-    const box2d::Cls *cls = a.cls + 9 * l;
+    const box2d::Cls *cls = clss + 9 * l;
     double           *x = arena + F.xoff;
     const double     *b = F.boff >= 0 ? arena + F.boff : a.btop;
-    for (int d = 0; d < F.ndirs; ++d, ++kn) sweep(F, cls, x, b, zs, F.dirs[d], a.mode, a.seed, a.ns[kn]);
+    for (int d = 0; d < F.ndirs; ++d, ++kn) sweep(F, cls, ft, x, b, zs, F.dirs[d], a.mode, a.seed, a.ns[kn]);
     const int n0 = F.n0, n1 = F.n1;
     {
       const box2d::Cls kin = cls[4];
@@ -173,21 +189,32 @@ __global__ void __launch_bounds__(NT, 1) tail2d_kernel(const __grid_constant__ A
     const Level     &C = a.lv[0];
     const TailNoise &tn = a.ns[kn];
     ++kn;
-    const NoiseArgs na{a.mode, tn.tape, a.seed, tn.call, 0};
     const double   *b0 = arena + C.boff;
     double         *x0 = arena + C.xoff, *tmp = arena + a.tmpoff;
     const int       lane = tid & 31, gw = tid >> 5, nw = NT >> 5, n = a.nc;
     for (int i = gw; i < n; i += nw) {
-      const double *row = a.W + (size_t)i * n;
+      const double *row = (a.woff >= 0 ? arena + a.woff : a.W) + (size_t)i * n;
       double        acc = 0.0;
       for (int k = lane; k < i + 1; k += 32) acc = fma(row[k], b0[k], acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) tmp[i] = na.mode != PMG_NOISE_NONE ? __dadd_rn(acc, noise_value(na, i)) : acc;
+      if (lane == 0) {
+        double zn = 0.0; // noise_value(na, i), with the shared-memory tables
+        if (a.mode == PMG_NOISE_INJECTED) zn = tn.tape[i];
+        else if (a.mode == PMG_NOISE_PHILOX) {
+          uint32_t w0, w1, w2, w3;
+          philox4x32_10((uint32_t)(i >> 2), 0u, (uint32_t)tn.call, (uint32_t)(tn.call >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w0, w1, w2, w3);
+          double zc, zsn;
+          if (i & 2) fastnormal::box_muller(ft, w2, w3, zc, zsn);
+          else fastnormal::box_muller(ft, w0, w1, zc, zsn);
+          zn = (i & 1) ? zsn : zc;
+        }
+        tmp[i] = a.mode != PMG_NOISE_NONE ? __dadd_rn(acc, zn) : acc;
+      }
     }
     __syncthreads();
     for (int i = gw; i < n; i += nw) {
-      const double *row = a.WT + (size_t)i * n;
+      const double *row = (a.wtoff >= 0 ? arena + a.wtoff : a.WT) + (size_t)i * n;
       double        acc = 0.0;
       for (int k = i + lane; k < n; k += 32) acc = fma(row[k], tmp[k], acc);
 #pragma unroll
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) tail2d_kernel(const __grid_constant__ A
   }
   for (int l = 1; l <= top; ++l) {
     const Level      &F = a.lv[l], &C = a.lv[l - 1];
-    const box2d::Cls *cls = a.cls + 9 * l;
+    const box2d::Cls *cls = clss + 9 * l;
     double           *x = arena + F.xoff;
     const double     *b = F.boff >= 0 ? arena + F.boff : a.btop, *xc = arena + C.xoff;
     const float rfn0 = 1.0f / (float)F.n0;
@@ -218,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1) tail2d_kernel(const __grid_constant__ A
       x[t] = s;
     }
     __syncthreads();
-    for (int d = 0; d < F.ndirs; ++d, ++kn) sweep(F, cls, x, b, zs, F.dirs[d], a.mode, a.seed, a.ns[kn]);
+    for (int d = 0; d < F.ndirs; ++d, ++kn) sweep(F, cls, ft, x, b, zs, F.dirs[d], a.mode, a.seed, a.ns[kn]);
   }
   for (int t = tid; t < a.lv[top].n; t += NT) a.xtop[t] = arena[a.lv[top].xoff + t];
 }

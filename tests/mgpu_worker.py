@@ -60,7 +60,9 @@ def csr_dist_case(ctx, rank, world, user_coloring):
     vals = M.data[M.indptr[r0]:M.indptr[r1]].astype(np.float64)
     mat = pmg.Mat.from_csr_dist(ctx, n, r0, rp, cols, vals)
     assert mat.size == (r1 - r0, n, r0)
-    if user_coloring:
+    if user_coloring == "lex":  # global level sets: the sweep over all ranks IS the natural-order Gauss-Seidel sweep (PCPARSOR's result)
+        mat.set_coloring_auto(pmg.COLORING_LEXICOGRAPHIC)
+    elif user_coloring:
         gcol = orc.Coloring.greedy(A)
         mat.set_coloring(gcol.color[r0:r1], gcol.ncolors)
         bad = gcol.color.copy()
@@ -114,8 +116,20 @@ def csr_dist_case(ctx, rank, world, user_coloring):
         # accumulates in global column order: same noise, same colouring, results equal to rounding
         e1, e2, e3 = np.abs(got - ref).max() / np.abs(ref).max(), np.abs(gots - refs).max(), np.abs(gax - M @ x_full).max()
         ok = e1 < 1e-13 and e2 < 1e-13 and e3 < 1e-12
-        print(f"[mgpu] csr_dist_{'user' if user_coloring else 'auto'}: world={world} starts={starts.tolist()} colours={kk} sampler_vs_1gpu={e1:.2e} "
-              f"mcsor_vs_oracle_MPIAIJ={e2:.2e} mult={e3:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+        extra = ""
+        if user_coloring == "lex":
+            # the colouring must be the level-set colouring of the WHOLE matrix, and the sweep the one-colour natural-order sweep
+            # of the reference's 1-rank path (src/mc_sor.c:397-410) -- what PCPARSOR reproduces in parallel (src/pc_parsor.c:703-878)
+            lex = orc.Coloring.levelset(A)
+            nat = y0_full.copy()
+            orc.MCSOR(A, orc.Coloring.single(n), 1.3, orc.SOR_SYMMETRIC).apply(b_full, nat)
+            e4 = np.abs(gots - nat).max()
+            same = bool(np.array_equal(lex.color, col)) and lex.ncolors == kk
+            ok = ok and same and e4 < 1e-13
+            extra = f" global_levelset={same} vs_natural_order_sweep={e4:.2e}"
+        tag = "lexicographic" if user_coloring == "lex" else ("user" if user_coloring else "auto")
+        print(f"[mgpu] csr_dist_{tag}: world={world} starts={starts.tolist()} colours={kk} sampler_vs_1gpu={e1:.2e} "
+              f"mcsor_vs_oracle_MPIAIJ={e2:.2e} mult={e3:.2e}{extra} -> {'OK' if ok else 'FAIL'}", flush=True)
         single.close()
     dist.barrier()
     return ok
@@ -160,7 +174,7 @@ def main():
             single.close()
         dist.barrier()
     if not sys.argv[1:]:
-        for user in (False, True):
+        for user in (False, True, "lex"):
             if not csr_dist_case(ctx, rank, world, user) and rank == 0:
                 failed.append("csr_dist")
     flag = torch.tensor([len(failed)], device="cuda")

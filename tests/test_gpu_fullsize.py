@@ -140,3 +140,90 @@ def test_full_size_vcycle_paths_agree_and_fixed_point(pmg, ctx, monkeypatch):
         del pc, mat
     assert torch.equal(out[0][0], out[1][0])
     assert out[0][1] * 2 < out[1][1]
+
+
+# ---- BASELINE's full sizes against the ORACLE itself (one oracle sweep / V-cycle of these sizes is seconds of CPU) -------------------
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+RTOL = 1e-12  # north_star: injected-noise sweeps agree with the reference to 1e-12 in FP64
+
+
+def test_full_size_fused_2d_sweep_matches_oracle(pmg, ctx, orc):
+    """config 2's grid, 4097^2: one symmetric multicolour Gibbs sweep (omega = 1.3) of the fused TMA kernel with an injected tape
+    against the oracle's MCSORApply restatement on the assembled operator (src/mc_sor.c:241-296, src/pc_mcgibbs.c:119-182)."""
+    dims = (4097, 4097, 1)
+    rng = np.random.default_rng(11)
+    A = orc.laplace(2, *dims, kappa=1.0)
+    col = orc.Coloring.parity(dims[:2])
+    mat, pc = _gibbs(pmg, ctx, 2, dims, 1.0, "injected", omega=1.3, sweep="symmetric")
+    z = rng.standard_normal(pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    y = y0.copy()
+    pc.apply_richardson(b, y, its=1)
+    ref = orc.gibbs_richardson(A, b, y0.copy(), 1, orc.Noise.tape(z), col, 1.3, orc.SOR_SYMMETRIC)
+    assert _relerr(y, ref) < RTOL, _relerr(y, ref)
+    assert np.array_equal(y, ref)  # same FMA contract as the oracle: bit-exact in practice
+
+
+def test_full_size_gamgmc_sample_matches_oracle(pmg, ctx, orc):
+    """config 2 itself: one PCGAMGMC V(1,1) sample on 4097^2 with the bench's hierarchy (10 levels, 9 x 9 dense Cholesky coarsest),
+    injected tape, through the one-pass kernels and the shared-memory tail, against the oracle's PCMG restatement
+    (src/pc_gamgmc.c:242-259)."""
+    n1, levels = 4097, 10
+    rng = np.random.default_rng(12)
+    lap = pmg.Mat.laplace(ctx, 2, n1, n1, 1, kappa=1.0)
+    pc = pmg.PC(ctx, "gamgmc")
+    pc.set_operator(lap)
+    pc.set_options({"-gamgmc_pc_mg_levels": levels, "-pc_b200_coloring": "parity"})
+    pc.setup()
+    omg = orc.MG.geometric(2, n1, n1, 1, 1.0, levels)
+    for l in range(levels):
+        d = omg.level_dims(l)
+        if l == 0:
+            omg.set_smoother(0, orc.KIND_CHOL, 1.0, 1, 1, None)
+        else:
+            omg.set_smoother(l, orc.KIND_SORGIBBS, 1.0, 1, 1, orc.Coloring.parity(d[:2], 2 if l == levels - 1 else 4))
+    omg.setup()
+    n = n1 * n1
+    z = rng.standard_normal(pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    y = y0.copy()
+    pc.apply_richardson(b, y, its=1)
+    ref = omg.richardson(orc.Noise.tape(z), b, y0.copy(), 1)
+    assert _relerr(y, ref) < RTOL, _relerr(y, ref)
+
+
+def test_full_size_fused_3d_sweep_matches_oracle(pmg, ctx, orc):
+    """config 3's grid, 512^3: one forward SOR-Gibbs sweep (omega = 1, the bench's kernel) of the fused 3D TMA kernel with an
+    injected tape against the oracle on the assembled 7-point operator (12 GB of CSR on the host)."""
+    import psutil
+    nn = 512 if psutil.virtual_memory().available > 40 * 2**30 else 320  # the assembled 512^3 operator needs ~12 GB + vectors
+    dims = (nn, nn, nn)
+    rng = np.random.default_rng(13)
+    A = orc.laplace(3, *dims, kappa=1.0)
+    col = orc.Coloring.parity(dims)
+    mat = pmg.Mat.laplace(ctx, 3, *dims, kappa=1.0)
+    pc = pmg.PC(ctx, "sorgibbs")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_b200_noise": "injected"})
+    pc.setup()
+    z = rng.standard_normal(pc.noise_per_sample())
+    pc.set_noise_tape(z)
+    b, y0 = rng.standard_normal(A.n), rng.standard_normal(A.n)
+    y = y0.copy()
+    pc.apply_richardson(b, y, its=1)
+    ref = orc.gibbs_richardson(A, b, y0.copy(), 1, orc.Noise.tape(z), col, 1.0, orc.SOR_FORWARD)
+    assert nn == 512, "host memory too small for the assembled 512^3 operator: ran 320^3 instead"
+    assert _relerr(y, ref) < RTOL, _relerr(y, ref)
+    assert np.array_equal(y, ref)
