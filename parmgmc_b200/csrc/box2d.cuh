@@ -341,12 +341,6 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   double bPrev[4] = {0, 0, 0, 0};                                          // b row e-2 (MODE_RESTRICT)
   double rP1[4] = {0, 0, 0, 0}, rP2[4] = {0, 0, 0, 0};                     // residual rows e-3, e-4 of the step being done
 
-  // The normals of a step are generated one step AHEAD: Philox -> Box-Muller is a ~25-deep chain of dependent FP64 operations and
-  // so are the row updates; a warp issues in order, so the two chains only overlap when they are independent inside one
-  // iteration (measured on B200: a step costs ~1.8 us of dependent-issue latency, profiles/r2_summary.md).
-  double zA[4], zB[4];
-  W.noise_row(e0, zA);
-  W.noise_row(e0 - 1, zB);
   int e = e0;
   for (int t = 0; t < T; ++t, e += 2) {
     const int      s   = t % STAGES;
@@ -370,11 +364,9 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       W.prolong(e + 2, xb);
       if (e + 2 <= elast) W.prefetch_coarse(e + 3);
     }
-    double zA2[4] = {0, 0, 0, 0}, zB2[4] = {0, 0, 0, 0};
-    if (t + 1 < T) {
-      W.noise_row(e + 2, zA2);
-      W.noise_row(e + 1, zB2);
-    }
+    double zA[4], zB[4];
+    W.noise_row(e, zA);
+    W.noise_row(e - 1, zB);
     W.row_update(e, R0, Rm1, xa, bA, zA);      // A row e: neighbours rows e-1, e+1 old
     W.row_update(e - 1, Rm1, Rm2, R0, bB, zB); // B row e-1: neighbour rows e-2, e final
     if (out_lane) {
@@ -405,8 +397,6 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       Rm2[m] = R0[m];
       Rm1[m] = xa[m];
       R0[m]  = xb[m];
-      zA[m]  = zA2[m];
-      zB[m]  = zB2[m];
     }
   }
 }

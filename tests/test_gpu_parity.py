@@ -1394,3 +1394,55 @@ def test_shared_memory_tail_default_sizing_is_bit_identical(pmg, ctx, dims, leve
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
     assert out[0][1] < out[1][1]
+
+
+# ---- the Matern sampler object (src/ms.c) and the Python module (python/main.cc) over the device samplers ------------
+def test_ms_object_and_pymgmc_module(pmg, ctx):
+    from parmgmc_b200 import pymgmc
+    from parmgmc_b200.ms import MS
+    import scipy.sparse as sp
+    nx, N = 17, 4000
+    ms = MS(ctx)
+    ms.set_from_options({"-matern_kappa": 6.0, "-ms_gamgmc_pc_mg_levels": 3})
+    ms.set_grid(2, nx, nx)
+    ms.setup()
+    pymgmc.use(ctx)
+    pymgmc.seed(77)
+    A = ms.get_precision_matrix()
+    n = A.n
+    # exact covariance of the target N(0, A^-1) from the operator applied to the unit vectors
+    dense = np.stack([A.mult(np.eye(n)[:, j].copy()) for j in range(n)], axis=1)
+    Sigma = np.linalg.inv(dense)
+    x = np.zeros(n)
+    ms.set_num_samples(200)
+    ms.sample(x)  # burn-in
+    ms.set_num_samples(N)
+    meas = np.full(n, 1.0 / n)
+    ms.set_qoi(lambda it, y: float(meas @ y))
+    for keep in (True, False):
+        ms.begin_save_samples(keep=keep)
+        if keep:
+            assert len(ms.get_samples()) == N
+        ms.sample(x)
+        ms.end_save_samples()
+        mean, var = ms.get_mean_and_var()
+        q = ms.get_qoi_values()
+        assert np.linalg.norm(mean) < 4.5 * np.sqrt(np.trace(Sigma) / N)                  # E y = 0
+        assert np.abs(var / np.diag(Sigma) - 1.0).max() < 6.0 * np.sqrt(2.0 / N) * 1.5    # MGMC samples are nearly independent
+        qv = meas @ Sigma @ meas
+        assert abs(q.mean()) < 4.5 * np.sqrt(qv / N) and abs(q.var(ddof=1) / qv - 1.0) < 0.15
+    try:
+        ms.get_samples()
+        raise AssertionError("MSGetSamples outside a save window must fail (src/ms.c:201)")
+    except RuntimeError:
+        pass
+    # pymgmc: seed() makes the chain reproducible, PCSetSampleCallback sees every sample
+    out = []
+    for _ in range(2):
+        pymgmc.seed(5)
+        seen = []
+        pymgmc.PCSetSampleCallback(ms.pc, lambda it, y: seen.append((it, float(y[0]))))
+        y = np.zeros(n)
+        ms.pc.apply_richardson(None, y, its=5)
+        out.append((y.copy(), seen))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1] and [s[0] for s in out[0][1]] == [0, 1, 2, 3, 4]
