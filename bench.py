@@ -221,7 +221,7 @@ def run_reference(args):
                             "sample": f"{T} chains x {steps_done} step(s) x {per_step} sample(s) of the full {nx}x{ny} workload (slowest chain {slowest:.1f} s, per-chain budget {args.ref_budget_s:.0f} s); "
                                       "the reference (PETSc+MPI) cannot be built here, so each chain is the oracle port of its 1-rank path"},
            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -405,7 +405,7 @@ def run_b200(args):
         dist.broadcast(flag, src=0)
         if int(flag.item()):
             if rank == 0:
-                print(json.dumps({"metric": "mgmc_samples_per_s", "error": "multi-GPU parity check failed", "parity_check": parity}), flush=True)
+                _emit({"metric": "mgmc_samples_per_s", "error": "multi-GPU parity check failed", "parity_check": parity})
             dist.destroy_process_group()
             sys.exit(1)
         ctx.set_seed(0xCAFE)
@@ -636,12 +636,35 @@ def run_b200(args):
             out["parity_check"] = parity
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+    box sets NCCL_DEBUG=VERSION): everything but the JSON line goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

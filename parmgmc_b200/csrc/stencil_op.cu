@@ -315,9 +315,10 @@ __device__ __forceinline__ bool quad_of_thread(const Geom &g, int nq, int &t, in
 __global__ void __launch_bounds__(256) lap_residual3_pitched_kernel(Geom g, LapTab tab, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ out)
 {
   const int nq = (int)(g.ld >> 2);
-  int       t, j, k;
-  if (!quad_of_thread(g, nq, t, j, k)) return;
-  const int64_t idx = 4 * (int64_t)t + g.ld * ((int64_t)j + g.n1 * (int64_t)k);
+  int       t, j, kl;
+  if (!quad_of_thread(g, nq, t, j, kl)) return; // kl: plane of the slab (the vectors start at the first owned plane, ghost planes in place around them)
+  const int     k   = kl + (int)g.slo;
+  const int64_t idx = 4 * (int64_t)t + g.ld * ((int64_t)j + g.n1 * (int64_t)kl);
   const bool    S = j > 0, N = j < g.n1 - 1, D = k > 0, U = k < g.n2 - 1;
   double        xc[4], xs[4] = {0, 0, 0, 0}, xn[4] = {0, 0, 0, 0}, xd[4] = {0, 0, 0, 0}, xu[4] = {0, 0, 0, 0}, bb[4], r[4];
   ldg256(x + idx, xc);
@@ -346,12 +347,13 @@ __global__ void __launch_bounds__(256) lap_residual3_pitched_kernel(Geom g, LapT
   }
   stg256(out + idx, r);
 }
-__global__ void __launch_bounds__(256) prolong3_pitched_kernel(Geom gf, Geom gc, const double *__restrict__ xc, double *__restrict__ xf)
+__global__ void __launch_bounds__(256) prolong3_pitched_kernel(Geom gf, Geom gc, const double *__restrict__ xc, const double *__restrict__ clo, const double *__restrict__ chi, double *__restrict__ xf)
 {
   const int nq = (int)(gf.ld >> 2);
-  int       t, j, k;
-  if (!quad_of_thread(gf, nq, t, j, k)) return;
-  const int64_t idx = 4 * (int64_t)t + gf.ld * ((int64_t)j + gf.n1 * (int64_t)k);
+  int       t, j, kl;
+  if (!quad_of_thread(gf, nq, t, j, kl)) return; // kl: plane of the fine slab; xc holds the coarse slab, clo / chi the coarse planes below / above it
+  const int     k   = kl + (int)gf.slo;
+  const int64_t idx = 4 * (int64_t)t + gf.ld * ((int64_t)j + gf.n1 * (int64_t)kl);
   double        s[4];
   ld256(xf + idx, s);
   const int cj = (j & 1) ? 2 : 1, ck = (k & 1) ? 2 : 1;
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(256) prolong3_pitched_kernel(Geom gf, Geom gc,
     for (int bq = 0; bq < cj; ++bq) {
       const int J = J0 + bq;
       if (J >= gc.n1) continue;
-      const double *row = xc + gc.ld * ((int64_t)J + gc.n1 * (int64_t)K);
+      const double *row = K < gc.slo ? clo + gc.ld * (int64_t)J : (K >= gc.shi ? chi + gc.ld * (int64_t)J : xc + gc.ld * ((int64_t)J + gc.n1 * (int64_t)(K - gc.slo)));
       const double  v0 = I0 < gc.n0 ? __ldg(row + I0) : 0.0, v1 = I0 + 1 < gc.n0 ? __ldg(row + I0 + 1) : 0.0, v2 = I0 + 2 < gc.n0 ? __ldg(row + I0 + 2) : 0.0;
       const double  we = (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0), wo = 0.5 * (cj == 2 ? 0.5 : 1.0) * (ck == 2 ? 0.5 : 1.0); // even / odd fine column
       if (I0 < gc.n0) s[0] = fma(we, v0, s[0]);
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(256) restrict3_pitched_kernel(Geom gf, Geom gc
   const int      nqc = (int)((gc.n0 + 3) >> 2);
   const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (unsigned)nqc * (unsigned)gc.n1) return;
-  const int J = (int)(q / (unsigned)nqc), t = (int)(q - (unsigned)J * (unsigned)nqc), K = (int)blockIdx.y;
+  const int J = (int)(q / (unsigned)nqc), t = (int)(q - (unsigned)J * (unsigned)nqc), Kl = (int)blockIdx.y, K = Kl + (int)gc.slo; // Kl: plane of the coarse slab
   double    acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int dk = -1; dk <= 1; ++dk) {
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(256) restrict3_pitched_kernel(Geom gf, Geom gc
     for (int dj = -1; dj <= 1; ++dj) {
       const int j = 2 * J + dj;
       if (j < 0 || j >= gf.n1) continue;
-      const double *row = r + gf.ld * ((int64_t)j + gf.n1 * (int64_t)k);
+      const double *row = r + gf.ld * ((int64_t)j + gf.n1 * (int64_t)(k - gf.slo)); // r starts at the first owned fine plane; planes slo-1 / shi are its ghost planes, in place
       const int     i0 = 8 * t; // fine column of the thread's first coarse node
       double        v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // fine columns i0-1 .. i0+7; columns >= ld are not loaded
       if (i0 > 0) v[0] = __ldg(row + i0 - 1);
@@ -422,7 +424,14 @@ __global__ void __launch_bounds__(256) restrict3_pitched_kernel(Geom gf, Geom gc
   }
 #pragma unroll
   for (int m = 0; m < 4; ++m)
-    if (4 * t + m < gc.n0) bc[4 * t + m + gc.ld * ((int64_t)J + gc.n1 * (int64_t)K)] = acc[m];
+    if (4 * t + m < gc.n0) bc[4 * t + m + gc.ld * ((int64_t)J + gc.n1 * (int64_t)Kl)] = acc[m];
+}
+
+// the four-columns-per-thread transfers above on a slab pair: pitched fine vectors (row stride a multiple of 4) with their ghost
+// planes in place, coarse vectors in the natural layout with rows short enough for one launch
+static bool pitched3_slab_ok(const Geom &gf, const Geom &gc)
+{
+  return gf.dim == 3 && (gf.ld & 3) == 0 && gf.shi > gf.slo && gc.shi > gc.slo && gc.shi - gc.slo <= 65535 && gf.shi - gf.slo <= 65535 && !std::getenv("PMG_NO_PITCHED3_SLAB");
 }
 
 // natural (row stride n0) <-> pitched (row stride pitch) copies of a 2D slab
@@ -1191,6 +1200,8 @@ struct LapOp final : GridOp {
     PMG_PLAN_CHECK(pl);
     const double *xo = x + off;
     if (g.dim == 2) lap_apply_kernel<2, true><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, tab, b + off, xo, xo - gp.unit, xo + gp.nl, r + off);
+    else if (!std::getenv("PMG_NO_PITCHED3_SLAB")) // four columns per thread, ghost planes read in place (the per-node kernel costs 2x, profiles/r1_summary.md)
+      lap_residual3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)(g.shi - g.slo)), 256, 0, ctx->stream>>>(gp, tab, b + off, xo, r + off);
     else lap_apply_kernel<3, true><<<pl.grid, pl.block, 0, ctx->stream>>>(gp, tab, b + off, xo, xo - gp.unit, xo + gp.nl, r + off);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -1598,7 +1609,7 @@ struct LapOp final : GridOp {
       const Geom gp = pitched(g, pitch());
       if (xc) { // x_old = xin + P xc, in place (the caller's iterate buffer: it is dead after this sweep)
         const Geom &gc = static_cast<GridOp *>(coarse)->g;
-        prolong3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)g.n2), 256, 0, ctx->stream>>>(gp, gc, xc, const_cast<double *>(xin));
+        prolong3_pitched_kernel<<<dim3((unsigned)(((pitch() >> 2) * g.n1 + 255) / 256), (unsigned)g.n2), 256, 0, ctx->stream>>>(gp, gc, xc, nullptr, nullptr, const_cast<double *>(xin));
         PMG_CUDA(cudaGetLastError());
         ctx->launches++;
       }
@@ -2349,6 +2360,7 @@ struct GridTransfer final : Transfer {
     PMG_PLAN_CHECK(pl);
     const double *ro = r + off;
     if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, bcoarse);
+    else if (pitched3_slab_ok(gf, gc)) restrict3_pitched_kernel<<<dim3((unsigned)((((gc.n0 + 3) >> 2) * gc.n1 + 255) / 256), (unsigned)(gc.shi - gc.slo)), 256, 0, ctx->stream>>>(gf, gc, ro, bcoarse);
     else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, bcoarse);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -2364,6 +2376,7 @@ struct GridTransfer final : Transfer {
     const Plan  pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
     PMG_PLAN_CHECK(pl);
     if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf + off);
+    else if (pitched3_slab_ok(gf, gc)) prolong3_pitched_kernel<<<dim3((unsigned)(((gf.ld >> 2) * gf.n1 + 255) / 256), (unsigned)(gf.shi - gf.slo)), 256, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf + off);
     else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, coarse->ghost_lo.p, coarse->ghost_hi.p, xf + off);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -2430,6 +2443,7 @@ struct ReplicatingTransfer final : Transfer {
       PMG_PLAN_CHECK(pl);
       const double *ro = r + off;
       if (gf.dim == 2) restrict_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, slab.p);
+      else if (pitched3_slab_ok(gf, gc)) restrict3_pitched_kernel<<<dim3((unsigned)((((gc.n0 + 3) >> 2) * gc.n1 + 255) / 256), (unsigned)(gc.shi - gc.slo)), 256, 0, ctx->stream>>>(gf, gc, ro, slab.p);
       else restrict_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, ro, ro - gf.unit, ro + gf.nl, slab.p);
       PMG_CUDA(cudaGetLastError());
       ctx->launches++;
@@ -2445,6 +2459,7 @@ struct ReplicatingTransfer final : Transfer {
     const Plan    pl = gf.dim == 2 ? plan_nodes<2>(gf) : plan_nodes<3>(gf);
     PMG_PLAN_CHECK(pl);
     if (gf.dim == 2) prolong_kernel<2><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf + off);
+    else if (pitched3_slab_ok(gf, gc)) prolong3_pitched_kernel<<<dim3((unsigned)(((gf.ld >> 2) * gf.n1 + 255) / 256), (unsigned)(gf.shi - gf.slo)), 256, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf + off);
     else prolong_kernel<3><<<pl.grid, pl.block, 0, ctx->stream>>>(gf, gc, xc, xc - gc.unit, xc + gc.nl, xf + off);
     PMG_CUDA(cudaGetLastError());
     ctx->launches++;
