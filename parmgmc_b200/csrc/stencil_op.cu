@@ -25,6 +25,7 @@
 #include "stream2d.cuh"
 #include "sweep2d.cuh"
 #include "sweep3d.cuh"
+#include "sweep3d_ws.cuh"
 #include "box_stream.cuh"
 #include "box2d.cuh"
 #include "box3d.cuh"
@@ -1352,8 +1353,52 @@ struct LapOp final : GridOp {
     return 0;
   }
   bool split_launch = false; // set by the sweep that started its halo exchange on the communication stream
+  // the persistent warp-specialised kernel (sweep3d_ws.cuh): device Philox noise, swizzled boxes; one CTA per SM draws tiles
+  DevBuf<sweep3d::WsQueue> queue3;
+  int launch3_ws(sweep3d::Args &a, const double *b, const double *xin)
+  {
+    using namespace sweep3d;
+    constexpr int NW = WS_NW;
+    auto          kern = sweep3d_ws_kernel;
+    const size_t  sm   = Smem<NW, WS_SX, WS_SB, true>::total;
+    PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    if (!queue3.p) {
+      PMG_TRY(queue3.alloc(1));
+      PMG_TRY(queue3.zero(ctx->stream));
+    }
+    a.swizzle = 1;
+    const int64_t dims[4] = {4, pitch() / 4, g.n1, g.shi - g.slo + 2 * GH()}, strides[4] = {1, 4, pitch(), pitch() * g.n1};
+    const int     boxx[4] = {4, 32, NW + 2, 1}, boxb[4] = {4, 32, NW, 1};
+    const int     boxx16[4] = {4, 16, 2 * NW + 2, 1}, boxb16[4] = {4, 16, 2 * NW, 1};
+    PMG_TRY(make_tensor_map(a.tm_x, xin, 4, dims, strides, boxx, true));
+    PMG_TRY(make_tensor_map(a.tm_b, b ? b : xin, 4, dims, strides, boxb, true));
+    PMG_TRY(make_tensor_map(a.tm_x16, xin, 4, dims, strides, boxx16, true));
+    PMG_TRY(make_tensor_map(a.tm_b16, b ? b : xin, 4, dims, strides, boxb16, true));
+    static const int bz_env = std::getenv("PMG_SW3_BZ") ? std::atoi(std::getenv("PMG_SW3_BZ")) : 0;
+    const int        bz     = bz_env > 0 ? bz_env : 64;
+    if (items3_bz != bz || items3_nw != NW) PMG_TRY(build_items3(bz, NW));
+    a.queue = queue3.p;
+    auto go = [&](const sweep3d::Item *items, int n) {
+      a.items  = items;
+      a.nitems = n;
+      kern<<<(unsigned)std::min(n, ctx->sm_count), NW * 64, sm, ctx->stream>>>(a);
+    };
+    if (split_launch && nitems3_nohalo > 0 && nitems3_nohalo < nitems3) { // interior tiles | wait for the halo | boundary tiles
+      go(items3.p, nitems3_nohalo);
+      PMG_TRY(halo_wait());
+      go(items3.p + nitems3_nohalo, nitems3 - nitems3_nohalo);
+      ctx->launches++;
+    } else {
+      if (split_launch) PMG_TRY(halo_wait());
+      go(items3.p, nitems3);
+    }
+    split_launch = false;
+    return 0;
+  }
   template <int NOISE> int launch3_cfg(int cfg, sweep3d::Args &a, const double *b, const double *xin)
   {
+    static const bool plain = std::getenv("PMG_SW3_PLAIN") != nullptr;
+    if (cfg == 7 && NOISE == sweep3d::NOISE_PHILOX && !plain) return launch3_ws(a, b, xin);
     switch (cfg) {
     case 1: return launch3<NOISE, 8, 3, 2, 2>(a, b, xin);  // 256 threads, 128 registers, 2 CTAs / SM
     case 2: return launch3<NOISE, 16, 4, 2, 1>(a, b, xin); // 512 threads, 128 registers, 1 CTA / SM
@@ -1382,8 +1427,12 @@ struct LapOp final : GridOp {
     if (!xin) PMG_FAIL(PMG_ERR_ARG, "fused 3D sweep needs an iterate");
     LapTab t;
     fill_tab(co.omega, t);
-    static const int cfg_env = std::getenv("PMG_SW3_CFG") ? std::atoi(std::getenv("PMG_SW3_CFG")) : -1;
-    const int        cfg     = cfg_env >= 0 && cfg_env <= 6 ? cfg_env : (g.n1 >= 48 ? 6 : 1); // 6: warp-specialised for Philox, <16,4,2,1> otherwise
+    const char      *cfg_str = std::getenv("PMG_SW3_CFG"); // read per call: the tests switch kernels inside one process
+    const int        cfg_env = cfg_str ? std::atoi(cfg_str) : -1;
+    // warp-specialised kernels for Philox on grids with >= 48 rows: 7 = persistent (sweep3d_ws.cuh), 6 = one CTA per tile.  Measured
+    // on 512^3 (profiles/r2_summary.md): with a right-hand side both are bound by the memory system at the same time (6 is 0 - 2 %
+    // ahead), without one (prior sampling, 16 B per update) the persistent kernel's shorter instruction stream is 16 % faster
+    const int        cfg     = cfg_env >= 0 && cfg_env <= 7 ? cfg_env : (g.n1 >= 48 ? (b ? 6 : 7) : 1);
     Args a;
     a.nx = (int)g.n0; a.ny = (int)g.n1; a.nz = (int)g.n2; a.slo = (int)g.slo; a.shi = (int)g.shi;
     a.tlo = (int)g.slo - GH(); a.thi = (int)g.shi + GH();

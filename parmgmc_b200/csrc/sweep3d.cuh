@@ -49,6 +49,10 @@ struct Item {
   int narrow; // 1: the last, short strip of a row (at most 56 columns): 16 lanes per grid row, two grid rows per warp
 };
 
+struct WsQueue { // work queue of the persistent kernel (sweep3d_ws.cuh): device memory, zero between launches
+  unsigned next;
+};
+
 struct Args {
   CUtensorMap   tm_x, tm_b; // {4, pitch/4, ny, local planes} FP64 tensors (SWIZZLE_32B); boxes 4 x 32 x (NW+2) x 1 and 4 x 32 x NW x 1
   CUtensorMap   tm_x16, tm_b16; // the same tensors with the boxes of a narrow strip: 4 x 16 x (2NW+2) x 1 and 4 x 16 x 2NW x 1
@@ -56,6 +60,8 @@ struct Args {
   int           slo, shi; // owned planes: the planes that are written, and the planes the injected tape covers
   int           tlo, thi; // planes held by the tensors and by xout: the owned planes plus two ghost planes per side on a slab
   const Item   *items;
+  int           nitems;   // persistent kernel: tiles of this launch, drawn from `queue`
+  WsQueue      *queue;
   int           pitch;    // row stride of xout
   long long     pplane;   // plane stride of xout = pitch * ny
   int           flip;     // 0: forward sweep (colour (i+j+k) even first); 1: backward

@@ -1167,7 +1167,7 @@ def test_device_qoi_trace_welford_and_iact(pmg, ctx, orc):
 # ---- the fused 3D sweep on shapes that exercise narrow last strips (16 lanes per grid row), thin z-edge bands, ------------
 # ---- z-constant edge tiles and ragged tile edges: bitwise equal to one launch per colour (itself pinned to the oracle) ------
 @pytest.mark.parametrize("noise", ["philox", "injected", "none"])
-@pytest.mark.parametrize("dims", [(150, 40, 20), (130, 35, 9), (50, 64, 16), (512, 33, 12), (176, 61, 70), (57, 31, 12), (36, 30, 5)])
+@pytest.mark.parametrize("dims", [(150, 40, 20), (130, 35, 9), (50, 64, 16), (512, 33, 12), (176, 61, 70), (57, 31, 12), (36, 30, 5), (300, 100, 40), (260, 50, 141), (128, 48, 7)])
 def test_fused_3d_sweep_shapes_equal_per_colour(pmg, ctx, dims, noise, monkeypatch):
     rng = np.random.default_rng(SEED)
     n = dims[0] * dims[1] * dims[2]
@@ -1191,6 +1191,34 @@ def test_fused_3d_sweep_shapes_equal_per_colour(pmg, ctx, dims, noise, monkeypat
         out.append((y, pc.last_stats()["launches"]))
     assert np.array_equal(out[0][0], out[1][0])
     assert out[0][1] != out[1][1]  # two code paths
+
+
+# ---- the persistent warp-specialised 3D sweep (sweep3d_ws.cuh; device Philox noise; the default without a right-hand side, ----
+# ---- PMG_SW3_CFG=7 forces it with one): interior, edge, z-constant and narrow tiles, several z bands, tiles that continue ----
+# ---- a CTA's mbarrier phases from the tile before -- bitwise equal to the one-CTA-per-tile kernel and to one launch per colour
+@pytest.mark.parametrize("rhs", [False, True])
+@pytest.mark.parametrize("dims", [(300, 100, 40), (260, 50, 141), (128, 48, 7), (50, 64, 16), (176, 61, 70), (512, 70, 9)])
+def test_persistent_3d_sweep_equals_per_tile_and_per_colour(pmg, ctx, dims, rhs, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1] * dims[2]
+    b, y0 = (rng.standard_normal(n) if rhs else None), rng.standard_normal(n)
+    out = []
+    for path in ("persistent", "per_tile", "per_colour"):
+        monkeypatch.delenv("PMG_NO_FUSED", raising=False)
+        monkeypatch.setenv("PMG_SW3_CFG", "7" if path == "persistent" else "6")
+        if path == "per_colour":
+            monkeypatch.setenv("PMG_NO_FUSED", "1")
+        mat = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.7)
+        pc = pmg.PC(ctx, "mcgibbs")
+        pc.set_operator(mat)
+        pc.set_options({"-pc_mcgibbs_omega": 1.3, "-pc_mcgibbs_symmetric": "", "-pc_b200_noise": "philox"})
+        pc.setup()
+        ctx.set_seed(11)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=2)
+        out.append(y)
+    assert np.array_equal(out[0], out[2])
+    assert np.array_equal(out[1], out[2])
 
 
 # ---- BASELINE config 5: P1 finite elements on data/lshape.msh, 17 ball observations with sigma^2 = 1e-5 as a MATLRC term ------

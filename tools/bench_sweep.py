@@ -13,7 +13,7 @@ stream = torch.cuda.current_stream()
 ctx = pmg.Context(0, stream=stream.cuda_stream, seed=0xCAFE)
 mat = pmg.Mat.laplace(ctx, dim, n, n, n if dim == 3 else 1, kappa=1.0)
 y = torch.zeros(mat.n, dtype=torch.float64, device="cuda")
-b = torch.zeros(mat.n, dtype=torch.float64, device="cuda")
+b = None if os.environ.get("NOB") else torch.zeros(mat.n, dtype=torch.float64, device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 out = {}
 if what in ("both", "gibbs"):
