@@ -22,6 +22,8 @@
 //
 // Arithmetic per node is box_sweep_kernel<3>'s / box_apply_kernel<3>'s, fma for fma (bit-identical results; tested).
 #pragma once
+#include <type_traits>
+
 #include "common.hpp"
 #include "philox.cuh"
 
@@ -183,6 +185,227 @@ template <int NT> __global__ void __launch_bounds__(NT, 1) box3_sweep_kernel(con
       phase(0, aa, ab, jz0);
     }
   }
+}
+
+// ---- the same sweep with the block's rows staged in shared memory, DE-INTERLEAVED by column parity ------------------------
+// box3_sweep_kernel reads its 26 neighbours with stride-2 64-bit loads: a warp's load touches 512 bytes of L1 for 256 useful
+// ones, and the kernel is bound by L1 wavefronts (profiles/r2_summary.md).  Here the rows of planes k-1, k, k+1 live in a RING
+// of shared-memory rows with the even columns of a grid row in one array and the odd columns in another (zeros for rows /
+// planes / columns outside the grid: their class coefficients are zero, so they add fma(0, 0, s) = s).  The rows block m+1
+// needs beyond those of block m are fetched with cp.async (8 bytes per copy, which de-interleaves for free) while block m is
+// swept, so no load latency is exposed; the rows of plane k are never re-read from global memory (the phases write their
+// results to shared AND global memory).  The noisy right-hand side w = b + sqrtdiag z of the block's rows is formed once, four
+// nodes per generator call, into shared memory before the block's phases: a phase touches global memory with stores only.
+// A colour phase reads unit-stride: a thread owns TWO neighbouring nodes of its colour (array indices q0, q0 + 1, q0 even)
+// and fetches, per neighbouring row, the pair of its own parity and the aligned pair of the other parity with one 128-bit load
+// each, plus one 64-bit load for the third column of the other parity -- 27 load instructions and 360 bytes for two nodes
+// instead of 52 and 832.  The first and last column of a row (boundary classes in x) are items of their own at the end of the
+// work list; boundary rows / planes run the pair code with their class's coefficients from the table.
+// Arithmetic per node: box_sweep_kernel<3>'s, fma for fma.
+struct SmemGeom {
+  int H;  // doubles per parity array of a staged row (2 leading zeros, the columns, trailing zeros), even
+  int RR; // rows of the ring per plane = 4R + 3: rows lo-1 .. hi+1 of the block being swept, and the 2R further rows of the next
+};
+__device__ __forceinline__ int soff(int col, int H) { return ((col & 1) ? H + 2 : 2) + (col >> 1); } // col = -1 and col = n0 fall on zero pads
+__device__ __forceinline__ void cp_async8(double *dst, const double *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int NT> __global__ void __launch_bounds__(NT, 1) box3_sweep_smem_kernel(const __grid_constant__ Args a, int kpar, int backward, NoiseArgs na, SmemGeom sg)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cls    *cls = reinterpret_cast<Cls *>(smem_raw);
+  double *zs  = reinterpret_cast<double *>(cls + 27); // noisy right-hand side of the block's rows, [2R+1][pitch4]
+  const int R = a.R, n0 = a.n0, n1 = a.n1, H = sg.H, RS = 2 * sg.H, RR = sg.RR;
+  double *xs  = zs + (size_t)(2 * R + 1) * a.pitch4; // [3][RR][RS]
+  const int k = a.slo + ((kpar ^ a.slo) & 1) + 2 * (int)blockIdx.x;
+  if (k >= a.shi) return;
+  for (int q = threadIdx.x; q < (int)(sizeof(Tab) / sizeof(double)); q += NT) reinterpret_cast<double *>(cls)[q] = reinterpret_cast<const double *>(a.tab)[q];
+  for (int q = threadIdx.x; q < 3 * RR * RS; q += NT) xs[q] = 0.0; // pads and absent planes stay zero for the whole launch
+  const double *P[3];
+  plane_ptrs(a, a.x, k, P);
+  const double *P0 = k - 1 >= 0 ? P[0] : nullptr, *P1 = P[1], *P2 = k + 1 < a.n2 ? P[2] : nullptr;
+  double       *xk = a.x + (long long)(k - a.slo) * n0 * n1;
+  const double *bk = a.b ? a.b + (long long)(k - a.slo) * n0 * n1 : nullptr;
+  const double *tk = na.mode == PMG_NOISE_INJECTED ? na.tape + (long long)(k - a.slo) * n0 * n1 : nullptr;
+  const int     cz = cls1(k, a.n2);
+  const int     qrow = a.pitch4 >> 2, ne = (n0 + 1) >> 1, no = n0 >> 1;
+  const int     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long PS = (long long)RR * RS; // plane stride of the ring
+  __syncthreads();
+
+  auto slot = [&](int j) { return (j + 1) % RR; }; // ring row of grid row j >= -1
+  // rows [ja, jb) of the three planes into the ring: one (plane, row) per warp at a time
+  auto prefetch = [&](int ja, int jb) {
+    const int nrow = jb - ja;
+    for (int rw = warp; rw < 3 * nrow; rw += NT / 32) {
+      const int     dk = rw / nrow, j = ja + (rw - dk * nrow);
+      const double *pl = dk == 0 ? P0 : (dk == 1 ? P1 : P2);
+      if (pl == nullptr) continue;
+      double *dst = xs + dk * PS + (long long)slot(j) * RS;
+      if (j >= 0 && j < n1) {
+        const double *src = pl + (long long)j * n0;
+        for (int i = lane; i < n0; i += 32) cp_async8(dst + soff(i, H), src + i);
+      } else {
+        for (int i = lane; i < n0; i += 32) dst[soff(i, H)] = 0.0;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // w = b + sqrtdiag z (noisy_rhs_id: two roundings) of rows [jz0, jz1), four nodes per generator call
+  auto rhs_rows = [&](int jz0, int jz1) {
+    const int   total = (jz1 - jz0) * qrow;
+    const float rq = 1.0f / (float)qrow;
+    for (int w = threadIdx.x; w < total; w += NT) {
+      const int r = (int)(((float)w + 0.5f) * rq), qi = w - r * qrow, j = jz0 + r, i0 = 4 * qi;
+      double    bv[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (bk && i0 + m < n0) bv[m] = bk[j * n0 + i0 + m];
+      if (na.mode == PMG_NOISE_PHILOX) philox_normal_quad(na.seed, na.call, (uint64_t)((long long)k * n1 + j) * (uint64_t)qrow + (uint64_t)qi, z);
+      else if (na.mode == PMG_NOISE_INJECTED) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (i0 + m < n0) z[m] = tk[j * n0 + i0 + m];
+      }
+      const int cy = cls1(j, n1);
+      double   *d  = zs + r * a.pitch4 + i0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int    cx = cls1(i0 + m, n0);
+        const double sd = (cx == 1 && cy == 1 && cz == 1) ? a.in.sd : cls[(i0 + m < n0 ? cx : 1) + 3 * cy + 9 * cz].sd;
+        d[m]            = na.mode == PMG_NOISE_NONE ? bv[m] : __dadd_rn(__dmul_rn(z[m], sd), bv[m]);
+      }
+    }
+  };
+  // one node through the class table (first / last column of a row)
+  auto node_generic = [&](int i, int j, int jz0) {
+    const Cls &c   = cls[cls1(i, n0) + 3 * cls1(j, n1) + 9 * cz];
+    double     sum = zs[(j - jz0) * a.pitch4 + i];
+    const int  s1 = slot(j), s0 = s1 == 0 ? RR - 1 : s1 - 1, s2 = s1 + 1 == RR ? 0 : s1 + 1;
+    const int  ro[3] = {s0 * RS, s1 * RS, s2 * RS};
+#pragma unroll
+    for (int dk = 0; dk < 3; ++dk)
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) {
+        const double *row = xs + dk * PS + ro[dj];
+#pragma unroll
+        for (int di = 0; di < 3; ++di) {
+          if (dk == 1 && dj == 1 && di == 1) continue;
+          sum = fma(c.nc[9 * dk + 3 * dj + di], row[soff(i + di - 1, H)], sum);
+        }
+      }
+    double      *ctr = xs + PS + ro[1];
+    const int    o   = soff(i, H);
+    const double xn  = fma(c.idiag, sum, __dmul_rn(a.omo, ctr[o]));
+    ctr[o]         = xn;
+    xk[j * n0 + i] = xn;
+  };
+  // two neighbouring nodes of one colour (array indices q0, q0 + 1 of row j, both interior in x or masked out); the class of
+  // the row / plane supplies the coefficients: kernel parameters for the interior class, the table otherwise
+  auto pair = [&](auto itag, const Cls *c, int ci, int j, int q0, int jz0) {
+    constexpr bool IN = decltype(itag)::value;
+    const int      so = ci ? H + 2 : 2, to = ci ? 2 : H + 2, te_off = ci ? 2 : -1; // own-parity array, other-parity array, its third column
+    const int      iA = 2 * q0 + ci, iB = iA + 2;
+    const bool     vA = iA >= 1 && iA <= n0 - 2, vB = iB <= n0 - 2;
+    const double   idiag = IN ? a.in.idiag : c->idiag;
+    const double  *wrow = zs + (j - jz0) * a.pitch4;
+    double         sA = vA ? wrow[iA] : 0.0, sB = vB ? wrow[iB] : 0.0, xoA = 0.0, xoB = 0.0;
+    const int      s1 = slot(j), s0 = s1 == 0 ? RR - 1 : s1 - 1, s2 = s1 + 1 == RR ? 0 : s1 + 1;
+    const int      ro[3] = {s0 * RS, s1 * RS, s2 * RS};
+#pragma unroll
+    for (int dk = 0; dk < 3; ++dk) {
+      double2 s2v[3], t2[3];
+      double  te[3];
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) { // the loads of a plane are issued before its fmas
+        const double *row = xs + dk * PS + ro[dj];
+        s2v[dj] = *reinterpret_cast<const double2 *>(row + so + q0);
+        t2[dj]  = *reinterpret_cast<const double2 *>(row + to + q0);
+        te[dj]  = row[to + q0 + te_off];
+      }
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) {
+        const double wA = ci ? t2[dj].x : te[dj], eA = ci ? t2[dj].y : t2[dj].x;
+        const double wB = ci ? t2[dj].y : t2[dj].x, eB = ci ? te[dj] : t2[dj].y;
+        const double n0c = IN ? a.in.nc[9 * dk + 3 * dj] : c->nc[9 * dk + 3 * dj], n1c = IN ? a.in.nc[9 * dk + 3 * dj + 1] : c->nc[9 * dk + 3 * dj + 1],
+                     n2c = IN ? a.in.nc[9 * dk + 3 * dj + 2] : c->nc[9 * dk + 3 * dj + 2];
+        sA = fma(n0c, wA, sA);
+        sB = fma(n0c, wB, sB);
+        if (dk == 1 && dj == 1) {
+          xoA = s2v[dj].x;
+          xoB = s2v[dj].y;
+        } else {
+          sA = fma(n1c, s2v[dj].x, sA);
+          sB = fma(n1c, s2v[dj].y, sB);
+        }
+        sA = fma(n2c, eA, sA);
+        sB = fma(n2c, eB, sB);
+      }
+    }
+    const double xnA = fma(idiag, sA, __dmul_rn(a.omo, xoA)), xnB = fma(idiag, sB, __dmul_rn(a.omo, xoB));
+    double      *ctr = xs + PS + ro[1] + so + q0;
+    if (vA) {
+      ctr[0]          = xnA;
+      xk[j * n0 + iA] = xnA;
+    }
+    if (vB) {
+      ctr[1]          = xnB;
+      xk[j * n0 + iB] = xnB;
+    }
+  };
+  // one colour phase: column parity ci on rows ja, ja+2, ... < jb.  Work list: the pairs of every row, then the first / last
+  // column of the rows as items of their own
+  auto phase = [&](int ci, int ja, int jb, int jz0) {
+    const int   nr = jb > ja ? (jb - ja + 1) / 2 : 0;
+    const int   nq = ci == 0 ? ne : no, np2 = (nq + 1) >> 1;
+    const int   nb = (ci == 0 ? 1 : 0) + ((((n0 - 1) & 1) == ci && n0 > 1) ? 1 : 0); // boundary columns 0 and / or n0 - 1
+    const int   tot_pairs = nr * np2, first_b = (tot_pairs + 31) & ~31, total = first_b + nr * nb; // the boundary items start a warp of their own:
+    const float rnp = 1.0f / (float)max(np2, 1);                                                   // a warp that ran both paths would hold up the phase
+    for (int w = threadIdx.x; w < total; w += NT) {
+      if (w >= tot_pairs && w < first_b) continue;
+      if (w < tot_pairs) {
+        const int r = (int)(((float)w + 0.5f) * rnp), p = w - r * np2;
+        const int j = ja + 2 * r, cy = cls1(j, n1);
+        if (cy == 1 && cz == 1) pair(std::true_type{}, nullptr, ci, j, 2 * p, jz0);
+        else pair(std::false_type{}, cls + 1 + 3 * cy + 9 * cz, ci, j, 2 * p, jz0);
+      } else {
+        const int q = w - first_b, r = nb == 2 ? q >> 1 : q;
+        const int i = (ci == 0 && q - r * nb == 0) ? 0 : n0 - 1, j = ja + 2 * r;
+        node_generic(i, j, jz0);
+      }
+    }
+    __syncthreads();
+  };
+
+  prefetch(-1, 2 * R + 2); // rows -1 .. 2R+1 of block 0
+  for (int m = 0;; ++m) {
+    const int lo = 2 * R * m, hi = 2 * R * (m + 1);
+    if (lo >= n1 + 1) break;
+    const int jz0 = backward ? lo : (m == 0 ? 0 : lo + 1), jz1 = backward ? min(hi, n1) : min(hi + 1, n1);
+    if (jz1 <= jz0) break;
+    rhs_rows(jz0, jz1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    prefetch(hi + 2, hi + 2 * R + 2); // what block m+1 reads beyond this block's rows; the ring rows it overwrites are those of rows < lo-1
+    if (!backward) {
+      const int aa = m == 0 ? 0 : lo + 2, ab = min(hi + 1, n1); // even rows
+      const int ba = lo + 1, bb = min(hi, n1);                  // odd rows
+      phase(0, aa, ab, jz0);
+      phase(1, aa, ab, jz0);
+      phase(0, ba, bb, jz0);
+      phase(1, ba, bb, jz0);
+    } else {
+      const int ba = lo + 1, bb = min(hi, n1); // odd rows
+      const int aa = lo, ab = min(hi, n1);     // even rows of [lo, hi)
+      phase(1, ba, bb, jz0);
+      phase(0, ba, bb, jz0);
+      phase(1, aa, ab, jz0);
+      phase(0, aa, ab, jz0);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // out = b - A x (RES) or A x on one plane per CTA; rows of the plane in blocks, unit-stride accesses

@@ -2099,12 +2099,52 @@ struct BoxOp final : GridOp {
     const int nt = box3_nt();
     const int np = (int)((g.n0 + 1) / 2);
     static const int r_env = std::getenv("PMG_BOX3_R") ? std::atoi(std::getenv("PMG_BOX3_R")) : 0;
+    const int        dv = ctx->device & 15;
+    // staged variant (rows of three planes in shared memory, de-interleaved by column parity): a thread owns two nodes, so a block
+    // of R even rows keeps nt threads busy when R * ceil(np / 2) is about nt; R is bounded by the shared memory of one SM
+    box3d::SmemGeom sg{0, 0};
+    size_t          sm = 0;
+    bool            staged = !std::getenv("PMG_BOX3_NO_SMEM") && g.n0 >= 5;
+    if (staged) {
+      sg.H  = (int)((((g.n0 + 1) / 2 + 1) & ~(int64_t)1) + 4);
+      a.R   = r_env > 0 ? r_env : std::max(1, std::min(16, nt / ((np + 1) / 2)));
+      auto need = [&](int R) { return sizeof(box3d::Tab) + ((size_t)(2 * R + 1) * a.pitch4 + (size_t)3 * (4 * R + 3) * 2 * sg.H) * sizeof(double); };
+      while (a.R > 1 && need(a.R) > 224 * 1024) --a.R;
+      sm     = need(a.R);
+      sg.RR  = 4 * a.R + 3;
+      staged = sm <= 224 * 1024;
+    }
+    if (staged) {
+      auto kern = nt == 1024 ? box3d::box3_sweep_smem_kernel<1024> : (nt == 256 ? box3d::box3_sweep_smem_kernel<256> : box3d::box3_sweep_smem_kernel<512>);
+      static size_t sms_set[16] = {0};
+      if (sm > sms_set[dv]) {
+        PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+        sms_set[dv] = std::max<size_t>(sm, 48 * 1024);
+      }
+      bool dirty[2] = {true, true}; // ghost planes: see below
+      for (int s = 0; s < 2; ++s) {
+        const int kp = dir == PMG_SOR_FORWARD_SWEEP ? s : 1 - s;
+        if (dirty[1 - kp]) {
+          PMG_TRY(halo(y));
+          dirty[0] = dirty[1] = false;
+        }
+        dirty[kp] = true;
+        const int64_t first = g.slo + ((kp ^ g.slo) & 1);
+        const int64_t np_k  = first < g.shi ? (g.shi - first + 1) / 2 : 0;
+        if (np_k > 0) {
+          kern<<<(unsigned)np_k, nt, sm, ctx->stream>>>(a, kp, dir == PMG_SOR_FORWARD_SWEEP ? 0 : 1, na, sg);
+          PMG_CUDA(cudaGetLastError());
+          ctx->launches++;
+        }
+      }
+      ctx->dof_updates += g.nl;
+      return 0;
+    }
     a.R = r_env > 0 ? r_env : std::max(1, std::min(16, nt / np));
-    const size_t sm = sizeof(box3d::Tab) + (size_t)(2 * a.R + 1) * a.pitch4 * sizeof(double);
+    sm  = sizeof(box3d::Tab) + (size_t)(2 * a.R + 1) * a.pitch4 * sizeof(double);
     if (sm > 200 * 1024) PMG_FAIL(PMG_ERR_SUP, "27-point plane sweep: grid rows of %lld nodes do not fit the shared-memory staging", (long long)g.n0);
     auto kern = nt == 1024 ? box3d::box3_sweep_kernel<1024> : (nt == 256 ? box3d::box3_sweep_kernel<256> : box3d::box3_sweep_kernel<512>);
     static size_t sm_set[16] = {0};
-    const int     dv = ctx->device & 15;
     if (sm > sm_set[dv]) {
       PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
       sm_set[dv] = std::max<size_t>(sm, 48 * 1024);

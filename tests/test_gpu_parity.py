@@ -1343,10 +1343,12 @@ def test_box3_plane_sweep_and_residual_are_bit_identical(pmg, ctx, dims, levels,
     n = dims[0] * dims[1] * dims[2]
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
     out = []
-    for plane in (True, False):
-        if plane:
-            monkeypatch.delenv("PMG_NO_BOX3", raising=False)
-        else:
+    for path in ("staged", "plane", "colour"):  # rows staged in shared memory (default) | plain loads | one launch per colour
+        monkeypatch.delenv("PMG_NO_BOX3", raising=False)
+        monkeypatch.delenv("PMG_BOX3_NO_SMEM", raising=False)
+        if path == "plane":
+            monkeypatch.setenv("PMG_BOX3_NO_SMEM", "1")
+        elif path == "colour":
             monkeypatch.setenv("PMG_NO_BOX3", "1")
             monkeypatch.setenv("PMG_NO_BOX_PAIR", "1")
         lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.8)
@@ -1362,11 +1364,12 @@ def test_box3_plane_sweep_and_residual_are_bit_identical(pmg, ctx, dims, levels,
         y = y0.copy()
         pc.apply_richardson(b, y, its=2)
         out.append((y, pc.last_stats()["launches"]))
-    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
-    assert out[0][1] < out[1][1]
+    assert np.array_equal(out[0][0], out[2][0]), relerr(out[0][0], out[2][0])
+    assert np.array_equal(out[1][0], out[2][0]), relerr(out[1][0], out[2][0])
+    assert out[0][1] < out[2][1] and out[1][1] < out[2][1]
 
 
-@pytest.mark.parametrize("dims", [(1025, 14, 5), (257, 22, 7), (33, 70, 9)])
+@pytest.mark.parametrize("dims", [(1025, 14, 5), (257, 22, 7), (33, 70, 9), (61, 30, 9), (2049, 10, 5)])
 def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims, monkeypatch):
     """The number of grid rows per block follows from the row length (level 1 of these grids: 513 nodes -> 1 even row per
     block, 129 -> 7, 17 -> 16): the result must equal the per-colour path for all of them, symmetric sweeps included."""
@@ -1374,10 +1377,12 @@ def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims
     n = dims[0] * dims[1] * dims[2]
     b, y0 = rng.standard_normal(n), rng.standard_normal(n)
     out = []
-    for plane in (True, False):
-        if plane:
-            monkeypatch.delenv("PMG_NO_BOX3", raising=False)
-        else:
+    for path in ("staged", "plane", "colour"):
+        monkeypatch.delenv("PMG_NO_BOX3", raising=False)
+        monkeypatch.delenv("PMG_BOX3_NO_SMEM", raising=False)
+        if path == "plane":
+            monkeypatch.setenv("PMG_BOX3_NO_SMEM", "1")
+        elif path == "colour":
             monkeypatch.setenv("PMG_NO_BOX3", "1")
             monkeypatch.setenv("PMG_NO_BOX_PAIR", "1")
         lap = pmg.Mat.laplace(ctx, 3, *dims, kappa=0.8)
@@ -1390,7 +1395,8 @@ def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims
         y = y0.copy()
         pc.apply_richardson(b, y, its=1)
         out.append(y)
-    assert np.array_equal(out[0], out[1]), relerr(out[0], out[1])
+    assert np.array_equal(out[0], out[2]), relerr(out[0], out[2])
+    assert np.array_equal(out[1], out[2]), relerr(out[1], out[2])
 
 
 @pytest.mark.parametrize("dims,levels,extra", [
