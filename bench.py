@@ -545,8 +545,19 @@ def run_b200(args):
         barrier()
         ms3 = max_over_ranks(e0.elapsed_time(e1) / 20)
         ach3 = bpu * mat3.n / (ms3 * 1e-3) / 1e9
-        gibbs3d = {"workload": f"3D 7-point {n3}^3 per GPU, fused red-black sweep (sweep3d_kernel), sorgibbs (omega = 1)", "sweep_ms": ms3, "dof_updates_per_s": world * mat3.n / (ms3 * 1e-3),
+        gibbs3d = {"workload": f"3D 7-point {n3}^3 per GPU, fused red-black sweep with a right-hand side (sweep3d_kernel, warp-specialised, one CTA per tile), sorgibbs (omega = 1)", "sweep_ms": ms3, "dof_updates_per_s": world * mat3.n / (ms3 * 1e-3),
                    "roofline": {"bound": "hbm", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak, "frac_of_nominal_8TBs": ach3 / 8000.0, "algorithmic_bytes_per_dof_update": bpu}}
+        # prior sampling (b = NULL: nothing to read but the iterate): the persistent warp-specialised kernel (sweep3d_ws.cuh), 16 B / update
+        if world == 1:
+            g3.apply_richardson_dev(None, y3, its=3)
+            e0.record(stream)
+            g3.apply_richardson_dev(None, y3, its=20)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms3n = e0.elapsed_time(e1) / 20
+            ach3n = 16.0 * mat3.n / (ms3n * 1e-3) / 1e9
+            gibbs3d["no_rhs"] = {"workload": "the same sweep with b = NULL (prior sampling; sweep3d_ws_kernel, persistent)", "sweep_ms": ms3n, "dof_updates_per_s": mat3.n / (ms3n * 1e-3),
+                                 "roofline": {"bound": "hbm", "achieved": ach3n, "peak": peak, "unit": "GB/s", "frac": ach3n / peak, "algorithmic_bytes_per_dof_update": 16.0}}
         del g3, mat3, y3, b3
 
     # ---- config 4: MGMC V-cycle on a 3D grid, 513 x 513 x (512 N + 1), z-slabs, dense Cholesky coarsest ----
@@ -571,12 +582,21 @@ def run_b200(args):
             m3.apply_richardson_dev(bm, ym, its=2)
             barrier()
             e0.record(stream)
-            m3.apply_richardson_dev(bm, ym, its=8)
+            its3 = 16  # one call: the layout copies of b and y (odd row length -> pitched copies) are paid once per call
+            m3.apply_richardson_dev(bm, ym, its=its3)
             e1.record(stream)
             barrier()
-            msm = max_over_ranks(e0.elapsed_time(e1)) / 8
+            msm = max_over_ranks(e0.elapsed_time(e1)) / its3
+            # bytes per sample and fine DOF: SURVEY 8(d)'s literal form at omega = 1 (K3 24 + 2 K1 24 + K3 24 + K4 9 + K5 17 + 2 K6 24 = 170) and
+            # the compulsory traffic of the passes this implementation runs (2 sweeps 24 + residual 24 + restriction 9 + prolongation 17 = 98),
+            # both times the level series 8/7
+            ndof = float(matm.n)
+            sv, cp = 170.0 * ndof * 8.0 / 7.0, 98.0 * ndof * 8.0 / 7.0
             mgmc3d = {"workload": f"3D 7-point {nm}x{nm}x{nzm} ({nm}x{nm}x{nm - 1 if world > 1 else nm} per GPU), PCGAMGMC V(1,1), {lv3} levels, SOR-Gibbs smoother, dense Cholesky coarsest ({d[0]}x{d[1]}x{d[2]})",
-                      "ms_per_sample": msm, "samples_per_s": 1e3 / msm, "slab_samples_per_s": world * 1e3 / msm, "launches_per_sample": m3.last_stats()["launches"] / 8}
+                      "ms_per_sample": msm, "samples_per_s": 1e3 / msm, "slab_samples_per_s": world * 1e3 / msm, "launches_per_sample": m3.last_stats()["launches"] / its3, "samples_per_call": its3,
+                      "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "survey_bytes_per_sample": sv, "survey_GBs": sv / (msm * 1e-3) / 1e9, "survey_frac": sv / (msm * 1e-3) / 1e9 / peak,
+                                   "compulsory_bytes_per_sample": cp, "compulsory_GBs": cp / (msm * 1e-3) / 1e9, "compulsory_frac": cp / (msm * 1e-3) / 1e9 / peak,
+                                   "note": "per GPU; survey = SURVEY 8(d) literal per-pass byte counts, compulsory = what the passes of this implementation must move"}}
             del m3, matm, ym, bm
         except Exception as e:
             mgmc3d = {"error": repr(e)}
@@ -618,7 +638,8 @@ def run_b200(args):
         out = {"metric": "mgmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": workload_config(args, world), "samples_per_step": S,
-               "impl_notes": {"parallelism": f"row-slab x{world}, NCCL halo" if world > 1 else "single GPU", "noise": "device Philox4x32-10 + Box-Muller, keyed on the global index",
+               "impl_notes": {"parallelism": (f"row-slab x{world}, ghost rows through peer memory over NVLink (CUDA IPC mailboxes, one kernel per exchange); NCCL for the gather of replicated levels"
+                                               if ctx.comm_p2p() else f"row-slab x{world}, NCCL send/recv halo") if world > 1 else "single GPU", "noise": "device Philox4x32-10 + Box-Muller, keyed on the global index",
                               "sweep_order": "red-black on the fine level, four-colour on the Galerkin levels", "unit_of_work": "one sample of one 4097^2-DOF slab (a sample of the N-slab grid counts N)"},
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(8 * nloc), "d2h_bytes_per_step": int(8 * nloc),
                        "note": "per step: H2D of the chain state y from pinned memory, S samples, D2H of y; b = NULL (zero right-hand side, never uploaded)"},

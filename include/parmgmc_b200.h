@@ -78,6 +78,10 @@ int pmg_ctx_set_draw_counter(pmg_ctx ctx, uint64_t draws); /* (y, seed, draw cou
 int pmg_comm_unique_id(unsigned char id[128]);
 int pmg_ctx_comm_init(pmg_ctx ctx, int rank, int nranks, const unsigned char id[128]);
 int pmg_ctx_comm_rank(pmg_ctx ctx, int *rank, int *nranks);
+/* 1: the ghost exchange of slab-partitioned grid operators (the per-colour VecScatter of src/mc_sor.c:318-319, :345-346) runs
+ * through peer memory over NVLink (mailboxes mapped with CUDA IPC at pmg_ctx_comm_init); 0: through ncclSend / ncclRecv
+ * (environment PMG_NO_P2P, or no peer access between the neighbours' devices) */
+int pmg_ctx_comm_p2p(pmg_ctx ctx, int *enabled);
 
 /* ---- operators -------------------------------------------------------------------------------
  * pmg_mat_create_csr: what the shim gets from MatSeqAIJGetCSRAndMemType (src/mc_sor.c:142,250);

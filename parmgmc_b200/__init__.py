@@ -61,6 +61,7 @@ SIGNATURES = {
     "pmg_comm_unique_id": (C.c_int, [C.c_char_p]),
     "pmg_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
     "pmg_ctx_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pmg_ctx_comm_p2p": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pmg_mat_create_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _f64p, C.POINTER(_vp)]),
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
@@ -202,6 +203,12 @@ class Context:
 
     def comm_init(self, rank: int, nranks: int, unique_id: bytes):
         _check(lib().pmg_ctx_comm_init(self._h, rank, nranks, unique_id))
+
+    def comm_p2p(self) -> bool:
+        """True when the slab halo exchange runs through peer memory (CUDA IPC mailboxes), False when through NCCL."""
+        on = C.c_int()
+        _check(lib().pmg_ctx_comm_p2p(self._h, C.byref(on)))
+        return bool(on.value)
 
     def normal_fill(self, seed, call, row0, n):
         z = np.empty(n, np.float64)

@@ -127,6 +127,12 @@ struct pmg_ctx_s {
   void        *nccl_comm  = nullptr;
   int          rank = 0, nranks = 1;
   cudaStream_t comm_stream = nullptr;
+  // peer-memory halo exchange (comm.cu): this rank's mailbox, the neighbours' mailboxes mapped through CUDA IPC, and the
+  // exchange counters per channel (0: compute stream, 1: communication stream) and side (0: rank-1, 1: rank+1)
+  void              *p2p_base    = nullptr;
+  void              *p2p_peer[2] = {nullptr, nullptr};
+  unsigned long long p2p_seq[2][2] = {{0, 0}, {0, 0}}, p2p_ctas[2] = {0, 0};
+  bool               p2p_ok = false;
   // measurement
   int64_t launches = 0, dof_updates = 0;
   // objects created on a context keep it alive: pmg_ctx_destroy only drops the caller's reference
@@ -134,6 +140,7 @@ struct pmg_ctx_s {
 };
 void pmg_ctx_retain(pmg_ctx ctx);
 void pmg_ctx_release(pmg_ctx ctx);
+void comm_p2p_teardown(pmg_ctx ctx); // comm.cu
 
 // One N(0,1) block: what a single VecSetRandomStandardNormal call (src/parmgmc.c:70-116) produces.
 struct NoiseArgs {

@@ -52,6 +52,7 @@ void pmg_ctx_release(pmg_ctx ctx)
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  comm_p2p_teardown(ctx);
   delete ctx;
 }
 

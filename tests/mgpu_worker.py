@@ -143,6 +143,8 @@ def main():
     uid = [pmg.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
+    if rank == 0:
+        print(f"[mgpu] slab halo exchange: {'peer memory (CUDA IPC mailboxes)' if ctx.comm_p2p() else 'NCCL send/recv'}", flush=True)
     names = sys.argv[1:] or sorted(CASES)
     failed = []
     for name in names:
