@@ -1,6 +1,7 @@
 // common.hpp -- internal types of the B200 sampling library (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; a no-op unless a profiler injects itself
 
 #include <cstdarg>
 #include <cstdint>
@@ -137,6 +138,15 @@ struct pmg_ctx_s {
   int64_t launches = 0, dof_updates = 0;
   // objects created on a context keep it alive: pmg_ctx_destroy only drops the caller's reference
   int refs = 1;
+};
+// The reference's two PetscLogEvents as NVTX ranges under the same names: "MulticolSOR" around MCSORApply
+// (src/mc_sor.c:221,237) and "VecSetRandN" around the generator fill (src/parmgmc.c:76,114; here the fill is fused into the
+// sweep kernels, so the range brackets the stand-alone fills only).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
 };
 void pmg_ctx_retain(pmg_ctx ctx);
 void pmg_ctx_release(pmg_ctx ctx);

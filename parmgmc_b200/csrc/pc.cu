@@ -291,6 +291,7 @@ struct GibbsCore {
   double lrc_omega_build = 1.0; // the reference builds Bb with a temporary MCSOR at its default omega (src/mc_sor.c:583-593)
   int sample(NoiseStream &ns, const double *b, double *y)
   {
+    NvtxRange range("MulticolSOR");
     PMG_TRY(ensure());
     if (LrcData *lrc = op->lrc_data()) {
       if (type == PMG_SOR_SYMMETRIC_SWEEP) {
@@ -605,7 +606,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     auto      smooth = [&]() -> int {
       for (int d : dirs) {
         PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
-        PMG_TRY(v.op->stream_sweep(d, v.smp.gibbs.coeffs, b, v.x.p, v.x2.p, na));
+        { NvtxRange range("MulticolSOR"); PMG_TRY(v.op->stream_sweep(d, v.smp.gibbs.coeffs, b, v.x.p, v.x2.p, na)); }
         std::swap(v.x, v.x2);
       }
       return 0;
@@ -632,7 +633,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
     auto      smooth = [&]() -> int {
       for (int d : dirs) {
         PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
-        PMG_TRY(v.op->fused_sweep(d, v.smp.gibbs.coeffs, b, cur, oth, na, nullptr, nullptr, nullptr));
+        { NvtxRange range("MulticolSOR"); PMG_TRY(v.op->fused_sweep(d, v.smp.gibbs.coeffs, b, cur, oth, na, nullptr, nullptr, nullptr)); }
         std::swap(cur, oth);
       }
       return 0;
@@ -681,7 +682,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
       const double nn = (double)v.op->n(), k1 = v.smp.gibbs.omega == 1.0 ? 24.0 : 32.0;
       PMG_TRY(prof_begin(pc, "L" + std::to_string(l) + (last ? " pre-sample+residual+restrict" : " sweep"), nn * ((b ? 8 : 0) + (xin ? 8 : 0) + 8 + (last ? 2 : 0)), nn * (k1 + (last ? 34 : 0))));
     }
-    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, xin, oth, na, c.op, nullptr, last ? c.b.p : nullptr));
+    { NvtxRange range("MulticolSOR"); PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, xin, oth, na, c.op, nullptr, last ? c.b.p : nullptr)); }
     PMG_TRY(prof_end(pc));
     std::swap(cur, oth);
   }
@@ -695,7 +696,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
       const double nn = (double)v.op->n(), k1 = v.smp.gibbs.omega == 1.0 ? 24.0 : 32.0;
       PMG_TRY(prof_begin(pc, "L" + std::to_string(l) + (s == 0 ? " prolong+post-sample" : " sweep"), nn * ((b ? 8 : 0) + 8 + 8 + (s == 0 ? 2 : 0)), nn * (k1 + (s == 0 ? 18 : 0))));
     }
-    PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? pc->lv[l - 1].x.p : nullptr, nullptr));
+    { NvtxRange range("MulticolSOR"); PMG_TRY(v.op->fused_sweep(dirs[s], v.smp.gibbs.coeffs, b, cur, oth, na, c.op, s == 0 ? pc->lv[l - 1].x.p : nullptr, nullptr)); }
     PMG_TRY(prof_end(pc));
     std::swap(cur, oth);
   }
@@ -1081,7 +1082,7 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
       for (int64_t it = 0; it < its; ++it) {
         for (int d : dirs) {
           PMG_TRY(pc->noise.next(ctx, n, op->row0(), na));
-          PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, pb, cur, oth, na, nullptr, nullptr, nullptr));
+          { NvtxRange range("MulticolSOR"); PMG_TRY(op->fused_sweep(d, pc->smp.gibbs.coeffs, pb, cur, oth, na, nullptr, nullptr, nullptr)); }
           std::swap(cur, oth);
         }
         if (pc->cb || pc->qoi.on || it + 1 == its) {
@@ -1606,6 +1607,7 @@ int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int
   DevBuf<double> d;
   PMG_TRY(d.alloc((size_t)n));
   NoiseArgs na{PMG_NOISE_PHILOX, nullptr, seed, call, row0};
+  NvtxRange range("VecSetRandN");
   PMG_TRY(launch_normal_fill(ctx, na, n, d.p));
   PMG_CUDA(cudaMemcpyAsync(z, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));

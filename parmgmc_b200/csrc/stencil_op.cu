@@ -1311,10 +1311,10 @@ struct LapOp final : GridOp {
     using namespace sweep3d;
     auto         kern = sweep3d_kernel<NOISE, NW, SX, SB, MINB, WS>;
     const size_t sm   = Smem<NW, SX, SB, WS>::total;
-    static bool  attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[16] = {false}; // per device: function attributes belong to the device's context
+    if (!attr_set[ctx->device & 15]) {
       PMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      attr_set = true;
+      attr_set[ctx->device & 15] = true;
     }
     static const bool swz = std::getenv("PMG_SW3_PLAIN") == nullptr; // SWIZZLE_32B boxes: conflict-free shared-memory reads
     a.swizzle = swz ? 1 : 0;
@@ -2704,7 +2704,8 @@ int grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSa
   for (int q = 0; q < nns; ++q) a.ns[q] = ns[q];
   // one cluster of up to 8 CTAs x 1024 threads; small tails run in fewer CTAs (a barrier between fewer SMs is cheaper)
   const int64_t big = a.lv[nlev - 1].g.nl;
-  static int cl_max = 0; // 16 CTAs per cluster where the device allows it (non-portable size), else the portable 8
+  static int cl_max_dev[16] = {0}; // per device: 16 CTAs per cluster where the device allows it (non-portable size), else the portable 8
+  int       &cl_max = cl_max_dev[ctx->device & 15];
   if (!cl_max) {
     cl_max = 8;
     bool ok = cudaFuncSetAttribute(grid_tail_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess && cudaFuncSetAttribute(grid_tail_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
