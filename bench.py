@@ -18,6 +18,7 @@ One JSON line.  Beyond the contract's keys:
                     passes the kernel replaces (K1 = 24 B at omega = 1), which fusion can exceed
   roofline_vcycle   the whole sample: sum over launches of the byte table / ms_per_sample / peak (table in DESIGN.md section 3)
   kernels           the profile itself (share, GB/s per kernel)
+  multi_chain       N = 1: throughput of 4 independent chains of the headline sampler sharing the GPU (informational; `value` is ONE chain)
   gibbs2d, gibbs3d  stand-alone fused red-black sweeps (K1, 24 B / DOF-update at omega = 1), 4097^2 and 512^3 per GPU
   csr_sweep         K2: assembled 7-point 256^3 operator, SELL colour sweep (N = 1)
   mgmc3d            config 4's V-cycle: 513 x 513 x (512 N + 1), z-slabs
@@ -601,6 +602,50 @@ def run_b200(args):
         except Exception as e:
             mgmc3d = {"error": repr(e)}
 
+    # ---- independent chains on one GPU (what the reference arm does with its CPU cores): one stream, one context and one host
+    # ---- thread per chain; the launch-latency-bound small levels of one chain run beside the other chains' kernels.  Reported
+    # ---- beside the headline, which stays ONE chain ----
+    multi_chain = None
+    if world == 1 and not args.no_multi_chain:
+        try:
+            import threading
+            chains = []
+            for c in range(args.chains):
+                st = torch.cuda.Stream()
+                cx = pmg.Context(local, stream=st.cuda_stream, seed=0xCAFE + 1 + c)
+                mt = pmg.Mat.laplace(cx, 2, nx, ny, 1, args.kappa)
+                p2 = pmg.PC(cx, "gamgmc")
+                p2.set_operator(mt)
+                p2.set_options({"-gamgmc_pc_mg_levels": args.levels, "-pc_b200_noise": "philox"})
+                p2.setup()
+                yc = torch.zeros(mt.n, dtype=torch.float64, device="cuda")
+                p2.apply_richardson_dev(None, yc, its=3)
+                chains.append((st, cx, mt, p2, yc))
+            torch.cuda.synchronize()
+            ncall = 4
+
+            def _work(ch):
+                for _ in range(ncall):
+                    ch[3].apply_richardson_dev(None, ch[4], its=S)
+
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            th = [threading.Thread(target=_work, args=(ch,)) for ch in chains]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            eb.record()
+            torch.cuda.synchronize()
+            msc = ea.elapsed_time(eb)
+            tot = args.chains * S * ncall
+            multi_chain = {"workload": f"{args.chains} independent chains of the headline sampler on one GPU (one stream and one host thread each), {S} samples per call, {ncall} calls per chain",
+                           "chains": args.chains, "samples": tot, "ms": msc, "samples_per_s": 1e3 * tot / msc, "ms_per_sample": msc / tot, "vs_one_chain": (1e3 * tot / msc) / value}
+            del chains
+        except Exception as e:
+            multi_chain = {"error": repr(e)}
+
     # ---- K2: assembled-operator path, SELL colour sweep on the 7-point 256^3 operator (N = 1) ----
     csr_sweep = None
     if world == 1 and not args.no_csr:
@@ -653,6 +698,8 @@ def run_b200(args):
             out["mgmc3d"] = mgmc3d
         if csr_sweep is not None:
             out["csr_sweep"] = csr_sweep
+        if multi_chain is not None:
+            out["multi_chain"] = multi_chain
         if parity is not None:
             out["parity_check"] = parity
         if cpu is not None:
@@ -704,6 +751,8 @@ def main():
     ap.add_argument("--no-gibbs3d", action="store_true", help="skip the 3D 7-point sweep measurement")
     ap.add_argument("--no-mgmc3d", action="store_true", help="skip the 3D V-cycle measurement")
     ap.add_argument("--no-csr", action="store_true", help="skip the assembled-operator (K2) measurement")
+    ap.add_argument("--no-multi-chain", action="store_true", help="skip the concurrent-chains measurement (N = 1)")
+    ap.add_argument("--chains", type=int, default=4, help="independent chains of the concurrent-chains measurement")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the multi-GPU parity check (N > 1)")
     ap.add_argument("--cpu-samples", type=int, default=4)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the MPIAIJ-emulation CPU baseline (0: all host cores)")
