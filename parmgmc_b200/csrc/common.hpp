@@ -414,4 +414,21 @@ bool grid_tail_smem_fits(int nlev, LevelOp *const *ops, int64_t chol_n); // leve
 int  grid_tail_cycle(pmg_ctx ctx, int nlev, const TailLevelSpec *lv, const CholSampler &chol, int noise_mode, uint64_t seed, const TailNoise *ns, int nns);
 
 int launch_normal_fill(pmg_ctx ctx, const NoiseArgs &na, int64_t n, double *z_dev);
+// Batched fill of the noise blocks of several 2D levels in ONE launch (csr_op.cu): segment s is the block `call` of an nx x ny
+// level whose generator index space is padded to `pitch` columns (philox.cuh); the values land in natural layout (row stride nx)
+// and are, bit for bit, the ones the sweep kernels would generate on the fly.
+struct PrefillSeg {
+  double  *dst;
+  int      nx, ny, pitch;
+  uint64_t call;
+  int64_t  q0; // first quad of the segment in the launch's work list
+};
+constexpr int PREFILL_MAX = 24;
+struct PrefillArgs {
+  int        nseg;
+  int64_t    total; // quads of all segments
+  uint64_t   seed;
+  PrefillSeg seg[PREFILL_MAX];
+};
+int launch_noise_prefill(pmg_ctx ctx, const PrefillArgs &a);
 int launch_axpy(pmg_ctx ctx, int64_t n, double a, const double *x, double *y); // y += a x

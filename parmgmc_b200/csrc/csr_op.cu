@@ -733,6 +733,34 @@ int launch_normal_fill(pmg_ctx ctx, const NoiseArgs &na, int64_t n, double *z_de
   return 0;
 }
 
+// one thread = one generator call = four consecutive padded columns of one grid row of one segment
+__global__ void __launch_bounds__(256) noise_prefill_kernel(const __grid_constant__ PrefillArgs a)
+{
+  pdl_launch_dependents();
+  pdl_wait(); // the buffers were read by the sweeps of the sample before
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < a.total; q += (int64_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (s + 1 < a.nseg && q >= a.seg[s + 1].q0) ++s;
+    const int64_t ql   = q - a.seg[s].q0; // = (j * pitch + c) >> 2: the quad index of box2d.cuh's noise_row
+    const int     qrow = a.seg[s].pitch >> 2, nx = a.seg[s].nx;
+    const int     j = (int)(ql / qrow), c = 4 * (int)(ql - (int64_t)j * qrow);
+    double        z[4];
+    philox_normal_quad(a.seed, a.seg[s].call, (uint64_t)ql, z);
+    double *d = a.seg[s].dst + (int64_t)j * nx + c;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (c + m < nx) d[m] = z[m];
+  }
+}
+int launch_noise_prefill(pmg_ctx ctx, const PrefillArgs &a)
+{
+  if (a.total == 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>((a.total + 255) / 256, (int64_t)ctx->sm_count * 8);
+  PMG_CUDA(launch_pdl(ctx->stream, noise_prefill_kernel, dim3(grid), dim3(256), 0, a));
+  ctx->launches++;
+  return 0;
+}
+
 __global__ void axpy_kernel(int64_t n, double a, const double *__restrict__ x, double *__restrict__ y)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -370,6 +370,24 @@ struct pmg_pc_s {
   std::vector<MgLevel> lv;
   DevBuf<double>       w, work;
   bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
+  // Noise of the 9-point levels ahead of their sweeps (one device, Philox): those levels' one-pass kernels are bound by the
+  // latency of a band step, half of which is the generator; ONE batched launch at the start of a sample writes the normals of
+  // all their sweeps (launch_noise_prefill: the same values, bit for bit) and the sweeps read them as a tape.  The blocks a
+  // sample draws, and their order, are fixed by the hierarchy: the first sample records (level, pre/post, sweep) -> offset of
+  // the draw counter, the following ones use the record and check it draw by draw.
+  struct NoisePrefill {
+    struct Entry {
+      int            level, post, s;
+      int64_t        k; // draw counter of the block minus the draw counter at the start of the sample
+      int            nx, ny, pitch;
+      DevBuf<double> buf;
+    };
+    std::vector<Entry> entries;
+    bool               recorded = false, recording = false, active = false;
+    uint64_t           draws0 = 0;
+    size_t             cursor = 0;
+    void               reset() { entries.clear(); recorded = recording = active = false; cursor = 0; }
+  } prefill;
   int                  tail_top     = -1;   // levels 0 .. tail_top of the direct cycle run in one launch (mg_tail); -1: none
   // PCWOODBURY (src/woodbury.c): a sampler on the base matrix A of a MATLRC operator + the correction G
   pmg_pc               wb_sampler = nullptr;
@@ -582,6 +600,82 @@ static int sweep_dirs(const LevelSampler &s, std::vector<int> &dirs)
 // PITCHED vectors of LevelOp::fused_size() elements (only the finest level can be one: the caller converts).
 static int mg_tail(pmg_pc pc, int lt);
 
+// ---- noise of the 9-point levels ahead of their sweeps (pmg_pc_s::NoisePrefill) --------------------------------------------
+static bool prefill_wanted(pmg_pc pc)
+{
+  return pc->noise.mode == PMG_NOISE_PHILOX && !pc->noise.parent && pc->ctx->nranks == 1 && !std::getenv("PMG_NO_PREFILL");
+}
+static int prefill_begin(pmg_pc pc)
+{
+  auto &pf = pc->prefill;
+  pf.active = pf.recording = false;
+  if (!prefill_wanted(pc)) return 0;
+  pf.draws0 = pc->ctx->draws;
+  pf.cursor = 0;
+  if (!pf.recorded) {
+    pf.entries.clear();
+    pf.recording = true;
+    return 0;
+  }
+  if (pf.entries.empty()) return 0;
+  PrefillArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.seed = pc->ctx->seed;
+  for (auto &e : pf.entries) {
+    PrefillSeg &sg = a.seg[a.nseg++];
+    sg.dst = e.buf.p; sg.nx = e.nx; sg.ny = e.ny; sg.pitch = e.pitch;
+    sg.call = pf.draws0 + (uint64_t)e.k;
+    sg.q0   = a.total;
+    a.total += (int64_t)(e.pitch >> 2) * e.ny;
+  }
+  PMG_TRY(prof_begin(pc, "noise of the 9-point levels (one launch)", 8.0 * (double)a.total * 4, 0.0));
+  PMG_TRY(launch_noise_prefill(pc->ctx, a));
+  PMG_TRY(prof_end(pc));
+  pf.active = true;
+  return 0;
+}
+// after noise.next() of sweep s (pre: post = 0, post-smoothing: 1) of level l: record the block, or hand the sweep its tape
+static int prefill_hook(pmg_pc pc, int l, int post, int s, LevelOp *op, NoiseArgs &na)
+{
+  auto &pf = pc->prefill;
+  if (pf.recording) {
+    int     dim;
+    int64_t dims[3];
+    if (na.mode != PMG_NOISE_PHILOX || !op->level_pitch || !op->structured(dim, dims) || dim != 2 || (int)pf.entries.size() >= PREFILL_MAX) return 0;
+    pmg_pc_s::NoisePrefill::Entry e;
+    e.level = l; e.post = post; e.s = s;
+    e.k  = (int64_t)(na.call - pf.draws0);
+    e.nx = (int)dims[0]; e.ny = (int)dims[1]; e.pitch = (int)op->level_pitch;
+    pf.entries.push_back(std::move(e));
+    return 0;
+  }
+  if (!pf.active) return 0;
+  if (pf.cursor < pf.entries.size()) {
+    auto &e = pf.entries[pf.cursor];
+    if (e.level == l && e.post == post && e.s == s && na.call == pf.draws0 + (uint64_t)e.k && na.mode == PMG_NOISE_PHILOX) {
+      ++pf.cursor;
+      na.mode = PMG_NOISE_INJECTED;
+      na.tape = e.buf.p;
+      return 0;
+    }
+  }
+  PMG_FAIL(PMG_ERR_NOISE, "gamgmc: the noise blocks of this sample are not the recorded ones (level %d, %s sweep %d): the hierarchy changed without pmg_pc_setup", l, post ? "post" : "pre", s);
+}
+static int prefill_end(pmg_pc pc)
+{
+  auto &pf = pc->prefill;
+  if (pf.recording) {
+    pf.recording = false;
+    for (auto &e : pf.entries) PMG_TRY(e.buf.alloc((size_t)e.nx * (size_t)e.ny));
+    pf.recorded = true;
+  } else if (pf.active && pf.cursor != pf.entries.size()) {
+    pf.active = false;
+    PMG_FAIL(PMG_ERR_NOISE, "gamgmc: %zu of the %zu prefilled noise blocks were not consumed", pf.entries.size() - pf.cursor, pf.entries.size());
+  }
+  pf.active = false;
+  return 0;
+}
+
 static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool zero_guess)
 {
   pmg_ctx  ctx = pc->ctx;
@@ -672,6 +766,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   for (size_t s = 0; s < dirs.size(); ++s) { // pre-smoothing; the last sweep also forms the coarse right-hand side
     const bool last = s + 1 == dirs.size();
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+    if (l < pc->nlevels - 1) PMG_TRY(prefill_hook(pc, l, 0, (int)s, v.op, na));
     const double *xin = (zero_guess && s == 0) ? nullptr : cur;
     if (!xin && !v.op->fused_null_xin_ok()) { // the 3D sweep reads its iterate through the TMA: hand it zeros
       PMG_CUDA(cudaMemsetAsync(cur, 0, (size_t)v.op->fused_size() * sizeof(double), ctx->stream));
@@ -692,6 +787,7 @@ static int mg_cycle_direct(pmg_pc pc, int l, const double *b, double *x, bool ze
   PMG_TRY(v.P->fused_before_prolong(c.x.p));
   for (size_t s = 0; s < dirs.size(); ++s) { // post-smoothing; the first sweep starts from x + P x_c
     PMG_TRY(pc->noise.next(ctx, v.op->n(), v.op->row0(), na));
+    if (l < pc->nlevels - 1) PMG_TRY(prefill_hook(pc, l, 1, (int)s, v.op, na));
     if (pc->prof_on) { // K5 (18) + K1
       const double nn = (double)v.op->n(), k1 = v.smp.gibbs.omega == 1.0 ? 24.0 : 32.0;
       PMG_TRY(prof_begin(pc, "L" + std::to_string(l) + (s == 0 ? " prolong+post-sample" : " sweep"), nn * ((b ? 8 : 0) + 8 + 8 + (s == 0 ? 2 : 0)), nn * (k1 + (s == 0 ? 18 : 0))));
@@ -742,6 +838,7 @@ static int mg_tail(pmg_pc pc, int lt)
 static int gamgmc_setup(pmg_pc pc)
 {
   pmg_ctx  ctx  = pc->ctx;
+  pc->prefill.reset();
   LevelOp *top  = pc->mat->op.get();                      // what the user handed over (possibly A + B S B^T)
   LevelOp *fine = top->lrc_base() ? top->lrc_base() : top; // the hierarchy is built from the base matrix (src/pc_gamgmc.c:296-353)
   // -pc_gamgmc_mg_type (src/pc_gamgmc.c:364): only the geometric hierarchy can be built without PETSc's GAMG
@@ -1024,7 +1121,9 @@ static int richardson_body(pmg_pc pc, const double *b, double *y, int64_t its, i
     }
     for (int64_t it = 0; it < its; ++it) {
       if (top_fused) {
+        PMG_TRY(prefill_begin(pc));
         PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, pc->pit_b.p, pc->pit_y.p, it == 0 && guesszero));
+        PMG_TRY(prefill_end(pc));
         if (pc->cb || pc->qoi.on || it + 1 == its) PMG_TRY(A->from_pitched(pc->pit_y.p, y));
       } else if (pc->direct_cycle) {
         PMG_TRY(mg_cycle_direct(pc, pc->nlevels - 1, b, y, it == 0 && guesszero));

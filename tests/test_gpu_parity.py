@@ -1399,6 +1399,40 @@ def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims
     assert np.array_equal(out[1], out[2]), relerr(out[1], out[2])
 
 
+# ---- noise of the 9-point levels written by ONE batched launch at the start of a sample (pc.cu NoisePrefill) and read by the
+# ---- one-pass kernels as a tape, against generation on the fly inside the kernels (PMG_NO_PREFILL): sample 0 records the blocks,
+# ---- samples 1.. use the record; several sweeps per level, symmetric sweeps, odd / even row lengths, two calls in a row -----------
+@pytest.mark.parametrize("dims,levels,extra", [
+    ((513, 257), 5, {"-pc_b200_tail_max_n": 0}),
+    ((257, 257), 6, {}),
+    ((300, 140), 4, {"-pc_b200_tail_max_n": 0, "-gamgmc_mg_levels_pc_type": "mcgibbs", "-gamgmc_mg_levels_pc_mcgibbs_symmetric": "", "-gamgmc_mg_levels_pc_mcgibbs_omega": 1.4}),
+    ((129, 385), 4, {"-pc_b200_tail_max_n": 0, "-gamgmc_mg_levels_ksp_max_it": 2}),
+])
+def test_prefilled_noise_equals_noise_on_the_fly(pmg, ctx, dims, levels, extra, monkeypatch):
+    rng = np.random.default_rng(SEED)
+    n = dims[0] * dims[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for prefill in (True, False):
+        if prefill:
+            monkeypatch.delenv("PMG_NO_PREFILL", raising=False)
+        else:
+            monkeypatch.setenv("PMG_NO_PREFILL", "1")
+        lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=0.9)
+        pc = pmg.PC(ctx, "gamgmc")
+        pc.set_operator(lap)
+        pc.set_options(dict(extra, **{"-gamgmc_pc_mg_levels": levels, "-pc_b200_noise": "philox"}))
+        pc.setup()
+        ctx.set_seed(77)
+        y = y0.copy()
+        pc.apply_richardson(b, y, its=4)
+        pc.apply_richardson(None, y, its=3)  # the record survives from call to call
+        out.append((y, pc.last_stats()["launches"], ctx.draw_counter))
+    assert np.array_equal(out[0][0], out[1][0]), relerr(out[0][0], out[1][0])
+    assert out[0][2] == out[1][2]
+    assert out[0][1] == out[1][1] + 3  # one more launch per sample that uses the record
+
+
 @pytest.mark.parametrize("dims,levels,extra", [
     ((257, 257), 6, {}),                                    # default sizing: levels 0..3 (65^2 and below) in the shared-memory tail
     ((513, 129), 7, {"-gamgmc_mg_levels_ksp_max_it": 2}),
