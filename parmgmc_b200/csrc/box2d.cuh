@@ -341,6 +341,13 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
   double bPrev[4] = {0, 0, 0, 0};                                          // b row e-2 (MODE_RESTRICT)
   double rP1[4] = {0, 0, 0, 0}, rP2[4] = {0, 0, 0, 0};                     // residual rows e-3, e-4 of the step being done
 
+  // injected noise (a tape in global memory, e.g. the batched prefill of pc.cu) is fetched one step ahead: a load issued in the
+  // step that uses it would put a global-memory latency on every band step
+  double zAn[4] = {0, 0, 0, 0}, zBn[4] = {0, 0, 0, 0};
+  if (NOISE == NOISE_RT) {
+    W.noise_row(e0, zAn);
+    W.noise_row(e0 - 1, zBn);
+  }
   int e = e0;
   for (int t = 0; t < T; ++t, e += 2) {
     const int      s   = t % STAGES;
@@ -365,8 +372,20 @@ __device__ __forceinline__ void run_warp(const Args &a, const fastnormal::Tables
       if (e + 2 <= elast) W.prefetch_coarse(e + 3);
     }
     double zA[4], zB[4];
-    W.noise_row(e, zA);
-    W.noise_row(e - 1, zB);
+    if (NOISE == NOISE_RT) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        zA[m] = zAn[m];
+        zB[m] = zBn[m];
+      }
+      if (t + 1 < T) {
+        W.noise_row(e + 2, zAn);
+        W.noise_row(e + 1, zBn);
+      }
+    } else {
+      W.noise_row(e, zA);
+      W.noise_row(e - 1, zB);
+    }
     W.row_update(e, R0, Rm1, xa, bA, zA);      // A row e: neighbours rows e-1, e+1 old
     W.row_update(e - 1, Rm1, Rm2, R0, bB, zB); // B row e-1: neighbour rows e-2, e final
     if (out_lane) {

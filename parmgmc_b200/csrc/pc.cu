@@ -370,9 +370,9 @@ struct pmg_pc_s {
   std::vector<MgLevel> lv;
   DevBuf<double>       w, work;
   bool                 direct_cycle = true; // cycle applied to (b, y) directly instead of y += MG(b - A y); same map, fewer passes
-  // Noise of the 9-point levels ahead of their sweeps (one device, Philox): those levels' one-pass kernels are bound by the
-  // latency of a band step, half of which is the generator; ONE batched launch at the start of a sample writes the normals of
-  // all their sweeps (launch_noise_prefill: the same values, bit for bit) and the sweeps read them as a tape.  The blocks a
+  // Opt-in (PMG_PREFILL=1; measured slower, see prefill_wanted): noise of the 9-point levels ahead of their sweeps (one device,
+  // Philox).  ONE batched launch at the start of a sample writes the normals of all their sweeps (launch_noise_prefill: the
+  // same values, bit for bit) and the sweeps read them as a tape.  The blocks a
   // sample draws, and their order, are fixed by the hierarchy: the first sample records (level, pre/post, sweep) -> offset of
   // the draw counter, the following ones use the record and check it draw by draw.
   struct NoisePrefill {
@@ -603,7 +603,10 @@ static int mg_tail(pmg_pc pc, int lt);
 // ---- noise of the 9-point levels ahead of their sweeps (pmg_pc_s::NoisePrefill) --------------------------------------------
 static bool prefill_wanted(pmg_pc pc)
 {
-  return pc->noise.mode == PMG_NOISE_PHILOX && !pc->noise.parent && pc->ctx->nranks == 1 && !std::getenv("PMG_NO_PREFILL");
+  // opt-in (PMG_PREFILL=1): measured SLOWER on B200 (4097^2: 0.474 against 0.445 ms per sample) -- the generator work is the same and
+  // in the sweeps it rides in issue slots that the dependent FP64 chain leaves empty anyway, while the batched launch costs
+  // ~25 us of its own; kept as a tested path because it turns any device-generated sample into a replayable tape
+  return pc->noise.mode == PMG_NOISE_PHILOX && !pc->noise.parent && pc->ctx->nranks == 1 && std::getenv("PMG_PREFILL") != nullptr;
 }
 static int prefill_begin(pmg_pc pc)
 {

@@ -1400,7 +1400,7 @@ def test_box3_plane_sweep_block_height_does_not_change_the_result(pmg, ctx, dims
 
 
 # ---- noise of the 9-point levels written by ONE batched launch at the start of a sample (pc.cu NoisePrefill) and read by the
-# ---- one-pass kernels as a tape, against generation on the fly inside the kernels (PMG_NO_PREFILL): sample 0 records the blocks,
+# ---- one-pass kernels as a tape (opt-in, PMG_PREFILL=1), against generation on the fly inside the kernels: sample 0 records the blocks,
 # ---- samples 1.. use the record; several sweeps per level, symmetric sweeps, odd / even row lengths, two calls in a row -----------
 @pytest.mark.parametrize("dims,levels,extra", [
     ((513, 257), 5, {"-pc_b200_tail_max_n": 0}),
@@ -1415,9 +1415,9 @@ def test_prefilled_noise_equals_noise_on_the_fly(pmg, ctx, dims, levels, extra, 
     out = []
     for prefill in (True, False):
         if prefill:
-            monkeypatch.delenv("PMG_NO_PREFILL", raising=False)
+            monkeypatch.setenv("PMG_PREFILL", "1")
         else:
-            monkeypatch.setenv("PMG_NO_PREFILL", "1")
+            monkeypatch.delenv("PMG_PREFILL", raising=False)
         lap = pmg.Mat.laplace(ctx, 2, *dims, kappa=0.9)
         pc = pmg.PC(ctx, "gamgmc")
         pc.set_operator(lap)
