@@ -1063,10 +1063,13 @@ struct GridOp : LevelOp {
   const double *halo_inflight = nullptr;
   virtual int   pitched_halo_on(double *pitched, cudaStream_t s) { (void)pitched; (void)s; return PMG_ERR_SUP; }
   // early exchange of the post-smoother's ghost rows (V-cycle): on unless PMG_NO_EARLY_HALO; split sweep launches: opt-in with
-  // PMG_OVERLAP_SWEEP (measured on 2 x B200, profiles/r2_summary.md: the exchange kernel only gets CTAs when the interior launch
-  // drains, so the split costs more than the exchange it hides)
+  // PMG_OVERLAP_SWEEP (3D; measured on 2 x B200 with NCCL, profiles/r2_summary.md: the exchange kernel only got CTAs when the interior
+  // launch drained, and the boundary tiles were full-height bands launched after it, so the split cost more than it hid)
   static bool   overlap_on() { return std::getenv("PMG_NO_EARLY_HALO") == nullptr; }
   static bool   overlap_sweep_on() { return std::getenv("PMG_OVERLAP_SWEEP") != nullptr; }
+  // 2D fused sweeps: on by default since the boundary rows are thin bands that run on the communication stream behind the exchange
+  // (2 x B200, 4097 x 4096 per GPU: sweep 101.4 -> 97.2 us, V-cycle sample 0.568 -> 0.557 ms); PMG_NO_OVERLAP_SWEEP switches it off
+  bool          overlap_sweep_here() const { return g.dim == 2 ? std::getenv("PMG_NO_OVERLAP_SWEEP") == nullptr : overlap_sweep_on(); }
   int halo_begin(double *v) override
   {
     if (!parallel || !overlap_on() || !ctx->comm_stream) return 0;
@@ -1414,7 +1417,7 @@ struct LapOp final : GridOp {
     split_launch = false;
     if (!parallel) return 0;
     if (halo_inflight == xin && xin) return halo_wait(); // exchanged ahead of time: one launch
-    if (overlap_sweep_on() && ctx->comm_stream) {
+    if (overlap_sweep_here() && overlap_on() && ctx->comm_stream) {
       PMG_TRY(halo_begin(const_cast<double *>(xin)));
       split_launch = true;
       return 0;
@@ -1469,22 +1472,32 @@ struct LapOp final : GridOp {
     for (int s = 0; s < nstrips; ++s) {
       const int  c0 = s * sweep2d::STRIP_OUT - 4;
       const bool edge_strip = !(c0 >= 1 && c0 + 127 <= g.n0 - 2);
-      int64_t    j = g.slo;
-      while (j < g.shi) {
-        const int64_t jb_full = std::min<int64_t>(j + by, g.shi);
+      int64_t    j = g.slo, end = g.shi;
+      // overlapped exchange (start_halo): the rows that read ghost rows are THIN bands of their own, which run on the communication
+      // stream right behind the exchange while the compute stream sweeps everything else
+      const int64_t thin = 8;
+      const bool    thin_on = parallel && overlap_sweep_here() && overlap_on() && g.shi - g.slo >= 4 * thin;
+      if (thin_on && g.slo > 0) {
+        slow.push_back(Item{s, (int)j, (int)(j + thin)});
+        j += thin;
+      }
+      if (thin_on && g.shi < g.n1) end = g.shi - thin;
+      while (j < end) {
+        const int64_t jb_full = std::min<int64_t>(j + by, end);
         const int     lo = restrict_mode ? 4 : 2, hi = restrict_mode ? 2 : 0;
         const bool    interior = !edge_strip && j - lo >= 1 && jb_full + hi <= g.n1 - 2 && j - lo - 1 >= g.slo && jb_full + hi + 2 < g.shi; // sweep2d_kernel's test
         const int64_t h  = interior ? by : std::max(2, (by * 3 / 4) & ~1); // edge warps run the table-driven loop: shorter bands
-        const int64_t jb = std::min<int64_t>(j + h, g.shi);
+        const int64_t jb = std::min<int64_t>(j + h, end);
         (interior ? fast : slow).push_back(Item{s, (int)j, (int)jb});
         j = jb;
       }
+      if (end < g.shi) slow.push_back(Item{s, (int)end, (int)g.shi});
     }
     out = slow;
     out.insert(out.end(), fast.begin(), fast.end());
     // tiles that read no ghost row first (they overlap the halo exchange), tiles along the slab boundaries last
     const int lo = restrict_mode ? 5 : 3, hi = restrict_mode ? 3 : 1;
-    auto      nohalo = [&](const Item &it) { return !parallel || (it.ja - lo >= g.slo && it.jb + hi < g.shi); };
+    auto      nohalo = [&](const Item &it) { return !parallel || ((it.ja - lo >= g.slo || g.slo == 0) && (it.jb + hi < g.shi || g.shi == g.n1)); }; // rows beyond the GRID are not ghost rows
     std::stable_partition(out.begin(), out.end(), nohalo);
     int &cnt = restrict_mode ? nohalo2r : nohalo2;
     cnt      = 0;
@@ -1513,9 +1526,12 @@ struct LapOp final : GridOp {
       a1.nitems = nh;
       a2.items  = a.items + nh;
       a2.nitems = a.nitems - nh;
+      // the boundary tiles follow the exchange on the communication stream (thin bands: build_items2) beside the interior tiles on
+      // the compute stream, which then waits for both
+      kern<<<(unsigned)((a2.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->comm_stream>>>(a2);
+      PMG_CUDA(cudaEventRecord(ev_halo, ctx->comm_stream));
       PMG_CUDA(launch_pdl(ctx->stream, kern, dim3((unsigned)((a1.nitems + WARPS - 1) / WARPS)), dim3(WARPS * 32), sm, a1));
       PMG_TRY(halo_wait());
-      kern<<<(unsigned)((a2.nitems + WARPS - 1) / WARPS), WARPS * 32, sm, ctx->stream>>>(a2);
       ctx->launches++;
     } else {
       if (split_launch) PMG_TRY(halo_wait());
@@ -1614,7 +1630,7 @@ struct LapOp final : GridOp {
         const int         nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
         int by = rby_env > 0 ? rby_env : std::max<int>(4, (int)(((g.shi - g.slo) * nstrips + slots - 1) / std::max(1, slots)));
         by += by & 1;
-        while (build_items2(by, list, true) > slots && rby_env <= 0 && by < g.shi - g.slo) by += 2;
+        while (build_items2(by, list, true) > slots - (parallel ? 8 : 0) && rby_env <= 0 && by < g.shi - g.slo) by += 2;
         nitems2r = (int)list.size();
         PMG_TRY(items2r.upload(list, ctx->stream));
         PMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1636,7 +1652,7 @@ struct LapOp final : GridOp {
       const int         nstrips = (int)((g.n0 + STRIP_OUT - 1) / STRIP_OUT);
       int by = by_env > 0 ? by_env : std::max<int>(2, (int)(((g.shi - g.slo) * nstrips + slots - 1) / std::max(1, slots)));
       by += by & 1;
-      while (build_items2(by, list) > slots && by_env <= 0 && by < g.shi - g.slo) by += 2;
+      while (build_items2(by, list) > slots - (parallel ? 8 : 0) && by_env <= 0 && by < g.shi - g.slo) by += 2;
       nitems2 = (int)list.size();
       PMG_TRY(items2.upload(list, ctx->stream));
       PMG_CUDA(cudaStreamSynchronize(ctx->stream));
