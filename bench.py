@@ -401,10 +401,21 @@ def run_b200(args):
     # ---- multi-GPU correctness first: a number from a wrong distributed path is worth nothing ----
     parity = None
     if world > 1 and not args.no_parity_check:
-        parity = parity_check(pmg, ctx, rank, world, local)
-        flag = torch.tensor([0 if (parity is None or parity["ok"]) else 1], device="cuda")
-        dist.broadcast(flag, src=0)
-        if int(flag.item()):
+        def _checked():
+            p = parity_check(pmg, ctx, rank, world, local)
+            f = torch.tensor([0 if (p is None or p["ok"]) else 1], device="cuda")
+            dist.broadcast(f, src=0)
+            return p, int(f.item())
+        parity, bad = _checked()
+        if bad and "PMG_NO_OVERLAP_SWEEP" not in os.environ:
+            # the newest distributed path (boundary bands of the 2D sweeps on the communication stream) has a switch: measure without it
+            # rather than not at all, and say so in the line
+            first = parity
+            os.environ["PMG_NO_OVERLAP_SWEEP"] = "1"
+            parity, bad = _checked()
+            if rank == 0 and parity is not None:
+                parity["fallback"] = {"PMG_NO_OVERLAP_SWEEP": "1", "failed_with_overlap": first}
+        if bad:
             if rank == 0:
                 _emit({"metric": "mgmc_samples_per_s", "error": "multi-GPU parity check failed", "parity_check": parity})
             dist.destroy_process_group()
