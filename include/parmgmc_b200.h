@@ -188,6 +188,11 @@ int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int
  * on a 7-point grid operator): `count` items of five ints (strip of 120 columns, first row, first plane, end plane, narrow-strip flag).
  * Needs no device; the CPU tests check that the tiles cover the owned planes exactly once.  items = NULL only counts. */
 int pmg_plan_sweep3d(int64_t nx, int64_t ny, int64_t nz, int64_t slo, int64_t shi, int bz, int nw, int32_t *items, int64_t capacity, int64_t *count);
+/* the same for the fused 2D sweep (csrc/sweep2d.cuh): `count` items of three ints (strip of 120 columns, first row, end row) for the rows
+ * [slo, shi) of an nx x ny grid in bands of `by` rows (fused residual + restriction variant: restrict_mode = 1).  The first `nohalo` tiles read
+ * no ghost row; with overlap = 1 the others are 8-row bands next to the neighbouring slabs, which run behind the ghost exchange (the
+ * per-colour scatter of src/mc_sor.c:318-319 overlapped with the interior rows). */
+int pmg_plan_sweep2d(int64_t nx, int64_t ny, int64_t slo, int64_t shi, int by, int restrict_mode, int overlap, int32_t *items, int64_t capacity, int64_t *count, int64_t *nohalo);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------- */
 /* average device time [ms] and launch count of the kernels the last apply_richardson* call issued */

@@ -66,6 +66,7 @@ SIGNATURES = {
     "pmg_mat_create_laplace": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "pmg_mat_create_lrc": (C.c_int, [_vp, C.c_int, _f64p, _f64p, C.POINTER(_vp)]),
     "pmg_plan_sweep3d": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "pmg_plan_sweep2d": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pmg_pc_set_qoi": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int]),
     "pmg_pc_get_qoi": (C.c_int, [_vp, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "pmg_pc_get_mean_var": (C.c_int, [_vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
@@ -252,6 +253,16 @@ def plan_sweep3d(nx, ny, nz, slab=None, bz=64, nw=16):
     out = np.empty((cnt.value, 5), np.int32)
     _check(lib().pmg_plan_sweep3d(nx, ny, nz, slo, shi, bz, nw, out.ctypes.data, cnt.value, C.byref(cnt)))
     return out
+
+
+def plan_sweep2d(nx, ny, slab=None, by=64, restrict_mode=False, overlap=True):
+    """Work list of the fused 2D sweep as ((items, 3) int32 array: strip, first row, end row; number of leading tiles that read no ghost row)."""
+    slo, shi = slab if slab is not None else (0, ny)
+    cnt, nh = C.c_int64(), C.c_int64()
+    _check(lib().pmg_plan_sweep2d(nx, ny, slo, shi, by, int(restrict_mode), int(overlap), None, 0, C.byref(cnt), C.byref(nh)))
+    out = np.empty((cnt.value, 3), np.int32)
+    _check(lib().pmg_plan_sweep2d(nx, ny, slo, shi, by, int(restrict_mode), int(overlap), out.ctypes.data, cnt.value, C.byref(cnt), C.byref(nh)))
+    return out, nh.value
 
 
 def autocorrelation(ctx: "Context", x):

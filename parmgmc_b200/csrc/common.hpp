@@ -314,6 +314,7 @@ int device_iact(pmg_ctx ctx, int64_t n, const double *x_host, double *tau, doubl
 
 // work list of the fused 3D sweep (stencil_op.cu), host only
 void sweep3d_plan(int64_t n0, int64_t n1, int64_t n2, int64_t slo, int64_t shi, int bz, int nw, bool allow_narrow, int thin_planes, std::vector<int32_t> &out);
+void sweep2d_plan(int64_t n0, int64_t n1, int64_t slo, int64_t shi, bool parallel, int by, bool restrict_mode, bool thin_on, std::vector<int32_t> &out, int &nohalo_count);
 
 // grid transfer between level l (fine) and l-1 (coarse): SURVEY Appendix A.3
 struct Transfer {

@@ -1702,6 +1702,21 @@ int pmg_plan_sweep3d(int64_t nx, int64_t ny, int64_t nz, int64_t slo, int64_t sh
   return PMG_OK;
 }
 
+int pmg_plan_sweep2d(int64_t nx, int64_t ny, int64_t slo, int64_t shi, int by, int restrict_mode, int overlap, int32_t *items, int64_t capacity, int64_t *count, int64_t *nohalo)
+{
+  if (nx < 8 || ny < 4 || slo < 0 || shi > ny || slo >= shi || by < 2 || (by & 1) || !count) PMG_FAIL(PMG_ERR_ARG, "pmg_plan_sweep2d: bad geometry");
+  std::vector<int32_t> flat;
+  int                  nh = 0;
+  sweep2d_plan(nx, ny, slo, shi, slo > 0 || shi < ny, by, restrict_mode != 0, overlap != 0, flat, nh);
+  *count = (int64_t)(flat.size() / 3);
+  if (nohalo) *nohalo = nh;
+  if (items) {
+    if (capacity < *count) PMG_FAIL(PMG_ERR_ARG, "pmg_plan_sweep2d: %lld items, capacity %lld", (long long)*count, (long long)capacity);
+    std::memcpy(items, flat.data(), flat.size() * sizeof(int32_t));
+  }
+  return PMG_OK;
+}
+
 int pmg_normal_fill(pmg_ctx ctx, uint64_t seed, uint64_t call, int64_t row0, int64_t n, double *z)
 {
   pmg_stale("pmg_normal_fill");

@@ -36,6 +36,52 @@ int comm_halo_exchange(pmg_ctx ctx, const double *send_lo, double *recv_lo, cons
 int comm_allgather_i64(pmg_ctx ctx, const int64_t *local_host, int count, int64_t *all_host);
 int comm_allgatherv(pmg_ctx ctx, const double *send, double *recv, const int64_t *counts, const int64_t *displs, cudaStream_t stream);
 
+// Work list of the fused 2D sweep (sweep2d.cuh), host only (also exported as pmg_plan_sweep2d for the CPU tests): items of three
+// ints (strip of 120 output columns, first row, end row).  Bands of `by` rows (edge strips / bands at the grid boundary, which run the
+// table-driven loop, 3/4 of that).  On a slab with the overlapped exchange (`thin_on`) the rows next to a NEIGHBOUR are bands of 8
+// rows of their own: they are the only tiles that read ghost rows, and run on the communication stream right behind the exchange.
+// Order: tiles that read no ghost row first (`nohalo` of them), the others last; within each group edge tiles before interior tiles.
+void sweep2d_plan(int64_t n0, int64_t n1, int64_t slo, int64_t shi, bool parallel, int by, bool restrict_mode, bool thin_on, std::vector<int32_t> &out, int &nohalo_count)
+{
+  struct It { int32_t s, ja, jb; };
+  const int       nstrips = (int)((n0 + sweep2d::STRIP_OUT - 1) / sweep2d::STRIP_OUT);
+  std::vector<It> slow, fast;
+  const int64_t   thin = 8;
+  thin_on = thin_on && parallel && shi - slo >= 4 * thin;
+  for (int s = 0; s < nstrips; ++s) {
+    const int  c0 = s * sweep2d::STRIP_OUT - 4;
+    const bool edge_strip = !(c0 >= 1 && c0 + 127 <= n0 - 2);
+    int64_t    j = slo, end = shi;
+    if (thin_on && slo > 0) {
+      slow.push_back(It{s, (int32_t)j, (int32_t)(j + thin)});
+      j += thin;
+    }
+    if (thin_on && shi < n1) end = shi - thin;
+    while (j < end) {
+      const int64_t jb_full = std::min<int64_t>(j + by, end);
+      const int     lo = restrict_mode ? 4 : 2, hi = restrict_mode ? 2 : 0;
+      const bool    interior = !edge_strip && j - lo >= 1 && jb_full + hi <= n1 - 2 && j - lo - 1 >= slo && jb_full + hi + 2 < shi; // sweep2d_kernel's test
+      const int64_t h  = interior ? by : std::max(2, (by * 3 / 4) & ~1); // edge warps run the table-driven loop: shorter bands
+      const int64_t jb = std::min<int64_t>(j + h, end);
+      (interior ? fast : slow).push_back(It{s, (int32_t)j, (int32_t)jb});
+      j = jb;
+    }
+    if (end < shi) slow.push_back(It{s, (int32_t)end, (int32_t)shi});
+  }
+  std::vector<It> all = slow;
+  all.insert(all.end(), fast.begin(), fast.end());
+  // a tile reads ghost rows when it reaches within lo / hi rows of a slab end that has a neighbour (rows beyond the GRID are not ghost rows)
+  const int lo = restrict_mode ? 5 : 3, hi = restrict_mode ? 3 : 1;
+  auto      nohalo = [&](const It &it) { return !parallel || ((it.ja - lo >= slo || slo == 0) && (it.jb + hi < shi || shi == n1)); };
+  std::stable_partition(all.begin(), all.end(), nohalo);
+  nohalo_count = 0;
+  out.clear();
+  for (const auto &it : all) {
+    nohalo_count += nohalo(it) ? 1 : 0;
+    out.push_back(it.s); out.push_back(it.ja); out.push_back(it.jb);
+  }
+}
+
 // Work list of the fused 3D sweep (sweep3d.cuh), host only (also exported as pmg_plan_sweep3d for the CPU tests): items of
 // five ints (strip, ya, ka, kb, narrow).  Strips of 120 output columns; tiles of nw - 2 output rows (narrow last strip of at
 // most 56 columns: 2 nw - 2 rows, 16 lanes per grid row); bands along z: `thin` planes where a plane lacks a z neighbour (the
@@ -1466,42 +1512,12 @@ struct LapOp final : GridOp {
   int                   nitems2 = 0, items2_cfg = -1;
   int build_items2(int by, std::vector<sweep2d::Item> &out, bool restrict_mode = false) const
   {
-    using sweep2d::Item;
-    const int         nstrips = (int)((g.n0 + sweep2d::STRIP_OUT - 1) / sweep2d::STRIP_OUT);
-    std::vector<Item> slow, fast;
-    for (int s = 0; s < nstrips; ++s) {
-      const int  c0 = s * sweep2d::STRIP_OUT - 4;
-      const bool edge_strip = !(c0 >= 1 && c0 + 127 <= g.n0 - 2);
-      int64_t    j = g.slo, end = g.shi;
-      // overlapped exchange (start_halo): the rows that read ghost rows are THIN bands of their own, which run on the communication
-      // stream right behind the exchange while the compute stream sweeps everything else
-      const int64_t thin = 8;
-      const bool    thin_on = parallel && overlap_sweep_here() && overlap_on() && g.shi - g.slo >= 4 * thin;
-      if (thin_on && g.slo > 0) {
-        slow.push_back(Item{s, (int)j, (int)(j + thin)});
-        j += thin;
-      }
-      if (thin_on && g.shi < g.n1) end = g.shi - thin;
-      while (j < end) {
-        const int64_t jb_full = std::min<int64_t>(j + by, end);
-        const int     lo = restrict_mode ? 4 : 2, hi = restrict_mode ? 2 : 0;
-        const bool    interior = !edge_strip && j - lo >= 1 && jb_full + hi <= g.n1 - 2 && j - lo - 1 >= g.slo && jb_full + hi + 2 < g.shi; // sweep2d_kernel's test
-        const int64_t h  = interior ? by : std::max(2, (by * 3 / 4) & ~1); // edge warps run the table-driven loop: shorter bands
-        const int64_t jb = std::min<int64_t>(j + h, end);
-        (interior ? fast : slow).push_back(Item{s, (int)j, (int)jb});
-        j = jb;
-      }
-      if (end < g.shi) slow.push_back(Item{s, (int)end, (int)g.shi});
-    }
-    out = slow;
-    out.insert(out.end(), fast.begin(), fast.end());
-    // tiles that read no ghost row first (they overlap the halo exchange), tiles along the slab boundaries last
-    const int lo = restrict_mode ? 5 : 3, hi = restrict_mode ? 3 : 1;
-    auto      nohalo = [&](const Item &it) { return !parallel || ((it.ja - lo >= g.slo || g.slo == 0) && (it.jb + hi < g.shi || g.shi == g.n1)); }; // rows beyond the GRID are not ghost rows
-    std::stable_partition(out.begin(), out.end(), nohalo);
-    int &cnt = restrict_mode ? nohalo2r : nohalo2;
-    cnt      = 0;
-    for (const auto &it : out) cnt += nohalo(it) ? 1 : 0;
+    std::vector<int32_t> flat;
+    int                  nh = 0;
+    sweep2d_plan(g.n0, g.n1, g.slo, g.shi, parallel, by, restrict_mode, parallel && overlap_sweep_here() && overlap_on(), flat, nh);
+    out.resize(flat.size() / 3);
+    for (size_t q = 0; q < out.size(); ++q) out[q] = sweep2d::Item{flat[3 * q], flat[3 * q + 1], flat[3 * q + 2]};
+    (restrict_mode ? nohalo2r : nohalo2) = nh;
     return (int)out.size();
   }
   mutable int nohalo2 = 0, nohalo2r = 0;

@@ -165,3 +165,38 @@ def test_sass_backs_the_design_claims():
     assert count(r"box2d_kernel", r"\bUTMALDG") > 0 and count(r"box2d_kernel", r"\bACQBULK") > 0
     assert count(r"box3_sweep_smem_kernel", r"\bLDGSTS") > 0 and count(r"box3_sweep_smem_kernel", r"\bLDS\.128") > 0
     assert count(r"halo_kernel", r"\.SYS\b") > 0
+
+
+# ---- host logic of the fused 2D sweep on slabs: the work list with the thin boundary bands of the overlapped exchange -------------
+@pytest.mark.parametrize("restrict_mode", [False, True])
+@pytest.mark.parametrize("nx,ny,slab,by", [
+    (4097, 32769, (0, 4096), 82),          # first rank of the 8-GPU headline: a neighbour above only
+    (4097, 32769, (12288, 16384), 82),     # a middle rank: thin bands at both ends
+    (4097, 32769, (28672, 32769), 82),     # last rank (owns the closing row)
+    (129, 257, (96, 128), 4),              # bench.py's parity case on 8 ranks: 32-row slabs
+    (129, 257, (224, 257), 4),
+    (300, 140, (40, 70), 6),               # 30 rows: too short for thin bands
+    (4097, 4097, None, 82),                # one GPU
+])
+def test_sweep2d_work_list_tiles_the_slab_exactly_once(nx, ny, slab, by, restrict_mode):
+    import parmgmc_b200 as pmg
+    slo, shi = slab if slab else (0, ny)
+    for overlap in (True, False):
+        items, nohalo = pmg.plan_sweep2d(nx, ny, slab, by, restrict_mode, overlap)
+        nstrips = (nx + 119) // 120
+        cover = np.zeros((shi - slo, nstrips), np.int32)
+        for s, ja, jb in items:
+            assert 0 <= s < nstrips and slo <= ja < jb <= shi
+            cover[ja - slo:jb - slo, s] += 1
+        assert cover.min() == 1 and cover.max() == 1
+        lo, hi = (5, 3) if restrict_mode else (3, 1)
+        reads_ghost = [(ja - lo < slo and slo > 0) or (jb + hi >= shi and shi < ny) for _, ja, jb in items]
+        # the tiles that read no ghost row come first, and `nohalo` counts exactly them
+        assert not any(reads_ghost[:nohalo]) and all(reads_ghost[nohalo:])
+        if slab is None:
+            assert nohalo == len(items)
+        elif overlap and shi - slo >= 32:
+            # every tile that reads ghost rows is an 8-row band at a slab end that has a neighbour: one per strip and such end
+            ends = (1 if slo > 0 else 0) + (1 if shi < ny else 0)
+            assert len(items) - nohalo == ends * nstrips
+            assert all(jb - ja == 8 for (_, ja, jb), g in zip(items, reads_ghost) if g)
