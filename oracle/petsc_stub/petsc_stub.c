@@ -153,6 +153,16 @@ PetscErrorCode PetscOptionsRangeReal(const char *opt, const char *text, const ch
   if (set) *set = s ? PETSC_TRUE : PETSC_FALSE;
   return 0;
 }
+PetscErrorCode PetscOptionsString(const char *opt, const char *text, const char *man, const char *cur, char *v, size_t len, PetscBool *set)
+{
+  (void)text;
+  (void)man;
+  (void)cur;
+  const char *s = opt_find(opt);
+  if (s) snprintf(v, len, "%s", s);
+  if (set) *set = s ? PETSC_TRUE : PETSC_FALSE;
+  return 0;
+}
 PetscErrorCode PetscOptionsBool(const char *opt, const char *text, const char *man, PetscBool cur, PetscBool *v, PetscBool *set)
 {
   (void)text;

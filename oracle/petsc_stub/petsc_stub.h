@@ -159,6 +159,7 @@ PetscErrorCode PetscOptionsGetReal(PetscOptions o, const char *pre, const char *
 #define PetscOptionsHeadEnd() (void)0
 PetscErrorCode PetscOptionsRangeReal(const char *opt, const char *text, const char *man, PetscReal cur, PetscReal *v, PetscBool *set, PetscReal lo, PetscReal hi);
 PetscErrorCode PetscOptionsBool(const char *opt, const char *text, const char *man, PetscBool cur, PetscBool *v, PetscBool *set);
+PetscErrorCode PetscOptionsString(const char *opt, const char *text, const char *man, const char *cur, char *v, size_t len, PetscBool *set);
 
 /* ---- Vec ---- */
 struct _p_Vec {
@@ -392,6 +393,16 @@ PetscErrorCode PCSetOperators(PC pc, Mat A, Mat P);
 PetscErrorCode PCSetUp(PC pc);
 PetscErrorCode PCDestroy(PC *pc);
 PetscErrorCode PCStubDestroy(PC *pc);
+/* what src/woodbury.c needs of a PC used as a member object: the type-independent entry points, the options prefix (kept, not
+ * used for look-ups: the stub's options table is flat) and a built-in exact solver type "cholesky" / "lu" (dense LU of pmat) */
+PetscErrorCode PCApply(PC pc, Vec x, Vec y);
+PetscErrorCode PCApplyRichardson(PC pc, Vec b, Vec y, Vec w, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt its, PetscBool guesszero, PetscInt *outits, PCRichardsonConvergedReason *reason);
+PetscErrorCode PCSetFromOptions(PC pc);
+PetscErrorCode PCReset(PC pc);
+PetscErrorCode PCSetOptionsPrefix(PC pc, const char *prefix);
+PetscErrorCode PCAppendOptionsPrefix(PC pc, const char *prefix);
+PetscErrorCode PCGetOptionsPrefix(PC pc, const char **prefix);
+#define PetscObjectIncrementTabLevel(obj, parent, n) 0
 PetscErrorCode PetscViewerASCIIPrintf(PetscViewer v, const char *fmt, ...);
 
 /* ---- rank emulation: threads of one process ---- */

@@ -471,6 +471,7 @@ PetscErrorCode PetscOptionsInt(const char *opt, const char *text, const char *ma
 }
 
 /* ---- PC objects used as members of other PCs (pc_sorgibbs.c creates a PCPARSOR for MPIAIJ operators) ------------------------ */
+static void stub_direct_register(void);
 PetscErrorCode PCCreate(MPI_Comm comm, PC *pc)
 {
   *pc              = calloc(1, sizeof(**pc));
@@ -480,6 +481,7 @@ PetscErrorCode PCCreate(MPI_Comm comm, PC *pc)
 }
 PetscErrorCode PCSetType(PC pc, PCType type)
 {
+  stub_direct_register();
   Mat keep = pc->pmat;
   PC  made = NULL;
   Mat dummy;
@@ -492,7 +494,60 @@ PetscErrorCode PCSetType(PC pc, PCType type)
   free(made);
   return MatDestroy(&dummy);
 }
+/* built-in exact solver ("cholesky" / "lu" of PETSc proper): y = pmat^-1 x by the dense LU of KSPSolve */
+static PetscErrorCode PCApply_StubDirect(PC pc, Vec x, Vec y)
+{
+  KSP ksp;
+  PetscCall(KSPCreate(pc->hdr.comm, &ksp));
+  PetscCall(KSPSetOperators(ksp, pc->pmat, pc->pmat));
+  PetscCall(KSPSolve(ksp, x, y));
+  return KSPDestroy(&ksp);
+}
+static PetscErrorCode PCCreate_StubDirect(PC pc)
+{
+  pc->ops->apply = PCApply_StubDirect;
+  return 0;
+}
+static void stub_direct_register(void)
+{
+  static int done = 0;
+  if (done) return;
+  done = 1;
+  PCRegister("cholesky", PCCreate_StubDirect);
+  PCRegister("lu", PCCreate_StubDirect);
+}
 PetscErrorCode PCSetOperators(PC pc, Mat A, Mat P) { pc->mat = A; pc->pmat = P; return 0; }
+PetscErrorCode PCApply(PC pc, Vec x, Vec y)
+{
+  PetscCheck(pc->ops->apply, PETSC_COMM_SELF, PETSC_ERR_SUP, "PCApply: the PC type has no apply");
+  return pc->ops->apply(pc, x, y);
+}
+PetscErrorCode PCApplyRichardson(PC pc, Vec b, Vec y, Vec w, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt its, PetscBool guesszero, PetscInt *outits, PCRichardsonConvergedReason *reason)
+{
+  PetscCheck(pc->ops->applyrichardson, PETSC_COMM_SELF, PETSC_ERR_SUP, "PCApplyRichardson: the PC type has no applyrichardson");
+  return pc->ops->applyrichardson(pc, b, y, w, rtol, abstol, dtol, its, guesszero, outits, reason);
+}
+PetscErrorCode PCSetFromOptions(PC pc) { return pc->ops->setfromoptions ? pc->ops->setfromoptions(pc, NULL) : 0; }
+PetscErrorCode PCReset(PC pc) { return pc->ops->reset ? pc->ops->reset(pc) : 0; }
+PetscErrorCode PCSetOptionsPrefix(PC pc, const char *prefix)
+{
+  pc->hdr.prefix = prefix ? strdup(prefix) : NULL; /* a few bytes per PC, never freed: test infrastructure */
+  return 0;
+}
+PetscErrorCode PCAppendOptionsPrefix(PC pc, const char *prefix)
+{
+  const char *old = pc->hdr.prefix ? pc->hdr.prefix : "";
+  char       *s   = malloc(strlen(old) + strlen(prefix) + 1);
+  strcpy(s, old);
+  strcat(s, prefix);
+  pc->hdr.prefix = s;
+  return 0;
+}
+PetscErrorCode PCGetOptionsPrefix(PC pc, const char **prefix)
+{
+  *prefix = pc->hdr.prefix;
+  return 0;
+}
 PetscErrorCode PCSetUp(PC pc) { return pc->ops->setup ? pc->ops->setup(pc) : 0; }
 PetscErrorCode PCDestroy(PC *pc)
 {

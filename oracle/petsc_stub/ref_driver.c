@@ -27,7 +27,6 @@ const char *PetscStubLastError(void);
   }
 ABSENT_PC(PCCreate_GAMGMC)  /* wraps PETSc's PCMG / PCGAMG: nothing to run without PETSc */
 ABSENT_PC(PCCreate_PARSOR)  /* raw MPI point-to-point: out of scope */
-ABSENT_PC(PCCreate_Woodbury)
 PetscErrorCode PCPARSORApplySOR(PC pc, Vec b, PetscInt its, PetscBool zero, Vec y)
 {
   (void)pc; (void)b; (void)its; (void)zero; (void)y;

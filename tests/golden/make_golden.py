@@ -132,9 +132,23 @@ def main_round2():
     np.savez(os.path.join(HERE, "round2_pins.npz"), **out)
 
 
+def main_woodbury():
+    """src/woodbury.c compiled into the same library (late round 2): PCWOODBURY on the round-2 MATLRC operator with an exact solver
+    and the samplers mcgibbs (forward, omega = 1) / sorgibbs / cholsampler.  Stream per sample: a fill of k normals (the observation
+    noise comes first, src/woodbury.c:273), then the sampler's fill of n."""
+    out = {}
+    A, B, S, b, y0 = lrc_problem()
+    ns = orc.Noise.rander48(5150)
+    out["woodbury__z"] = np.concatenate([orc.noise_fill(ns, m) for _ in range(3) for m in (4, A.n)])
+    for sampler in ("mcgibbs", "sorgibbs", "cholsampler"):
+        out[f"woodbury_{sampler}__y"] = ref.sampler_run("woodbury", A, b, y0.copy(), 3, 5150, opts=(("-pc_woodbury_solver", "cholesky"), ("-pc_woodbury_sampler", sampler)), lrc=(B, S))
+    np.savez(os.path.join(HERE, "woodbury_pins.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
     main_round2()
+    main_woodbury()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

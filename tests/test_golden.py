@@ -299,3 +299,45 @@ def test_cuda_matlrc_paths_match_reference_output(pmg, ctx, orc):
     y = np.zeros(A.n)
     ch.apply_richardson(b, y, its=1)
     assert rel(y, R2["lrc_chol__y"]) < 1e-10
+
+
+# ---- late round 2: src/woodbury.c (tests/golden/woodbury_pins.npz, written by make_golden.main_woodbury from the reference's own
+#      woodbury.c compiled against the stub) -------------------------------------------------------------------------------------
+WB = np.load(os.path.join(HERE, "golden", "woodbury_pins.npz"))
+
+
+def _woodbury_restatement(orc, A, B, S, b, y0, sampler, its, z):
+    """PCApplyRichardson_Woodbury (src/woodbury.c:259-286) with G = C (S^-1 + B^T C)^-1, C = A^-1 B (:21-86, exact solver)."""
+    Ad = A.to_scipy().toarray()
+    Cm = np.linalg.solve(Ad, B)
+    G = Cm @ np.linalg.inv(np.diag(1.0 / S) + B.T @ Cm)
+    noise = orc.Noise.tape(z)
+    lflat = orc.potrf_lower(Ad) if sampler == "cholsampler" else None
+    y = y0.copy()
+    for _ in range(its):
+        w = b + B @ (np.sqrt(np.abs(S)) * orc.noise_fill(noise, B.shape[1]))
+        y = orc.chol_sample(lflat, A.n, noise, w) if sampler == "cholsampler" else orc.gibbs_richardson(A, w, y, 1, noise, None, 1.0, orc.SOR_FORWARD)
+        y = y - G @ (B.T @ y)
+    return y
+
+
+@pytest.mark.parametrize("sampler", ["mcgibbs", "sorgibbs", "cholsampler"])
+def test_oracle_woodbury_matches_reference_output(orc, sampler):
+    A, B, S, b, y0 = lrc_problem(orc)
+    assert rel(_woodbury_restatement(orc, A, B, S, b, y0, sampler, 3, WB["woodbury__z"]), WB[f"woodbury_{sampler}__y"]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler", ["mcgibbs", "sorgibbs", "cholsampler"])
+def test_cuda_woodbury_matches_reference_output(pmg, ctx, orc, sampler):
+    """The CUDA PCWOODBURY against what the reference's own woodbury.c produced (one colour = the reference's 1-rank ordering)."""
+    A, B, S, b, y0 = lrc_problem(orc)
+    mat = pmg.Mat.lrc(device_mat(pmg, ctx, orc, A, "single", (13, 11)), B, S)
+    pc = pmg.PC(ctx, "woodbury")
+    pc.set_operator(mat)
+    pc.set_options({"-pc_woodbury_sampler": sampler, "-pc_woodbury_solver": "cholesky"})
+    pc.setup()
+    pc.set_noise_tape(WB["woodbury__z"])
+    y = y0.copy()
+    pc.apply_richardson(b, y, its=3)
+    assert rel(y, WB[f"woodbury_{sampler}__y"]) < 1e-9

@@ -255,3 +255,45 @@ def test_cholsampler_on_matlrc():
     P = A.to_scipy().toarray() + B @ np.diag(S) @ B.T
     y = orc.chol_sample(orc.potrf_lower(P), A.n, orc.Noise.rander48(77), b)
     assert rel(y, y_ref) < 1e-11
+
+
+# ---- PCWOODBURY: the reference's own src/woodbury.c compiled into oracle/_ref (stub additions: PCApply / PCApplyRichardson /
+# ---- PCSetFromOptions / prefix functions on member PCs, a built-in exact "cholesky" solver type) ------------------------------
+@pytest.mark.parametrize("sampler,its", [("mcgibbs", 1), ("mcgibbs", 3), ("sorgibbs", 2), ("cholsampler", 2)])
+def test_woodbury_sampler_matches_the_restatement(sampler, its):
+    """PCSetUp_Woodbury + PCWoodburyBuildLRCCorrection (src/woodbury.c:21-86, :141-186: C = solver(B) column by column,
+    G = C (S^-1 + B^T C)^-1) and PCApplyRichardson_Woodbury (:259-286): per sample the k normals of the observation noise are
+    drawn FIRST, w = b + B (sqrt|S| . eta), one Richardson step of the sampler on A with right-hand side w, then
+    y -= G (B^T y).  The restatement below is the one tests/test_gpu_parity.py holds the CUDA path against."""
+    rng = np.random.default_rng(SEED + 21)
+    A, B, S = _lrc_problem(rng, (9, 8) if sampler == "cholsampler" else (13, 11), 3)
+    n, k = A.n, B.shape[1]
+    b, y0 = rng.standard_normal(n), rng.standard_normal(n)
+    seen_ref = []
+    y_ref = ref.sampler_run("woodbury", A, b, y0.copy(), its, 5150, opts=[("-pc_woodbury_solver", "cholesky"), ("-pc_woodbury_sampler", sampler)], lrc=(B, S),
+                            callback=lambda it, y: seen_ref.append(y.copy()))
+    Ad = A.to_scipy().toarray()
+    Cm = np.linalg.solve(Ad, B)
+    G = Cm @ np.linalg.inv(np.diag(1.0 / S) + B.T @ Cm)
+    noise = orc.Noise.rander48(5150)
+    lflat = orc.potrf_lower(Ad) if sampler == "cholsampler" else None
+    y, seen = y0.copy(), []
+    for _ in range(its):
+        w = b + B @ (np.sqrt(np.abs(S)) * orc.noise_fill(noise, k))
+        if sampler == "cholsampler":
+            y = orc.chol_sample(lflat, n, noise, w)  # an exact sampler ignores the previous state
+        else:
+            y = orc.gibbs_richardson(A, w, y, 1, noise, None, 1.0, orc.SOR_FORWARD)
+        y = y - G @ (B.T @ y)
+        seen.append(y.copy())
+    assert rel(y, y_ref) < 1e-10
+    assert len(seen_ref) == its and all(rel(a, r) < 1e-10 for a, r in zip(seen, seen_ref))
+
+
+def test_woodbury_needs_a_matlrc_operator_and_both_members():
+    """src/woodbury.c:149, :159: without solver / sampler, or on a plain AIJ operator, set-up fails."""
+    A = orc.laplace(2, 5, 5, kappa=1.0)
+    with pytest.raises(RuntimeError, match="sampler and solver"):
+        ref.sampler_run("woodbury", A, np.ones(A.n), np.zeros(A.n), 1, 1, lrc=(np.ones((A.n, 1)), np.ones(1)))
+    with pytest.raises(RuntimeError, match="LRC"):
+        ref.sampler_run("woodbury", A, np.ones(A.n), np.zeros(A.n), 1, 1, opts=[("-pc_woodbury_solver", "cholesky"), ("-pc_woodbury_sampler", "sorgibbs")])
