@@ -405,6 +405,23 @@ PetscErrorCode PCGetOptionsPrefix(PC pc, const char **prefix);
 #define PetscObjectIncrementTabLevel(obj, parent, n) 0
 PetscErrorCode PetscViewerASCIIPrintf(PetscViewer v, const char *fmt, ...);
 
+/* ---- DMDA: just enough for src/problems.c (a one-rank 2D grid; the Mat is a dense mx my x mx my matrix, row = j mx + i) ---- */
+typedef struct _p_DM *DM;
+struct _p_DM {
+  PetscInt mx, my;
+};
+typedef struct {
+  PetscInt k, j, i, c;
+} MatStencil;
+typedef enum { MAT_FLUSH_ASSEMBLY = 1, MAT_FINAL_ASSEMBLY = 0 } MatAssemblyType;
+PetscErrorCode DMStubCreate2d(PetscInt mx, PetscInt my, DM *dm);
+PetscErrorCode DMDestroy(DM *dm);
+PetscErrorCode DMDAGetInfo(DM dm, PetscInt *dim, PetscInt *M, PetscInt *N, PetscInt *P, PetscInt *m, PetscInt *n, PetscInt *p, PetscInt *dof, PetscInt *s, void *bx, void *by, void *bz, void *st);
+PetscErrorCode DMDAGetCorners(DM dm, PetscInt *xs, PetscInt *ys, PetscInt *zs, PetscInt *xm, PetscInt *ym, PetscInt *zm);
+PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil *rows, PetscInt n, const MatStencil *cols, const PetscScalar *v, InsertMode mode);
+PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t);
+PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t);
+
 /* ---- rank emulation: threads of one process ---- */
 void PetscStubWorldBegin(int nranks);          /* called once before the rank threads start */
 void PetscStubWorldEnd(void);

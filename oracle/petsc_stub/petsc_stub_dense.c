@@ -643,3 +643,48 @@ void fftw_execute(const fftw_plan p)
   memcpy(p->out, w, sizeof(fftw_complex) * (size_t)n);
   free(w);
 }
+
+
+/* ---- DMDA for src/problems.c: one rank, 2D; the operator is assembled into a dense matrix (row = j mx + i) ------------------ */
+static PetscInt g_dmda_mx = 0;
+PetscErrorCode DMStubCreate2d(PetscInt mx, PetscInt my, DM *dm)
+{
+  *dm       = calloc(1, sizeof(**dm));
+  (*dm)->mx = mx;
+  (*dm)->my = my;
+  g_dmda_mx = mx;
+  return 0;
+}
+PetscErrorCode DMDestroy(DM *dm) { free(*dm); *dm = NULL; return 0; }
+PetscErrorCode DMDAGetInfo(DM dm, PetscInt *dim, PetscInt *M, PetscInt *N, PetscInt *P, PetscInt *m, PetscInt *n, PetscInt *p, PetscInt *dof, PetscInt *s, void *bx, void *by, void *bz, void *st)
+{
+  (void)m; (void)n; (void)p; (void)dof; (void)s; (void)bx; (void)by; (void)bz; (void)st;
+  if (dim) *dim = 2;
+  if (M) *M = dm->mx;
+  if (N) *N = dm->my;
+  if (P) *P = 1;
+  return 0;
+}
+PetscErrorCode DMDAGetCorners(DM dm, PetscInt *xs, PetscInt *ys, PetscInt *zs, PetscInt *xm, PetscInt *ym, PetscInt *zm)
+{
+  if (xs) *xs = 0;
+  if (ys) *ys = 0;
+  if (zs) *zs = 0;
+  if (xm) *xm = dm->mx;
+  if (ym) *ym = dm->my;
+  if (zm) *zm = 1;
+  return 0;
+}
+PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil *rows, PetscInt n, const MatStencil *cols, const PetscScalar *v, InsertMode mode)
+{
+  PetscCheck(is_dense(A) && g_dmda_mx > 0, PETSC_COMM_SELF, PETSC_ERR_SUP, "MatSetValuesStencil: dense matrix of a stub DMDA only");
+  for (PetscInt r = 0; r < m; ++r)
+    for (PetscInt c = 0; c < n; ++c) {
+      const PetscInt R = rows[r].j * g_dmda_mx + rows[r].i, Cc = cols[c].j * g_dmda_mx + cols[c].i;
+      double        *e = A->d + R + (size_t)Cc * (size_t)A->m;
+      *e               = mode == ADD_VALUES ? *e + v[r * n + c] : v[r * n + c];
+    }
+  return 0;
+}
+PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t) { (void)A; (void)t; return 0; }
+PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t) { (void)A; (void)t; return 0; }

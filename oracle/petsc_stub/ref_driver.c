@@ -379,3 +379,19 @@ int ref_cov_errors(int n, const int *rowptr, const int *col, const double *val, 
   PetscStubWorldEnd();
   return 0;
 }
+
+
+/* src/problems.c MatAssembleShiftedLaplaceFD on an mx x my grid (one rank): dense column-major result, n = mx my */
+#include "parmgmc/problems.h"
+int ref_assemble_laplace2d(int mx, int my, double kappa, double *dense_colmajor)
+{
+  DM  dm;
+  Mat A;
+  PetscCall(DMStubCreate2d(mx, my, &dm));
+  PetscCall(MatCreateSeqDense(MPI_COMM_SELF, mx * my, mx * my, NULL, &A)); /* the stub's dense Mat owns (zeroed) storage */
+  PetscCall(MatAssembleShiftedLaplaceFD(dm, kappa, A));
+  memcpy(dense_colmajor, A->d, sizeof(double) * (size_t)mx * my * mx * my);
+  PetscCall(MatDestroy(&A));
+  PetscCall(DMDestroy(&dm));
+  return 0;
+}

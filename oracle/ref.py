@@ -129,6 +129,17 @@ def sampler_run(pctype, A, b, y, its, seed, coloring=None, opts=(), lrc=None, ca
     return y
 
 
+def assemble_laplace2d(mx, my, kappa):
+    """MatAssembleShiftedLaplaceFD (src/problems.c:14-75) on an mx x my DMDA, one rank: the dense (mx my) x (mx my) operator."""
+    n = mx * my
+    d = np.zeros(n * n, np.float64)
+    f = lib().ref_assemble_laplace2d
+    f.argtypes = [C.c_int, C.c_int, C.c_double, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
+    f.restype = C.c_int
+    _check(f(mx, my, float(kappa), d))
+    return d.reshape(n, n).T.copy()  # column-major -> [row, col]
+
+
 def mcsor_apply_lrc(A, B, S, b, y, coloring=None, omega=1.0, sweep=1, nsweeps=1):
     """MCSORCreate / SetUp / Apply on the MATLRC operator A + B diag(S) B^T: the sweep on A followed by MCSORPostSOR_LRC with the
     correction MCSORBuildLRCCorrection built at set-up (src/mc_sor.c:101-112, :480-544, :565-595)."""

@@ -297,3 +297,15 @@ def test_woodbury_needs_a_matlrc_operator_and_both_members():
         ref.sampler_run("woodbury", A, np.ones(A.n), np.zeros(A.n), 1, 1, lrc=(np.ones((A.n, 1)), np.ones(1)))
     with pytest.raises(RuntimeError, match="LRC"):
         ref.sampler_run("woodbury", A, np.ones(A.n), np.zeros(A.n), 1, 1, opts=[("-pc_woodbury_solver", "cholesky"), ("-pc_woodbury_sampler", "sorgibbs")])
+
+
+@pytest.mark.parametrize("mx,my,kappa", [(5, 5, 1.0), (9, 6, 2.5), (17, 33, 0.3), (2, 7, 1.0)])
+def test_operator_assembly_matches_problems_c(mx, my, kappa):
+    """MatAssembleShiftedLaplaceFD (src/problems.c:14-75): off-diagonals -h with h = 1 / (mx - 1)^2 (the reference's `hinv2`, in both
+    directions), diagonal kappa^2 plus h once per existing neighbour, added in the order south, west, north, east.  The oracle's
+    operator (and with it every matrix the parity tests hand to both sides) must equal it entry for entry, bit for bit."""
+    ref_dense = ref.assemble_laplace2d(mx, my, kappa)
+    A = orc.laplace(2, mx, my, kappa=kappa)
+    mine = A.to_scipy().toarray()
+    assert np.array_equal(mine, ref_dense)
+    assert np.array_equal(mine != 0, ref_dense != 0)
